@@ -1,0 +1,207 @@
+"""f110-mpc on B200 — Python harness over the C ABI (include/f110_mpc_b200.h).
+
+The product is the CUDA library `libf110mpc_b200.so` (hand-written sm_100a kernels behind a C ABI) and the
+C++ host classes in `host/`.  This module is only the ctypes binding used by tests/ and bench.py; torch is
+used for device buffers, streams and torch.distributed — plumbing, not compute.  There is no CPU fallback:
+loading fails loudly if the CUDA library is missing, and every compute call fails without a CUDA device.
+
+Import with `importlib.import_module("f110-mpc_b200")` (the directory name is not a Python identifier).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libf110mpc_b200.so")
+
+SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED = 1, 2, -2
+PRIMAL_INFEASIBLE, DUAL_INFEASIBLE = -3, -4
+
+
+class MpcConfig(C.Structure):
+    """f110_mpc_config"""
+    _fields_ = [("horizon", C.c_int32), ("gap_mode", C.c_int32), ("dt", C.c_double), ("wheelbase", C.c_double),
+                ("q", C.c_double * 3), ("r", C.c_double * 2), ("u_des", C.c_double * 2), ("u_min", C.c_double * 2),
+                ("u_max", C.c_double * 2)]
+
+
+class SolverSettings(C.Structure):
+    """f110_solver_settings"""
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("eps_abs", C.c_double),
+                ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+                ("adaptive_rho_tolerance", C.c_double), ("max_iter", C.c_int32), ("check_termination", C.c_int32),
+                ("scaling", C.c_int32), ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+                ("warm_start", C.c_int32), ("scaled_termination", C.c_int32), ("reserved", C.c_int32)]
+
+
+EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
+           "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
+           "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
+           "f110_mpc_last_launches", "f110_collision_check_device", "f110_collision_check_host"]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    srcs += [os.path.join(_HERE, "Makefile"), os.path.join(_HERE, "..", "include", "f110_mpc_b200.h")]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+        if verbose or out.returncode:
+            print(out.stdout + out.stderr)
+        if out.returncode:
+            raise RuntimeError("nvcc build of libf110mpc_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (raises if it is not built — no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libf110mpc_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.f110_last_error.restype = C.c_char_p
+        L.f110_mpc_default_config.argtypes = [C.POINTER(MpcConfig)]
+        L.f110_solver_default_settings.argtypes = [C.POINTER(SolverSettings)]
+        L.f110_mpc_create.argtypes = [C.POINTER(MpcConfig), C.POINTER(SolverSettings), C.c_int, C.c_int, C.POINTER(vp)]
+        L.f110_mpc_destroy.argtypes = [vp]
+        L.f110_mpc_reset.argtypes = [vp]
+        L.f110_mpc_last_launches.argtypes = [vp]
+        L.f110_mpc_solve_host.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip]
+        L.f110_mpc_solve_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.f110_collision_check_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 9
+        L.f110_collision_check_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 8 + [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc:
+        raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, lib().f110_last_error().decode()))
+
+
+def default_config(horizon=30, gap_mode=0):
+    c = MpcConfig()
+    lib().f110_mpc_default_config(C.byref(c))
+    c.horizon = horizon
+    c.gap_mode = gap_mode
+    return c
+
+
+def default_settings(**kw):
+    s = SolverSettings()
+    lib().f110_solver_default_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise KeyError(k)
+        setattr(s, k, v)
+    return s
+
+
+def record_doubles(N):
+    return 11 + 3 * N
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def _tp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class MpcSolver:
+    """One handle per GPU (f110_mpc_create).  `solve_host` is the reference-facing call (host buffers in,
+    host buffers out); `solve_device` takes torch CUDA tensors and is stream-ordered."""
+
+    def __init__(self, config=None, settings=None, max_batch=4096, device=0):
+        self.config = config or default_config()
+        self.settings = settings or default_settings()
+        self.N = self.config.horizon
+        self.n = 5 * self.N + 3
+        self.m = 7 * self.N + 5
+        self.max_batch = max_batch
+        self.device = device
+        self._h = C.c_void_p()
+        _check(lib().f110_mpc_create(C.byref(self.config), C.byref(self.settings), max_batch, device, C.byref(self._h)),
+               "f110_mpc_create")
+
+    def solve_host(self, recs, want_xy=True):
+        recs = np.ascontiguousarray(recs, dtype=np.float64)
+        B = recs.shape[0]
+        x = np.empty((B, self.n)) if want_xy else None
+        y = np.empty((B, self.m)) if want_xy else None
+        u0 = np.empty((B, 2))
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        _check(lib().f110_mpc_solve_host(self._h, B, _dp(recs), recs.shape[1], _dp(x), _dp(y), _dp(u0), _ip(status),
+                                         _ip(iters)), "f110_mpc_solve_host")
+        return dict(x=x, y=y, u0=u0, status=status, iters=iters)
+
+    def solve_device(self, recs, x=None, y=None, u0=None, status=None, iters=None, rho_updates=None, info=None,
+                     stream=None, count=None):
+        """recs etc. are torch CUDA tensors (float64 / int32, contiguous)."""
+        B = recs.shape[0] if count is None else count
+        sp = C.c_void_p(stream) if stream else None
+        _check(lib().f110_mpc_solve_device(self._h, B, _tp(recs), recs.stride(0), _tp(x), _tp(y), _tp(u0), _tp(status),
+                                           _tp(iters), _tp(rho_updates), _tp(info), sp), "f110_mpc_solve_device")
+
+    def reset(self):
+        _check(lib().f110_mpc_reset(self._h), "f110_mpc_reset")
+
+    @property
+    def last_launches(self):
+        return lib().f110_mpc_last_launches(self._h)
+
+    def close(self):
+        if self._h:
+            lib().f110_mpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def collision_check_host(grid, offset, rot, pose_xy, table_xy, blocks=100, discrete=0.1, device=0):
+    """grid (S, blocks*blocks) f32 col-major cells; offset (S,2) f32; rot (S,4) f64; pose_xy (S,2) f64;
+    table_xy (P, samples, 2) f64.  Returns valid (S,P) u8, free_count (S,P) i32, end_world (S,P,2) f32."""
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    offset = np.ascontiguousarray(offset, dtype=np.float32)
+    rot = np.ascontiguousarray(rot, dtype=np.float64)
+    pose_xy = np.ascontiguousarray(pose_xy, dtype=np.float64)
+    table_xy = np.ascontiguousarray(table_xy, dtype=np.float64)
+    S = grid.shape[0]
+    P, samples = table_xy.shape[0], table_xy.shape[1]
+    valid = np.empty((S, P), dtype=np.uint8)
+    free = np.empty((S, P), dtype=np.int32)
+    endw = np.empty((S, P, 2), dtype=np.float32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    _check(lib().f110_collision_check_host(S, P, samples, blocks, discrete, vp(grid), vp(offset), vp(rot), vp(pose_xy),
+                                           vp(table_xy), vp(valid), vp(free), vp(endw), device),
+           "f110_collision_check_host")
+    return valid, free, endw
+
+
+def collision_check_device(grid, offset, rot, pose_xy, table_xy, valid, free_count, end_world, blocks=100, discrete=0.1,
+                           stream=None):
+    """torch CUDA tensors, stream-ordered."""
+    S = grid.shape[0]
+    P, samples = table_xy.shape[0], table_xy.shape[1]
+    sp = C.c_void_p(stream) if stream else None
+    _check(lib().f110_collision_check_device(S, P, samples, blocks, discrete, _tp(grid), _tp(offset), _tp(rot),
+                                             _tp(pose_xy), _tp(table_xy), _tp(valid), _tp(free_count), _tp(end_world),
+                                             sp), "f110_collision_check_device")

@@ -1,0 +1,39 @@
+// Kernel parameter block + launch entry of the batched ADMM solve (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace f110 {
+
+struct KParams {
+  // problem family (f110_mpc_config)
+  int N, B, stride, gap_mode;
+  double dt, wheelbase;
+  double Q[3], R[2], u_des[2], u_min[2], u_max[2];
+  // OSQP settings (f110_solver_settings)
+  double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+  int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval, warm_start;
+  // buffers (device)
+  const double* recs;
+  double* x_out;      // [B][5N+3] or null
+  double* y_out;      // [B][7N+5] or null
+  double* u0_out;     // [B][2] or null
+  int32_t* status;    // [B] or null
+  int32_t* iters;     // [B] or null
+  int32_t* rho_updates;  // [B] or null
+  double* info;       // [B][4] or null
+  double* state;      // [B][state_doubles(N)] warm-start slots (scaled iterates x, z, y + rho + flag) or null
+};
+
+// doubles per warm-start slot: x(5N+3) + z(7N+5) + y(7N+5) + rho + valid flag
+__host__ __device__ inline int state_doubles(int N) { return (5 * N + 3) + 2 * (7 * N + 5) + 2; }
+
+// Launch the solve for p.B QPs on `stream`. Returns the cudaError of the launch.
+cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches);
+
+cudaError_t launch_collision(int scenes, int paths, int samples, int blocks, float discrete, const float* grid,
+                             const float* offset, const double* rot, const double* pose_xy,
+                             const double* table_xy, uint8_t* valid, int32_t* free_count, float* end_world,
+                             cudaStream_t stream);
+
+}  // namespace f110

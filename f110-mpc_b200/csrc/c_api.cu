@@ -1,0 +1,241 @@
+// C ABI (include/f110_mpc_b200.h) over the CUDA kernels.  No CPU fallback: every compute entry needs a
+// CUDA device and fails with F110_ERR_CUDA otherwise.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/f110_mpc_b200.h"
+#include "admm_kernel.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(F110_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr)                                    \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+  } while (0)
+}  // namespace
+
+struct f110_mpc_solver {
+  f110_mpc_config cfg;
+  f110_solver_settings st;
+  int max_batch = 0;
+  int device = 0;
+  int last_launches = 0;
+  double* d_state = nullptr;  // warm-start slots
+  // staging for the host-buffer entry
+  double* d_recs = nullptr;
+  double* d_x = nullptr;
+  double* d_y = nullptr;
+  double* d_u0 = nullptr;
+  int32_t* d_status = nullptr;
+  int32_t* d_iters = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+const char* f110_last_error(void) { return g_err.c_str(); }
+
+int f110_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void f110_mpc_default_config(f110_mpc_config* c) {
+  // params.yaml values with the reference's C++ destination types
+  c->horizon = 30;
+  c->gap_mode = 0;
+  c->dt = (double)0.01f;            // float dt_ (mpc.h:48) widened at mpc.cpp:73
+  c->wheelbase = (double)0.3302f;   // model.cpp:32
+  c->q[0] = 10.0; c->q[1] = 10.0; c->q[2] = 0.0;
+  c->r[0] = 0.10; c->r[1] = 5.0;
+  c->u_des[0] = 4.5; c->u_des[1] = 0.0;
+  c->u_min[0] = (double)3.0f; c->u_min[1] = (double)-0.43f;  // constraints.cpp:20-21
+  c->u_max[0] = (double)4.5f; c->u_max[1] = (double)0.43f;   // constraints.cpp:18-19
+}
+
+void f110_solver_default_settings(f110_solver_settings* s) {
+  // OSQP v0.6.x defaults; the reference overrides only warm_start (mpc.cpp:98)
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 4000; s->check_termination = 25; s->scaling = 10;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 25;
+  s->warm_start = 1; s->scaled_termination = 0; s->reserved = 0;
+}
+
+int f110_mpc_record_doubles(int N) { return 11 + 3 * N; }
+int f110_mpc_num_variables(int N) { return 5 * N + 3; }
+int f110_mpc_num_constraints(int N) { return 7 * N + 5; }
+
+int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, int max_batch, int device,
+                    f110_mpc_solver** out) {
+  if (!cfg || !st || !out || max_batch <= 0) return fail(F110_ERR_ARG, "f110_mpc_create: null argument or max_batch <= 0");
+  if (cfg->horizon < 1 || cfg->horizon > F110_MAX_HORIZON) return fail(F110_ERR_ARG, "f110_mpc_create: horizon out of range");
+  if (cfg->horizon > 31) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: horizons above 31 are not built yet");
+  if (st->scaled_termination) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: scaled_termination = 1 is not supported");
+  if (st->max_iter < 1 || st->check_termination < 0 || st->scaling < 0) return fail(F110_ERR_ARG, "f110_mpc_create: bad settings");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(F110_ERR_CUDA, "f110_mpc_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(F110_ERR_ARG, "f110_mpc_create: bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  f110_mpc_solver* s = new f110_mpc_solver();
+  s->cfg = *cfg;
+  s->st = *st;
+  if (s->st.adaptive_rho_interval == 0) s->st.adaptive_rho_interval = 25;  // OSQP's timing-based choice, fixed
+  s->max_batch = max_batch;
+  s->device = device;
+  const int N = cfg->horizon;
+  const size_t ssz = (size_t)max_batch * f110::state_doubles(N) * sizeof(double);
+  e = cudaMalloc(&s->d_state, ssz);
+  if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    f110_mpc_destroy(s);
+    return cuda_fail(e, "f110_mpc_create: device allocation");
+  }
+  *out = s;
+  return F110_OK;
+}
+
+void f110_mpc_destroy(f110_mpc_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_state);
+  cudaFree(s->d_recs); cudaFree(s->d_x); cudaFree(s->d_y); cudaFree(s->d_u0);
+  cudaFree(s->d_status); cudaFree(s->d_iters);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int f110_mpc_reset(f110_mpc_solver* s) {
+  if (!s) return fail(F110_ERR_ARG, "f110_mpc_reset: null solver");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemset(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon) * sizeof(double)));
+  return F110_OK;
+}
+
+int f110_mpc_last_launches(const f110_mpc_solver* s) { return s ? s->last_launches : 0; }
+
+int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
+                          double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
+                          void* cuda_stream) {
+  if (!s || !d_recs) return fail(F110_ERR_ARG, "f110_mpc_solve_device: null solver or records");
+  if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_device: count exceeds max_batch");
+  if (rec_stride < f110_mpc_record_doubles(s->cfg.horizon)) return fail(F110_ERR_ARG, "f110_mpc_solve_device: record stride too small");
+  s->last_launches = 0;
+  if (count == 0) return F110_OK;
+  f110::KParams p;
+  p.N = s->cfg.horizon; p.B = count; p.stride = rec_stride; p.gap_mode = s->cfg.gap_mode;
+  p.dt = s->cfg.dt; p.wheelbase = s->cfg.wheelbase;
+  for (int i = 0; i < 3; ++i) p.Q[i] = s->cfg.q[i];
+  for (int i = 0; i < 2; ++i) { p.R[i] = s->cfg.r[i]; p.u_des[i] = s->cfg.u_des[i]; p.u_min[i] = s->cfg.u_min[i]; p.u_max[i] = s->cfg.u_max[i]; }
+  p.rho0 = s->st.rho; p.sigma = s->st.sigma; p.alpha = s->st.alpha; p.eps_abs = s->st.eps_abs; p.eps_rel = s->st.eps_rel;
+  p.eps_prim_inf = s->st.eps_prim_inf; p.eps_dual_inf = s->st.eps_dual_inf; p.adaptive_rho_tolerance = s->st.adaptive_rho_tolerance;
+  p.max_iter = s->st.max_iter; p.check_termination = s->st.check_termination; p.scaling = s->st.scaling;
+  p.adaptive_rho = s->st.adaptive_rho; p.adaptive_rho_interval = s->st.adaptive_rho_interval; p.warm_start = s->st.warm_start;
+  p.recs = d_recs; p.x_out = d_x; p.y_out = d_y; p.u0_out = d_u0; p.status = d_status; p.iters = d_iters;
+  p.rho_updates = d_rho_updates; p.info = d_info;
+  p.state = s->st.warm_start ? s->d_state : nullptr;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &s->last_launches);
+  if (e != cudaSuccess) return cuda_fail(e, "admm kernel launch");
+  return F110_OK;
+}
+
+int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int rec_stride, double* x, double* y, double* u0,
+                        int32_t* status, int32_t* iters) {
+  if (!s || !recs) return fail(F110_ERR_ARG, "f110_mpc_solve_host: null solver or records");
+  if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_host: count exceeds max_batch");
+  if (count == 0) return F110_OK;
+  const int N = s->cfg.horizon, n = 5 * N + 3, m = 7 * N + 5;
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->d_recs) {
+    const size_t B = s->max_batch;
+    CUDA_TRY(cudaMalloc(&s->d_recs, B * f110_mpc_record_doubles(N) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_x, B * n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_y, B * m * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_u0, B * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_status, B * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_iters, B * sizeof(int32_t)));
+  }
+  const int rd = f110_mpc_record_doubles(N);
+  if (rec_stride < rd) return fail(F110_ERR_ARG, "f110_mpc_solve_host: record stride too small");
+  CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rd * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
+                             cudaMemcpyHostToDevice, s->stream));
+  int rc = f110_mpc_solve_device(s, count, s->d_recs, rd, x ? s->d_x : nullptr, y ? s->d_y : nullptr, s->d_u0, s->d_status,
+                                 s->d_iters, nullptr, nullptr, s->stream);
+  if (rc) return rc;
+  if (x) CUDA_TRY(cudaMemcpyAsync(x, s->d_x, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (y) CUDA_TRY(cudaMemcpyAsync(y, s->d_y, (size_t)count * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (u0) CUDA_TRY(cudaMemcpyAsync(u0, s->d_u0, (size_t)count * 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, s->d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (iters) CUDA_TRY(cudaMemcpyAsync(iters, s->d_iters, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return F110_OK;
+}
+
+int f110_collision_check_device(int scenes, int paths, int samples, int blocks, float discrete, const float* d_grid,
+                                const float* d_offset, const double* d_rot, const double* d_pose_xy, const double* d_table_xy,
+                                uint8_t* d_valid, int32_t* d_free_count, float* d_end_world, void* cuda_stream) {
+  if (scenes < 0 || paths <= 0 || samples <= 0 || blocks <= 0) return fail(F110_ERR_ARG, "f110_collision_check: bad sizes");
+  if (!d_grid || !d_offset || !d_rot || !d_pose_xy || !d_table_xy || !d_valid || !d_free_count || !d_end_world)
+    return fail(F110_ERR_ARG, "f110_collision_check: null buffer");
+  cudaError_t e = f110::launch_collision(scenes, paths, samples, blocks, discrete, d_grid, d_offset, d_rot, d_pose_xy, d_table_xy,
+                                         d_valid, d_free_count, d_end_world, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "collision kernel launch");
+  return F110_OK;
+}
+
+int f110_collision_check_host(int scenes, int paths, int samples, int blocks, float discrete, const float* grid, const float* offset,
+                              const double* rot, const double* pose_xy, const double* table_xy, uint8_t* valid,
+                              int32_t* free_count, float* end_world, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(F110_ERR_CUDA, "f110_collision_check_host: no CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t gsz = (size_t)scenes * blocks * blocks * sizeof(float);
+  const size_t np = (size_t)scenes * paths;
+  float *d_grid = nullptr, *d_off = nullptr, *d_end = nullptr;
+  double *d_rot = nullptr, *d_pose = nullptr, *d_tab = nullptr;
+  uint8_t* d_valid = nullptr;
+  int32_t* d_free = nullptr;
+  int rc = F110_OK;
+  cudaError_t e = cudaSuccess;
+  auto T = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  T(cudaMalloc(&d_grid, gsz)); T(cudaMalloc(&d_off, scenes * 2 * sizeof(float))); T(cudaMalloc(&d_rot, scenes * 4 * sizeof(double)));
+  T(cudaMalloc(&d_pose, scenes * 2 * sizeof(double))); T(cudaMalloc(&d_tab, (size_t)paths * samples * 2 * sizeof(double)));
+  T(cudaMalloc(&d_valid, np)); T(cudaMalloc(&d_free, np * sizeof(int32_t))); T(cudaMalloc(&d_end, np * 2 * sizeof(float)));
+  if (e == cudaSuccess) {
+    T(cudaMemcpy(d_grid, grid, gsz, cudaMemcpyHostToDevice));
+    T(cudaMemcpy(d_off, offset, scenes * 2 * sizeof(float), cudaMemcpyHostToDevice));
+    T(cudaMemcpy(d_rot, rot, scenes * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    T(cudaMemcpy(d_pose, pose_xy, scenes * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    T(cudaMemcpy(d_tab, table_xy, (size_t)paths * samples * 2 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (e == cudaSuccess) {
+    rc = f110_collision_check_device(scenes, paths, samples, blocks, discrete, d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free,
+                                     d_end, nullptr);
+    if (rc == F110_OK) {
+      T(cudaMemcpy(valid, d_valid, np, cudaMemcpyDeviceToHost));
+      T(cudaMemcpy(free_count, d_free, np * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      T(cudaMemcpy(end_world, d_end, np * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+  }
+  cudaFree(d_grid); cudaFree(d_off); cudaFree(d_rot); cudaFree(d_pose); cudaFree(d_tab); cudaFree(d_valid); cudaFree(d_free); cudaFree(d_end);
+  if (rc != F110_OK) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "f110_collision_check_host");
+  return F110_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+/* f110_mpc_b200.h — C ABI of the B200-native batched per-cycle MPC solve.
+ *
+ * Drop-in boundary for the OSQP call inside the reference's MPC::Update
+ * (reference src/mpc.cpp:81-142, the only user of the OsqpEigen::Solver member declared at
+ * include/f110-mpc/mpc.h:63) and for the mini-path collision check of OdomCallback
+ * (reference src/project.cpp:76-113).  Plain pointers and sizes only; no torch / Eigen / ROS
+ * types.  All entry points return 0 on success, non-zero on an API error
+ * (f110_last_error() gives the text).  There is NO CPU fallback behind this ABI: without a
+ * CUDA device every compute entry fails with F110_ERR_CUDA.
+ *
+ * The QP is never shipped as CSC matrices.  One QP = one parameter record of
+ * f110_mpc_record_doubles(N) doubles — exactly what MPC::Update receives per cycle
+ * (mpc.cpp:69-80):
+ *     x0[3]      current state (x, y, ori)                      mpc.cpp:71
+ *     u_lin[2]   linearisation input (v, steer)                 mpc.cpp:73  -> model.cpp:30-59
+ *     l1[3]      half-plane line 1 (a, b, c+0.5)                mpc.cpp:75  -> constraints.cpp:255-260
+ *     l2[3]      half-plane line 2                              constraints.cpp:262-264
+ *     ref[3*N]   desired states 0..N-1 (x, y, ori)              mpc.cpp:72, 221-229
+ * The kernel linearises the kinematic bicycle (model.cpp:30-59), stacks the horizon
+ * (mpc.cpp:208-306) and runs the OSQP ADMM iteration with a structure-exploiting KKT solve.
+ *
+ * Solution layout = the reference's (mpc.cpp:26-29):
+ *     x[5N+3]  = [x_0(3) ... x_N(3) | u_0(2) ... u_{N-1}(2)]
+ *     y[7N+5]  = [dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N]
+ */
+#ifndef F110_MPC_B200_H
+#define F110_MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F110_OK 0
+#define F110_ERR_ARG 1
+#define F110_ERR_CUDA 2
+#define F110_ERR_UNSUPPORTED 3
+
+/* Per-QP status codes: OSQP's status_val (what OsqpEigen::Solver::solve() tests, mpc.cpp:133). */
+#define F110_SOLVED 1
+#define F110_SOLVED_INACCURATE 2
+#define F110_PRIMAL_INFEASIBLE_INACCURATE 3
+#define F110_DUAL_INFEASIBLE_INACCURATE 4
+#define F110_MAX_ITER_REACHED (-2)
+#define F110_PRIMAL_INFEASIBLE (-3)
+#define F110_DUAL_INFEASIBLE (-4)
+#define F110_NON_CVX (-7)
+#define F110_UNSOLVED (-10)
+
+#define F110_MAX_HORIZON 127
+
+/* What MPC::MPC reads from the parameter server (mpc.cpp:3-24) plus Constraints' input box
+ * (constraints.cpp:18-21) and Model's wheelbase (model.cpp:32). */
+typedef struct f110_mpc_config {
+  int32_t horizon;   /* params.yaml:12 */
+  int32_t gap_mode;  /* 0 = as shipped: gap rows bounded by (-INFTY, +INFTY) (mpc.cpp:297-298);
+                        1 = lower bound -l(2) restored (the commented code on those lines) */
+  double dt;         /* (double)0.01f — MPC::dt_ is a float (mpc.h:48) */
+  double wheelbase;  /* (double)0.3302f (model.cpp:32) */
+  double q[3];       /* state weights  q0 q1 q2 (params.yaml:1-3) */
+  double r[2];       /* input weights  r0 r1    (params.yaml:5-6) */
+  double u_des[2];   /* des_vel, des_steer      (params.yaml:42-43) */
+  double u_min[2];   /* umin, -0.43f            (constraints.cpp:20-21) */
+  double u_max[2];   /* umax, +0.43f            (constraints.cpp:18-19) */
+} f110_mpc_config;
+
+/* The OSQP settings the reference leaves at their defaults (it only sets warm start + verbosity,
+ * mpc.cpp:98-99), exported as knobs. */
+typedef struct f110_solver_settings {
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  double adaptive_rho_tolerance;
+  int32_t max_iter, check_termination, scaling;
+  int32_t adaptive_rho, adaptive_rho_interval; /* interval 0 (OSQP's timing-based choice) is mapped to 25 */
+  int32_t warm_start;                          /* 1: iterates and rho persist per QP slot between solves */
+  int32_t scaled_termination;                  /* must be 0 (OSQP default) */
+  int32_t reserved;
+} f110_solver_settings;
+
+typedef struct f110_mpc_solver f110_mpc_solver; /* opaque; owns device scratch only */
+
+void f110_mpc_default_config(f110_mpc_config* cfg);
+void f110_solver_default_settings(f110_solver_settings* s);
+int f110_mpc_record_doubles(int horizon); /* 11 + 3N */
+int f110_mpc_num_variables(int horizon);  /* 5N + 3  (mpc.cpp:26-28) */
+int f110_mpc_num_constraints(int horizon);/* 7N + 5  (mpc.cpp:29) */
+const char* f110_last_error(void);
+int f110_device_count(void);
+
+/* replaces: OsqpEigen::Solver construction + settings()/data()/initSolver() (mpc.cpp:98-129). */
+int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* settings, int max_batch,
+                    int device, f110_mpc_solver** out);
+void f110_mpc_destroy(f110_mpc_solver* s);
+
+/* replaces: updateGradient / updateLinearConstraintsMatrix / updateBounds / solve / getSolution
+ * (mpc.cpp:83-94, 133, 140) for `count` independent QPs.  HOST buffers; the call copies the
+ * records to the device, solves, copies results back and synchronises.  Any output may be NULL.
+ *   recs        count x f110_mpc_record_doubles(N), row stride `rec_stride` doubles
+ *   x, y        primal / dual (reference layout); NaN-filled for infeasible QPs like OSQP
+ *   u0          count x 2, first applied control (mpc.cpp:145-159 -> project.cpp:190-191)
+ *   status      per-QP OSQP status_val;  iters  per-QP ADMM iterations */
+int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int rec_stride, double* x,
+                        double* y, double* u0, int32_t* status, int32_t* iters);
+
+/* Same, DEVICE buffers, stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream),
+ * no synchronisation.  info: count x 4 = objective, primal residual, dual residual, rho at exit. */
+int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x,
+                          double* d_y, double* d_u0, int32_t* d_status, int32_t* d_iters,
+                          int32_t* d_rho_updates, double* d_info, void* cuda_stream);
+
+/* Forget the warm-start state of every slot (next solve starts from x = z = y = 0, rho = settings.rho). */
+int f110_mpc_reset(f110_mpc_solver* s);
+/* Number of kernels the last solve call launched (for launch accounting). */
+int f110_mpc_last_launches(const f110_mpc_solver* s);
+
+/* ---- mini-path collision check (project.cpp:76-113 with occupancy_grid.cpp:27-33, 90-101, 165-168
+ * and transforms.cpp:13-19).  Bit-exact integer/float contract; the tf2 rotation is an explicit input.
+ *   grid        scenes x blocks*blocks floats, Eigen column-major: cell(row, col) at row + col*blocks
+ *   offset      scenes x 2 floats   (OccGrid::occ_offset_)
+ *   rot         scenes x 4 doubles  (R00 R01 R10 R11 of the car->world basis)
+ *   pose_xy     scenes x 2 doubles  (pose.position.x, .y)
+ *   table_xy    paths x samples x 2 doubles (mini-path table, base_link; shared by all scenes)
+ * outputs (scenes x paths): valid (1 = every sample in-grid and free), free_count,
+ *   end_world (x, y floats; the world end point of valid paths, project.cpp:108-111). */
+int f110_collision_check_device(int scenes, int paths, int samples, int blocks, float discrete,
+                                const float* d_grid, const float* d_offset, const double* d_rot,
+                                const double* d_pose_xy, const double* d_table_xy, uint8_t* d_valid,
+                                int32_t* d_free_count, float* d_end_world, void* cuda_stream);
+int f110_collision_check_host(int scenes, int paths, int samples, int blocks, float discrete, const float* grid,
+                              const float* offset, const double* rot, const double* pose_xy,
+                              const double* table_xy, uint8_t* valid, int32_t* free_count, float* end_world,
+                              int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F110_MPC_B200_H */
