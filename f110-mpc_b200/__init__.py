@@ -39,7 +39,7 @@ class SolverSettings(C.Structure):
 EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
            "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
-           "f110_mpc_last_launches", "f110_collision_check_device", "f110_collision_check_host"]
+           "f110_mpc_last_launches", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma"]
 
 
 def build(force=False, verbose=False):
@@ -78,6 +78,7 @@ def lib():
         L.f110_mpc_solve_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.f110_collision_check_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 9
         L.f110_collision_check_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 8 + [C.c_int]
+        L.f110_bench_fp64_fma.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -137,14 +138,16 @@ class MpcSolver:
         _check(lib().f110_mpc_create(C.byref(self.config), C.byref(self.settings), max_batch, device, C.byref(self._h)),
                "f110_mpc_create")
 
-    def solve_host(self, recs, want_xy=True):
+    def solve_host(self, recs, want_xy=True, out=None):
+        """`out` may carry preallocated (e.g. pinned) u0/status/iters/x/y arrays."""
         recs = np.ascontiguousarray(recs, dtype=np.float64)
         B = recs.shape[0]
-        x = np.empty((B, self.n)) if want_xy else None
-        y = np.empty((B, self.m)) if want_xy else None
-        u0 = np.empty((B, 2))
-        status = np.empty(B, dtype=np.int32)
-        iters = np.empty(B, dtype=np.int32)
+        out = out or {}
+        x = out.get("x", np.empty((B, self.n)) if want_xy else None)
+        y = out.get("y", np.empty((B, self.m)) if want_xy else None)
+        u0 = out.get("u0", np.empty((B, 2)))
+        status = out.get("status", np.empty(B, dtype=np.int32))
+        iters = out.get("iters", np.empty(B, dtype=np.int32))
         _check(lib().f110_mpc_solve_host(self._h, B, _dp(recs), recs.shape[1], _dp(x), _dp(y), _dp(u0), _ip(status),
                                          _ip(iters)), "f110_mpc_solve_host")
         return dict(x=x, y=y, u0=u0, status=status, iters=iters)
@@ -174,6 +177,12 @@ class MpcSolver:
             self.close()
         except Exception:
             pass
+
+
+def fp64_fma_peak_tflops(device=0, iters=20000):
+    t = C.c_double()
+    _check(lib().f110_bench_fp64_fma(device, iters, C.byref(t)), "f110_bench_fp64_fma")
+    return t.value
 
 
 def collision_check_host(grid, offset, rot, pose_xy, table_xy, blocks=100, discrete=0.1, device=0):

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
   const int k = lane;
   const bool act = k <= N;   // lane owns a stage
   const bool actu = k < N;   // stage has an input (and box rows, and a successor)
+  const bool hasp = act && k > 0;  // stage has a predecessor (lanes above N must stay identically zero)
   const int nvar = 5 * N + 3;
   int nlev = 0;
   while ((1 << nlev) <= N && nlev < MAX_LEVELS) ++nlev;
@@ -250,6 +251,16 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) tb[j] = eb[j] * du[j];
+    if (!act) {  // lanes above N: keep D = E = 1
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { tx[j] = 1.0; td[j] = 1.0; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { tg[j] = 1.0; }
+    }
+    if (!actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { tu[j] = 1.0; tb[j] = 1.0; }
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) dx[j] *= rsqrt(limit_scaling(tx[j]));
 #pragma unroll
@@ -402,7 +413,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
 #pragma unroll
     for (int e = 0; e < 9; ++e) {
       const double t = __shfl_up_sync(FULL, Rn[e], 1);
-      Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : t;
+      Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? t : 0.0);
     }
     double Bm[9], Lm[9], Um[9];
     {
@@ -432,9 +443,9 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const double r0 = Rt[3 * i], r1 = Rt[3 * i + 1], r2 = Rt[3 * i + 2];
-        Lm[3 * i + 0] = (k > 0) ? -r0 : 0.0;
-        Lm[3 * i + 1] = (k > 0) ? -r1 : 0.0;
-        Lm[3 * i + 2] = (k > 0) ? -(r0 * md.a02 + r1 * md.a12 + r2) : 0.0;
+        Lm[3 * i + 0] = hasp ? -r0 : 0.0;
+        Lm[3 * i + 1] = hasp ? -r1 : 0.0;
+        Lm[3 * i + 2] = hasp ? -(r0 * md.a02 + r1 * md.a12 + r2) : 0.0;
       }
       if (!act) {
 #pragma unroll
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const double fp = __shfl_up_sync(FULL, f[i], 1);
-      r[i] = gx[i] - t3[i] + ((k > 0) ? fp : 0.0);
+      r[i] = gx[i] - t3[i] + (hasp ? fp : 0.0);
     }
     // PCR: apply the stored multipliers level by level
     for (int lev = 0; lev < nlev; ++lev) {
@@ -564,7 +575,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
     for (int i = 0; i < 3; ++i) {
       pred[i] += axt[i];
       const double pp = __shfl_up_sync(FULL, pred[i], 1);
-      ztd[i] = ((k > 0) ? pp : 0.0) - xt[i];
+      ztd[i] = (hasp ? pp : 0.0) - xt[i];
     }
     const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
     const double al = p.alpha, oma = 1.0 - p.alpha;
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
     for (int i = 0; i < 3; ++i) {
       pred[i] += ax[i];
       const double pp = __shfl_up_sync(FULL, pred[i], 1);
-      Axd[i] = ((k > 0) ? pp : 0.0) - s.x[i];
+      Axd[i] = (hasp ? pp : 0.0) - s.x[i];
     }
     const double Axg[2] = {s.gm[0] * s.x[0] + s.gm[1] * s.x[1] + s.gm[2] * s.x[2], s.gm[3] * s.x[0] + s.gm[4] * s.x[1] + s.gm[5] * s.x[2]};
     // A' y, P x
@@ -754,7 +765,7 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
     for (int i = 0; i < 3; ++i) {
       pred[i] += ax[i];
       const double pp = __shfl_up_sync(FULL, pred[i], 1);
-      const double a = ((k > 0) ? pp : 0.0) - ddx[i];
+      const double a = (hasp ? pp : 0.0) - ddx[i];
       const double sb_ = edv[i] * s.bd[i];
       if (act && ((sb_ < INF_THRESH && a > th) || (sb_ > -INF_THRESH && a < -th))) bad = true;
     }
@@ -807,6 +818,21 @@ __global__ void __launch_bounds__(32 * WARPS) admm_kernel(const KParams p) {
       }
     }
     iterate();
+#ifdef F110_DEBUG_NAN
+    {
+      int code = 0;
+      for (int j = 0; j < 3; ++j) { if (!isfinite(s.x[j])) code |= 1; if (!isfinite(s.zd[j])) code |= 4; if (!isfinite(s.yd[j])) code |= 32; }
+      for (int j = 0; j < 2; ++j) { if (!isfinite(s.u[j])) code |= 2; if (!isfinite(s.zg[j])) code |= 8; if (!isfinite(s.zb[j])) code |= 16; if (!isfinite(s.yg[j])) code |= 64; if (!isfinite(s.yb[j])) code |= 128; }
+      unsigned bal = __ballot_sync(FULL, code != 0);
+      if (bal) {
+        int first = __ffs(bal) - 1;
+        int c0 = __shfl_sync(FULL, code, first);
+        if (lane == 0 && p.info) { double* io = p.info + 4 * (size_t)qp; io[0] = iter; io[1] = first; io[2] = c0; io[3] = (double)bal; }
+        if (p.status && lane == 0) p.status[qp] = -99;
+        return;
+      }
+    }
+#endif
     can_check = chk;
     if (chk) {
       update_info();

@@ -83,3 +83,70 @@ def tracking_batch(B, N=30, seed=20240905, gaps=False, table=None):
         r[:, :2] = ref
         recs[b, 11:] = r.reshape(-1)
     return recs
+
+
+# ---- scenes for the mini-path collision check ---------------------------------
+def golden_dir():
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def reference_data():
+    """Fixtures derived from the reference's csv/ files (scripts/make_golden.py)."""
+    import os
+    return np.load(os.path.join(golden_dir(), "reference_data.npz"))
+
+
+def skirk_waypoints():
+    """Trajectory::ReadCSV (trajectory.cpp:18-55): float x, y and heading atan2f from the previous point."""
+    xy = reference_data()["skirk_xy"].astype(np.float32)
+    prev = np.roll(xy, 1, axis=0)
+    # `temp[(i-1)%temp.size()]` with a 32-bit unsigned i (trajectory.cpp:40-43): at i = 0 the index is
+    # (2^32 - 1) % size, not size - 1
+    prev[0] = xy[(2 ** 32 - 1) % len(xy)]
+    ori = np.arctan2((xy[:, 1] - prev[:, 1]).astype(np.float32), (xy[:, 0] - prev[:, 0]).astype(np.float32)).astype(np.float32)
+    return xy, ori
+
+
+SCAN_BEAMS = 1080
+SCAN_ANGLE_MIN = float(np.float32(-2.35))
+SCAN_ANGLE_INC = float(np.float32(4.7 / 1079))
+SCAN_ANGLE_MAX = float(np.float32(np.float32(-2.35) + np.float32(1079) * np.float32(4.7 / 1079)))
+
+
+def render_scan(x, y, yaw, boxes, max_range=10.0):
+    """Ray-cast axis-aligned boxes (cx, cy, half) into a 1080-beam scan taken from the car pose."""
+    ang = SCAN_ANGLE_MIN + np.arange(SCAN_BEAMS) * SCAN_ANGLE_INC + yaw
+    dx, dy = np.cos(ang), np.sin(ang)
+    r = np.full(SCAN_BEAMS, max_range)
+    for (cx, cy, h) in boxes:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tx1, tx2 = (cx - h - x) / dx, (cx + h - x) / dx
+            ty1, ty2 = (cy - h - y) / dy, (cy + h - y) / dy
+        tmin = np.maximum(np.minimum(tx1, tx2), np.minimum(ty1, ty2))
+        tmax = np.minimum(np.maximum(tx1, tx2), np.maximum(ty1, ty2))
+        hit = (tmax >= tmin) & (tmax > 0) & (tmin > 0)
+        r = np.where(hit & (tmin < r), tmin, r)
+    return r.astype(np.float32)
+
+
+def scene_batch(S, seed=20240902):
+    """S scenes: pose = a skirk waypoint, 1-3 box obstacles 0.3-0.6 m wide 0.8-2.0 m ahead.
+    Returns poses (S,7), yaw (S,), scans (S,1080) float32."""
+    rng = np.random.default_rng(seed)
+    xy, ori = skirk_waypoints()
+    poses = np.zeros((S, 7))
+    yaws = np.zeros(S)
+    scans = np.zeros((S, SCAN_BEAMS), dtype=np.float32)
+    for s in range(S):
+        i = rng.integers(0, len(xy))
+        x, y, yaw = float(xy[i, 0]), float(xy[i, 1]), float(ori[i])
+        boxes = []
+        for _ in range(rng.integers(1, 4)):
+            d = rng.uniform(0.8, 2.0)
+            lat = rng.uniform(-0.8, 0.8)
+            boxes.append((x + d * np.cos(yaw) - lat * np.sin(yaw), y + d * np.sin(yaw) + lat * np.cos(yaw), rng.uniform(0.15, 0.3)))
+        poses[s] = yaw_pose(x, y, yaw)
+        yaws[s] = yaw
+        scans[s] = render_scan(x, y, yaw, boxes)
+    return poses, yaws, scans

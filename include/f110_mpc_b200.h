@@ -132,6 +132,10 @@ int f110_collision_check_host(int scenes, int paths, int samples, int blocks, fl
                               const double* table_xy, uint8_t* valid, int32_t* free_count, float* end_world,
                               int device);
 
+/* ---- measurement utility (not on the solve path): FP64 FMA issue rate of `device` in TFLOP/s, the
+ * roofline denominator for the ADMM kernel. */
+int f110_bench_fp64_fma(int device, int iters, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

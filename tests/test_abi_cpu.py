@@ -1,0 +1,60 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/f110_mpc_b200.h
+declares; without a CUDA device the compute entries fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "f110_mpc_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(f110_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points(pkg):
+    syms = declared_symbols()
+    assert set(syms) == set(pkg.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    pkg.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    for s in declared_symbols():
+        assert s in exported, s
+    L = ctypes.CDLL(pkg.LIB_PATH)        # loads without a GPU
+    for s in declared_symbols():
+        assert hasattr(L, s)
+
+
+def test_helpers_and_defaults(pkg):
+    L = pkg.lib()
+    assert L.f110_mpc_record_doubles(30) == 101 and L.f110_mpc_num_variables(30) == 153 and L.f110_mpc_num_constraints(30) == 215
+    c = pkg.default_config()
+    assert c.horizon == 30 and c.dt == pytest.approx(0.009999999776482582, abs=0) and c.wheelbase == pytest.approx(0.3301999866962433, abs=0)
+    assert list(c.q) == [10.0, 10.0, 0.0] and list(c.r) == [0.1, 5.0] and c.u_max[1] == pytest.approx(0.4300000071525574, abs=0)
+    s = pkg.default_settings()
+    assert (s.rho, s.sigma, s.alpha, s.eps_abs, s.max_iter, s.check_termination, s.scaling) == (0.1, 1e-6, 1.6, 1e-3, 4000, 25, 10)
+
+
+def test_no_cpu_fallback(pkg):
+    if pkg.lib().f110_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pkg.MpcSolver(max_batch=4)
+
+
+def test_product_does_not_touch_oracle():
+    # the oracle is test infrastructure: nothing under the package may import, link or load it
+    pk = os.path.join(ROOT, "f110-mpc_b200")
+    for dp, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "liboracle" not in txt and "oracle_py" not in txt and "osqp_restated" not in txt, f

@@ -1,0 +1,178 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): primal and dual within eps_abs = eps_rel = 1e-4 of the oracle,
+first applied control within 1e-3 relative (absolute floor 0.05 on the steering, whose set-point is 0);
+collision-check outputs bit-exact.  PARITY UNPINNED by the reference (it has no tests)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_ABS = TOL_REL = 1e-4
+
+
+def assert_solution_parity(g, o, N):
+    np.testing.assert_array_equal(g["status"], o["status"])
+    ok = o["status"] > 0
+    np.testing.assert_allclose(g["x"][ok], o["x"][ok], atol=TOL_ABS, rtol=TOL_REL)
+    np.testing.assert_allclose(g["y"][ok], o["y"][ok], atol=TOL_ABS, rtol=TOL_REL)
+    assert np.isnan(g["x"][~ok]).all() and np.isnan(g["y"][~ok]).all()     # OSQP NaN-fills infeasible solutions
+    u0g, u0o = g["x"][ok][:, 3 * (N + 1):3 * (N + 1) + 2], o["x"][ok][:, 3 * (N + 1):3 * (N + 1) + 2]
+    floor = np.array([0.0, 0.05])
+    assert (np.abs(u0g - u0o) <= 1e-3 * np.maximum(np.abs(u0o), floor)).all()
+    np.testing.assert_array_equal(g["u0"][ok], u0g)
+
+
+@pytest.mark.parametrize("N", [1, 5, 10, 20, 30, 31])
+@pytest.mark.parametrize("eps", [1e-3, 1e-4])
+def test_cold_batch_matches_oracle(pkg, oracle, workloads, N, eps):
+    B = 192
+    recs = workloads.tracking_batch(B, N, seed=100 + N)
+    g = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])        # same algorithm -> same iteration counts
+
+
+def test_gap_enabled_mode_including_infeasible(pkg, oracle, workloads):
+    N, B, eps = 30, 256, 1e-4
+    recs = workloads.tracking_batch(B, N, gaps=True)
+    g = pkg.MpcSolver(pkg.default_config(N, 1), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N, 1), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    assert (o["status"] == oracle.PRIMAL_INFEASIBLE).any() and (o["status"] == oracle.SOLVED).any()
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])
+
+
+def test_tight_tolerance_solutions_agree(pkg, oracle, workloads):
+    # at eps 1e-6 both sides sit on the (unique) solution; iteration counts may differ by one check period
+    N, B, eps = 30, 128, 1e-6
+    recs = workloads.tracking_batch(B, N, seed=77)
+    g = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    np.testing.assert_allclose(g["x"], o["x"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(g["y"], o["y"], atol=1e-5, rtol=1e-6)
+    assert np.abs(g["iters"] - o["iters"]).max() <= 25
+
+
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(GOLD) if f.startswith("qp_")))
+def test_golden_vectors(pkg, name):
+    gd = np.load(os.path.join(GOLD, name))
+    N, gap_mode, eps = int(gd["N"]), int(gd["gap_mode"]), float(gd["eps"])
+    B = gd["recs"].shape[0]
+    g = pkg.MpcSolver(pkg.default_config(N, gap_mode), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(gd["recs"])
+    assert_solution_parity(g, dict(status=gd["status"], x=gd["x"], y=gd["y"]), N)
+    np.testing.assert_array_equal(g["iters"], gd["iters"])
+
+
+def test_warm_start_sequence_matches_oracle(pkg, oracle, workloads):
+    # reference steady state: update q / A / bounds, keep iterates and rho (mpc.cpp:83-94, 98)
+    N, B = 30, 64
+    recs = workloads.tracking_batch(B, N, seed=9)
+    sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=1), B)
+    mb = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=1), B)
+    for step in range(4):
+        g = sol.solve_host(recs)
+        o = mb.solve(recs, warm=True)
+        assert_solution_parity(g, o, N)
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        u0 = o["x"][:, 3 * (N + 1):3 * (N + 1) + 2]
+        recs = recs.copy()
+        recs[:, 0] += 0.01 * u0[:, 0] * np.cos(recs[:, 2])       # roll the car forward one step
+        recs[:, 1] += 0.01 * u0[:, 0] * np.sin(recs[:, 2])
+        recs[:, 4] = u0[:, 1]
+    sol.reset()
+    g = sol.solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=0), B).solve(recs)
+    assert_solution_parity(g, o, N)
+
+
+def test_full_size_batch_kkt_properties(pkg, oracle, workloads):
+    # BASELINE size (4096 QPs): size-independent properties — KKT residuals of every returned (x, y)
+    N, B = 30, 4096
+    recs = workloads.tracking_batch(B, N, seed=4096)
+    g = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=1e-5, eps_rel=1e-5, warm_start=0), B).solve_host(recs)
+    assert (g["status"] == pkg.SOLVED).all()
+    cfg = oracle.default_cfg(N)
+    P, q, A, l, u = oracle.mpc_assemble_dense(cfg, recs[0])
+    eps = 1e-5
+    for b in range(0, B, 37):
+        P, q, A, l, u = oracle.mpc_assemble_dense(cfg, recs[b])
+        x, y = g["x"][b], g["y"][b]
+        Ax = A @ x
+        # OSQP's own stopping rule, evaluated independently (z = projection of Ax gives the smallest residual)
+        dua = np.abs(P @ x + q + A.T @ y).max()
+        pri = np.abs(Ax - np.clip(Ax, l, u)).max()
+        assert dua <= eps + eps * max(np.abs(P @ x).max(), np.abs(A.T @ y).max(), np.abs(q).max())
+        assert pri <= eps + eps * np.abs(Ax).max()
+    # all inputs inside the box, x0 pinned
+    u_all = g["x"][:, 3 * (N + 1):].reshape(B, N, 2)
+    assert (u_all[..., 0] >= 3 - 1e-4).all() and (u_all[..., 0] <= 4.5 + 1e-4).all() and (np.abs(u_all[..., 1]) <= 0.43 + 1e-4).all()
+    np.testing.assert_allclose(g["x"][:, :3], recs[:, :3], atol=1e-4)
+
+
+def test_api_errors(pkg):
+    sol = pkg.MpcSolver(max_batch=8)
+    with pytest.raises(RuntimeError, match="exceeds max_batch"):
+        sol.solve_host(np.zeros((9, 101)))
+    with pytest.raises(RuntimeError):
+        pkg.MpcSolver(pkg.default_config(200), max_batch=8)
+    assert sol.solve_host(np.zeros((0, 101)))["status"].shape == (0,)
+
+
+# ---- collision check: bit-exact ------------------------------------------------------------------------------
+def _scene_inputs(oracle, workloads, S, seed):
+    poses, yaws, scans = workloads.scene_batch(S, seed)
+    grids = np.zeros((S, 100 * 100), dtype=np.float32)
+    offs = np.zeros((S, 2), dtype=np.float32)
+    rots = np.zeros((S, 4))
+    for s in range(S):
+        grids[s], offs[s], _ = oracle.fill_grid(poses[s], workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC, scans[s])
+        rots[s] = oracle.car_to_world_R(poses[s])
+    return poses, grids, offs, rots
+
+
+@pytest.mark.parametrize("table_kind", ["steer19", "steer30", "csv10"])
+def test_collision_check_bit_exact(pkg, oracle, workloads, table_kind):
+    S = 96
+    poses, grids, offs, rots = _scene_inputs(oracle, workloads, S, 20240902)
+    if table_kind == "csv10":
+        table = workloads.reference_data()["local_traj10_xy"]
+    else:
+        table = oracle.traj_table(steer_discrete=19 if table_kind == "steer19" else 30)[:, :, :2]
+    table = np.ascontiguousarray(table)
+    valid, free, endw = pkg.collision_check_host(grids, offs, rots, poses[:, :2], table)
+    n_valid = 0
+    for s in range(S):
+        v, f, e = oracle.collision_check(grids[s], 100, 0.1, offs[s], rots[s], poses[s, :2], table)
+        np.testing.assert_array_equal(valid[s], v)
+        np.testing.assert_array_equal(free[s], f)
+        np.testing.assert_array_equal(endw[s].view(np.uint32), e.view(np.uint32))     # bit pattern
+        n_valid += int(v.sum())
+    assert 0 < n_valid < S * table.shape[0]          # the scenes exercise both outcomes
+
+
+def test_collision_check_edges(pkg, oracle):
+    # ragged sample counts (not a multiple of 32), out-of-grid samples, fully occupied and empty grids
+    rng = np.random.default_rng(5)
+    S = 8
+    grids = (rng.random((S, 100 * 100)) < 0.02).astype(np.float32)
+    grids[0] = 0.0
+    grids[1] = 1.0
+    offs = rng.uniform(-1, 1, (S, 2)).astype(np.float32)
+    yaw = rng.uniform(-3, 3, S)
+    rots = np.stack([np.cos(yaw), -np.sin(yaw), np.sin(yaw), np.cos(yaw)], axis=1)
+    pose = rng.uniform(-1, 1, (S, 2))
+    for samples in (1, 31, 33, 50, 100):
+        table = rng.uniform(-6, 6, (7, samples, 2))
+        table[0] *= 0.1                                   # one short path that stays inside the grid
+        valid, free, endw = pkg.collision_check_host(grids, offs, rots, pose, table)
+        for s in range(S):
+            v, f, e = oracle.collision_check(grids[s], 100, 0.1, offs[s], rots[s], pose[s], table)
+            np.testing.assert_array_equal(valid[s], v)
+            np.testing.assert_array_equal(free[s], f)
+            np.testing.assert_array_equal(endw[s].view(np.uint32), e.view(np.uint32))
+        assert valid[0, 0] == 1 and valid[1].sum() == 0
