@@ -3,7 +3,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef ADMM_WARPS
+#define ADMM_WARPS 1        // QPs (warps) per CTA
+#endif
+#ifndef ADMM_MIN_BLOCKS
+#define ADMM_MIN_BLOCKS 8   // resident CTAs per SM the register allocation must allow
+#endif
+
 namespace f110 {
+
+// per-QP scratch line in global memory: D, E (12) + previous iterate (12), one column per lane
+constexpr int SCRATCH_DOUBLES = 24 * 32;
 
 struct KParams {
   // problem family (f110_mpc_config)
@@ -23,6 +33,7 @@ struct KParams {
   int32_t* rho_updates;  // [B] or null
   double* info;       // [B][4] or null
   double* state;      // [B][state_doubles(N)] warm-start slots (scaled iterates x, z, y + rho + flag) or null
+  double* scratch;    // [B][SCRATCH_DOUBLES]
 };
 
 // doubles per warm-start slot: x(5N+3) + z(7N+5) + y(7N+5) + rho + valid flag

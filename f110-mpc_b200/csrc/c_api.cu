@@ -29,7 +29,8 @@ struct f110_mpc_solver {
   int max_batch = 0;
   int device = 0;
   int last_launches = 0;
-  double* d_state = nullptr;  // warm-start slots
+  double* d_state = nullptr;    // warm-start slots
+  double* d_scratch = nullptr;  // per-QP scratch lines (scaling vectors, previous iterate)
   // staging for the host-buffer entry
   double* d_recs = nullptr;
   double* d_x = nullptr;
@@ -99,6 +100,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   const size_t ssz = (size_t)max_batch * f110::state_doubles(N) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * f110::SCRATCH_DOUBLES * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);
@@ -112,6 +114,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->d_state);
+  cudaFree(s->d_scratch);
   cudaFree(s->d_recs); cudaFree(s->d_x); cudaFree(s->d_y); cudaFree(s->d_u0);
   cudaFree(s->d_status); cudaFree(s->d_iters);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -147,6 +150,7 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
   p.recs = d_recs; p.x_out = d_x; p.y_out = d_y; p.u0_out = d_u0; p.status = d_status; p.iters = d_iters;
   p.rho_updates = d_rho_updates; p.info = d_info;
   p.state = s->st.warm_start ? s->d_state : nullptr;
+  p.scratch = s->d_scratch;
   CUDA_TRY(cudaSetDevice(s->device));
   cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &s->last_launches);
   if (e != cudaSuccess) return cuda_fail(e, "admm kernel launch");
