@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libf110mpc_b200.so")
+LIB_PATH = os.environ.get("F110_LIB", os.path.join(_HERE, "libf110mpc_b200.so"))  # F110_LIB: tuning builds only
 
 SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED = 1, 2, -2
 PRIMAL_INFEASIBLE, DUAL_INFEASIBLE = -3, -4
