@@ -16,6 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("F110_LIB", os.path.join(_HERE, "libf110mpc_b200.so"))  # F110_LIB: tuning builds only
 
+HOST_LIB_PATH = os.path.join(_HERE, "libf110mpc_host.so")
+
 SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED = 1, 2, -2
 PRIMAL_INFEASIBLE, DUAL_INFEASIBLE = -3, -4
 
@@ -44,9 +46,11 @@ EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_
 
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    srcs = [os.path.join(_HERE, d, f) for d in ("csrc", "host") for f in os.listdir(os.path.join(_HERE, d))]
     srcs += [os.path.join(_HERE, "Makefile"), os.path.join(_HERE, "..", "include", "f110_mpc_b200.h")]
-    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    outs = [LIB_PATH, HOST_LIB_PATH]
+    stale = force or any(not os.path.exists(o) for o in outs) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(o) for o in outs) for s in srcs)
     if stale:
         out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
         if verbose or out.returncode:
@@ -214,3 +218,131 @@ def collision_check_device(grid, offset, rot, pose_xy, table_xy, valid, free_cou
     _check(lib().f110_collision_check_device(S, P, samples, blocks, discrete, _tp(grid), _tp(offset), _tp(rot),
                                              _tp(pose_xy), _tp(table_xy), _tp(valid), _tp(free_count), _tp(end_world),
                                              sp), "f110_collision_check_device")
+
+
+# ---- C++ host classes (f110-mpc_b200/host) through their C shims ---------------------------------------------------
+_host = None
+
+
+def host():
+    """libf110mpc_host.so: the ROS-free C++ mirror of the reference classes (MPC, Constraints, OccGrid, ...)."""
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError("libf110mpc_host.so is not built (run __graft_entry__.build())")
+        lib()
+        H = C.CDLL(HOST_LIB_PATH)
+        dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+        H.f110h_linearize.argtypes = [C.c_double] * 4 + [dp] * 3
+        H.f110h_traj_table.argtypes = [C.c_int, C.c_int, dp]
+        H.f110h_car_to_world_R.argtypes = [dp, dp]
+        H.f110h_fill_grid.argtypes = [dp, C.c_float, C.c_float, C.c_float, fp, C.c_int, fp, fp]
+        H.f110h_find_half_spaces.argtypes = [dp, C.c_float, C.c_float, C.c_float, fp, C.c_int, dp, dp, ip]
+        H.f110h_best_global_idx.argtypes = [fp, C.c_int, dp, dp]
+        H.f110h_mpc_create.restype = C.c_void_p
+        H.f110h_mpc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        H.f110h_mpc_destroy.argtypes = [C.c_void_p]
+        H.f110h_mpc_update_scan.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, fp, C.c_int]
+        H.f110h_mpc_update.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp]
+        H.f110h_plan.argtypes = [C.c_int, C.c_int, dp, C.c_float, C.c_float, C.c_float, fp, C.c_int, fp, C.c_int, C.c_int, dp,
+                                 C.POINTER(C.c_uint8), ip]
+        _host = H
+    return _host
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def host_linearize(ori, v, steer, dt):
+    A, B, Cc = np.zeros(9), np.zeros(6), np.zeros(3)
+    host().f110h_linearize(ori, v, steer, dt, _dp(A), _dp(B), _dp(Cc))
+    return A.reshape(3, 3), B.reshape(3, 2), Cc
+
+
+def host_traj_table(steer_discrete=30, traj_discrete=50):
+    out = np.zeros((steer_discrete + 1, traj_discrete, 3))
+    host().f110h_traj_table(steer_discrete, traj_discrete, _dp(out))
+    return out
+
+
+def host_car_to_world_R(pose7):
+    pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+    R = np.zeros(4)
+    host().f110h_car_to_world_R(_dp(pose7), _dp(R))
+    return R
+
+
+def host_fill_grid(pose7, angle_min, angle_max, angle_inc, ranges):
+    pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+    ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+    grid = np.zeros(100 * 100, dtype=np.float32)
+    off = np.zeros(2, dtype=np.float32)
+    host().f110h_fill_grid(_dp(pose7), angle_min, angle_max, angle_inc, _fp(ranges), len(ranges), _fp(grid), _fp(off))
+    return grid, off
+
+
+def host_find_half_spaces(state3, angle_min, angle_max, angle_inc, ranges):
+    state3 = np.ascontiguousarray(state3, dtype=np.float64)
+    ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+    l1, l2, lohi = np.zeros(3), np.zeros(3), np.zeros(2, dtype=np.int32)
+    ok = host().f110h_find_half_spaces(_dp(state3), angle_min, angle_max, angle_inc, _fp(ranges), len(ranges), _dp(l1), _dp(l2),
+                                       lohi.ctypes.data_as(C.POINTER(C.c_int)))
+    return bool(ok), l1, l2, lohi
+
+
+def host_best_global_idx(wp_xy, pose7):
+    wp_xy = np.ascontiguousarray(wp_xy, dtype=np.float32)
+    pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+    head = np.zeros(len(wp_xy))
+    idx = host().f110h_best_global_idx(_fp(wp_xy), len(wp_xy), _dp(pose7), _dp(head))
+    return idx, head
+
+
+class HostMPC:
+    """The C++ `MPC` class (host/mpc.h): Update(State, Input, vector<State>&) -> solved_trajectory()."""
+
+    def __init__(self, horizon=30, gap_mode=0, device=0):
+        self.N = horizon
+        self._h = host().f110h_mpc_create(horizon, gap_mode, device)
+        if not self._h:
+            raise RuntimeError("MPC construction failed: " + lib().f110_last_error().decode())
+
+    def update_scan(self, angle_min, angle_max, angle_inc, ranges):
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        host().f110h_mpc_update_scan(self._h, angle_min, angle_max, angle_inc, _fp(ranges), len(ranges))
+
+    def update(self, state3, input2, desired):
+        state3 = np.ascontiguousarray(state3, dtype=np.float64)
+        input2 = np.ascontiguousarray(input2, dtype=np.float64)
+        desired = np.ascontiguousarray(desired, dtype=np.float64)
+        N = self.N
+        inputs = np.zeros((N, 2)); x = np.zeros(5 * N + 3); y = np.zeros(7 * N + 5); l1l2 = np.zeros(6)
+        st, it = C.c_int(), C.c_int()
+        n = host().f110h_mpc_update(self._h, _dp(state3), _dp(input2), _dp(desired), desired.shape[0], _dp(inputs), _dp(x), _dp(y),
+                                    C.byref(st), C.byref(it), _dp(l1l2))
+        return dict(inputs=inputs[:n], x=x, y=y, status=st.value, iters=it.value, l1=l1l2[:3], l2=l1l2[3:])
+
+    def close(self):
+        if self._h:
+            host().f110h_mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_plan(pose7, angle_min, angle_max, angle_inc, ranges, wp_xy, steer_discrete=30, traj_discrete=50, device=0):
+    """One planning cycle (project.cpp:73-157): returns (chosen index or -1, mini_path (S,3), valid flags, best_global)."""
+    pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+    ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+    wp_xy = np.ascontiguousarray(wp_xy, dtype=np.float32)
+    path = np.zeros((traj_discrete, 3))
+    valid = np.zeros(steer_discrete + 1, dtype=np.uint8)
+    bg = C.c_int(-1)
+    idx = host().f110h_plan(steer_discrete, traj_discrete, _dp(pose7), angle_min, angle_max, angle_inc, _fp(ranges), len(ranges),
+                            _fp(wp_xy), len(wp_xy), device, _dp(path), valid.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(bg))
+    return idx, path, valid, bg.value

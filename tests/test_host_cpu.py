@@ -1,0 +1,58 @@
+"""CPU tests of the C++ host classes (f110-mpc_b200/host): the ROS-free mirror of the reference's Model /
+Constraints / OccGrid / Transforms / Trajectory / Traj_Plan against the oracle's independent restatement.
+Both are compiled with -ffp-contract=off from separately written sources; results must be bit-identical."""
+import numpy as np
+import pytest
+
+
+def test_linearize_bit_identical(pkg, oracle, workloads):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        th, de = rng.uniform(-3.1, 3.1), rng.uniform(-0.43, 0.43)
+        A, B, C = pkg.host_linearize(th, 4.5, de, workloads.DT_F32)
+        Ao, Bo, Co = oracle.linearize(th, 4.5, de, workloads.DT_F32)
+        np.testing.assert_array_equal(A, Ao); np.testing.assert_array_equal(B, Bo); np.testing.assert_array_equal(C, Co)
+
+
+@pytest.mark.parametrize("sd,td", [(30, 50), (19, 50), (30, 100)])
+def test_traj_table_bit_identical(pkg, oracle, sd, td):
+    np.testing.assert_array_equal(pkg.host_traj_table(sd, td), oracle.traj_table(steer_discrete=sd, traj_discrete=td))
+
+
+def test_grid_fill_and_rotation_bit_identical(pkg, oracle, workloads):
+    poses, yaws, scans = workloads.scene_batch(24, seed=3)
+    for s in range(24):
+        g, off = pkg.host_fill_grid(poses[s], workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC, scans[s])
+        go, offo, _ = oracle.fill_grid(poses[s], workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC, scans[s])
+        np.testing.assert_array_equal(g, go); np.testing.assert_array_equal(off, offo)
+        assert 0 < g.sum() < g.size
+        np.testing.assert_array_equal(pkg.host_car_to_world_R(poses[s]), oracle.car_to_world_R(poses[s]))
+
+
+def test_half_spaces_bit_identical(pkg, oracle, workloads):
+    rng = np.random.default_rng(1)
+    amin, amax, inc = workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC
+    n_ok = 0
+    for t in range(40):
+        r = rng.uniform(0.5, 2.8, 1080).astype(np.float32)
+        for _ in range(rng.integers(0, 4)):
+            a = rng.integers(150, 900); w = rng.integers(1, 200)
+            r[a:a + w] = rng.uniform(3.5, 10.0)
+        st = np.array([rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)])
+        ok, l1, l2, lohi = pkg.host_find_half_spaces(st, amin, amax, inc, r)
+        oko, l1o, l2o, lohio = oracle.find_half_spaces(st, amin, amax, inc, r)
+        assert ok == oko and tuple(lohi) == tuple(lohio)
+        if ok:
+            n_ok += 1
+            np.testing.assert_array_equal(l1, l1o); np.testing.assert_array_equal(l2, l2o)
+    assert n_ok > 10
+
+
+def test_lookahead_index_and_headings(pkg, oracle, workloads):
+    xy, ori = workloads.skirk_waypoints()
+    for i in range(0, 500, 23):
+        pose = workloads.yaw_pose(float(xy[i, 0]), float(xy[i, 1]), float(ori[i]))
+        idx, head = pkg.host_best_global_idx(xy, pose)
+        assert idx == oracle.best_global_idx(xy, pose, 2.5)
+    np.testing.assert_array_equal(head, oracle.waypoint_headings(xy))
+    np.testing.assert_allclose(head, ori, atol=1e-6)       # numpy's float32 arctan2 in workloads.py is within an ulp of atan2f
