@@ -48,7 +48,7 @@ def hbm_bytes_per_qp(N):
     return 8 * (11 + 3 * N) + 16 + 8
 
 
-def build_workload(W, rank):
+def build_workload(M, W, rank):
     """4096 QPs = 205 scenes x 20 mini-paths (truncated): ego on a skirk waypoint with a small tracking error,
     reference = mini-path p in the world frame; plus the scenes' occupancy grids for the collision check."""
     table = W.traj_table(steer_discrete=PATHS - 1, traj_discrete=SAMPLES)       # (20, 50, 3)
@@ -62,21 +62,9 @@ def build_workload(W, rank):
     for s in range(S):
         x, y, yaw = poses[s, 0], poses[s, 1], yaws[s]
         c, sn = np.cos(yaw), np.sin(yaw)
-        rots[s] = (c, -sn, sn, c)
-        offs[s] = (x + 0.275 * c, y + 0.275 * sn)
-        # synthetic occupancy: scan hits stamped with the 4x4 dilation pattern (numpy; the bit-exact fill is
-        # exercised in tests/, the check kernel only needs a grid)
-        ang = W.SCAN_ANGLE_MIN + np.arange(W.SCAN_BEAMS) * W.SCAN_ANGLE_INC + yaw
-        hx = scans[s] * np.cos(ang) + offs[s, 0]
-        hy = scans[s] * np.sin(ang) + offs[s, 1]
-        g = np.zeros((100, 100), dtype=np.float32)
-        for ox in (-0.15, -0.05, 0.05, 0.15):
-            for oy in (-0.15, -0.05, 0.05, 0.15):
-                col = ((hx + ox - offs[s, 0]) / 0.1 + 50).astype(np.int64)
-                row = ((hy + oy - offs[s, 1]) / 0.1 + 50).astype(np.int64)
-                ok = (col >= 0) & (col < 100) & (row >= 0) & (row < 100)
-                g[row[ok], col[ok]] = 1.0
-        grids[s] = g.T.reshape(-1)            # Eigen column-major: (row, col) at row + col*100
+        # occupancy grid and tf2 rotation from the product's C++ host classes (OccGrid::FillOccGrid, Transforms)
+        grids[s], offs[s] = M.host_fill_grid(poses[s], W.SCAN_ANGLE_MIN, W.SCAN_ANGLE_MAX, W.SCAN_ANGLE_INC, scans[s])
+        rots[s] = M.host_car_to_world_R(poses[s])
         lat, dyaw = rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2)
         x0 = np.array([x - sn * lat, y + c * lat, yaw + dyaw])
         for p in range(PATHS):
@@ -151,8 +139,10 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    M = importlib.import_module("f110-mpc_b200")
     W = importlib.import_module("f110-mpc_b200.workloads")
-    wl = build_workload(W, 0)
+    M.build()
+    wl = build_workload(M, W, 0)
     threads, secs = cpu_reference_run(wl["recs"], args.steps, args.warmup)
     tot = float(np.sum(secs))
     value = QPS_PER_GPU * args.steps / tot
@@ -181,6 +171,7 @@ def main_product(args):
     import torch.distributed as dist
     M = importlib.import_module("f110-mpc_b200")
     W = importlib.import_module("f110-mpc_b200.workloads")
+    SH = importlib.import_module("f110-mpc_b200.sharding")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,7 +182,7 @@ def main_product(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     M.build()
-    wl = build_workload(W, rank)
+    wl = build_workload(M, W, rank)
     B, S = QPS_PER_GPU, wl["scenes"]
     sol = M.MpcSolver(M.default_config(N_HORIZON), M.default_settings(warm_start=0), max_batch=B, device=local)
     # ---- device-resident inputs / outputs
@@ -204,19 +195,14 @@ def main_product(args):
     d_valid = torch.empty(S, PATHS, dtype=torch.uint8, device=dev)
     d_free = torch.empty(S, PATHS, dtype=torch.int32, device=dev)
     d_endw = torch.empty(S, PATHS, 2, dtype=torch.float32, device=dev)
-    d_result = torch.empty(B, 4, dtype=torch.float64, device=dev)            # u0(2), status, iters — what is gathered
-    d_gather = torch.empty(world * B, 4, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         M.collision_check_device(d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free, d_endw, stream=stream)
         sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
-        if world > 1:
-            d_result[:, :2] = d_u0
-            d_result[:, 2] = d_status
-            d_result[:, 3] = d_iters
-            dist.all_gather_into_tensor(d_gather, d_result)
+        if world > 1:   # the one collective: chosen controls of every rank, in batch order
+            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B)
 
     def barrier():
         if world > 1:
@@ -240,11 +226,8 @@ def main_product(args):
         kev[i][0].record()
         sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
         kev[i][1].record()
-        if world > 1:
-            d_result[:, :2] = d_u0
-            d_result[:, 2] = d_status
-            d_result[:, 3] = d_iters
-            dist.all_gather_into_tensor(d_gather, d_result)
+        if world > 1:   # the one collective: chosen controls of every rank, in batch order
+            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B)
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

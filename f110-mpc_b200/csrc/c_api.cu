@@ -201,44 +201,71 @@ int f110_collision_check_device(int scenes, int paths, int samples, int blocks, 
   return F110_OK;
 }
 
+// Device staging for the host-buffer collision entry: grown on demand, kept for the life of the process so a
+// per-cycle caller pays no cudaMalloc.  One cache per host thread (and device).
+namespace {
+struct CollisionCache {
+  int device = -1;
+  size_t cap_grid = 0, cap_scene = 0, cap_tab = 0, cap_out = 0;
+  float *grid = nullptr, *off = nullptr, *endw = nullptr;
+  double *rot = nullptr, *pose = nullptr, *tab = nullptr;
+  uint8_t* valid = nullptr;
+  int32_t* free_cnt = nullptr;
+  cudaStream_t stream = nullptr;
+  void release() {
+    cudaFree(grid); cudaFree(off); cudaFree(endw); cudaFree(rot); cudaFree(pose); cudaFree(tab); cudaFree(valid); cudaFree(free_cnt);
+    grid = off = endw = nullptr; rot = pose = tab = nullptr; valid = nullptr; free_cnt = nullptr;
+    cap_grid = cap_scene = cap_tab = cap_out = 0;
+  }
+};
+thread_local CollisionCache g_cc;
+}  // namespace
+
 int f110_collision_check_host(int scenes, int paths, int samples, int blocks, float discrete, const float* grid, const float* offset,
                               const double* rot, const double* pose_xy, const double* table_xy, uint8_t* valid,
                               int32_t* free_count, float* end_world, int device) {
+  if (scenes < 0 || paths <= 0 || samples <= 0 || blocks <= 0) return fail(F110_ERR_ARG, "f110_collision_check: bad sizes");
+  if (!grid || !offset || !rot || !pose_xy || !table_xy || !valid || !free_count || !end_world)
+    return fail(F110_ERR_ARG, "f110_collision_check: null buffer");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(F110_ERR_CUDA, "f110_collision_check_host: no CUDA device (this library has no CPU fallback)");
+  if (scenes == 0) return F110_OK;
   CUDA_TRY(cudaSetDevice(device));
-  const size_t gsz = (size_t)scenes * blocks * blocks * sizeof(float);
-  const size_t np = (size_t)scenes * paths;
-  float *d_grid = nullptr, *d_off = nullptr, *d_end = nullptr;
-  double *d_rot = nullptr, *d_pose = nullptr, *d_tab = nullptr;
-  uint8_t* d_valid = nullptr;
-  int32_t* d_free = nullptr;
-  int rc = F110_OK;
-  cudaError_t e = cudaSuccess;
-  auto T = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  T(cudaMalloc(&d_grid, gsz)); T(cudaMalloc(&d_off, scenes * 2 * sizeof(float))); T(cudaMalloc(&d_rot, scenes * 4 * sizeof(double)));
-  T(cudaMalloc(&d_pose, scenes * 2 * sizeof(double))); T(cudaMalloc(&d_tab, (size_t)paths * samples * 2 * sizeof(double)));
-  T(cudaMalloc(&d_valid, np)); T(cudaMalloc(&d_free, np * sizeof(int32_t))); T(cudaMalloc(&d_end, np * 2 * sizeof(float)));
-  if (e == cudaSuccess) {
-    T(cudaMemcpy(d_grid, grid, gsz, cudaMemcpyHostToDevice));
-    T(cudaMemcpy(d_off, offset, scenes * 2 * sizeof(float), cudaMemcpyHostToDevice));
-    T(cudaMemcpy(d_rot, rot, scenes * 4 * sizeof(double), cudaMemcpyHostToDevice));
-    T(cudaMemcpy(d_pose, pose_xy, scenes * 2 * sizeof(double), cudaMemcpyHostToDevice));
-    T(cudaMemcpy(d_tab, table_xy, (size_t)paths * samples * 2 * sizeof(double), cudaMemcpyHostToDevice));
+  CollisionCache& c = g_cc;
+  if (c.device != device) {
+    if (c.device >= 0) { cudaSetDevice(c.device); c.release(); if (c.stream) cudaStreamDestroy(c.stream); c.stream = nullptr; cudaSetDevice(device); }
+    c.device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
-  if (e == cudaSuccess) {
-    rc = f110_collision_check_device(scenes, paths, samples, blocks, discrete, d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free,
-                                     d_end, nullptr);
-    if (rc == F110_OK) {
-      T(cudaMemcpy(valid, d_valid, np, cudaMemcpyDeviceToHost));
-      T(cudaMemcpy(free_count, d_free, np * sizeof(int32_t), cudaMemcpyDeviceToHost));
-      T(cudaMemcpy(end_world, d_end, np * 2 * sizeof(float), cudaMemcpyDeviceToHost));
-    }
+  const size_t gsz = (size_t)scenes * blocks * blocks, np = (size_t)scenes * paths, tsz = (size_t)paths * samples * 2;
+  if (gsz > c.cap_grid) { cudaFree(c.grid); c.grid = nullptr; CUDA_TRY(cudaMalloc(&c.grid, gsz * sizeof(float))); c.cap_grid = gsz; }
+  if ((size_t)scenes > c.cap_scene) {
+    cudaFree(c.off); cudaFree(c.rot); cudaFree(c.pose); c.off = nullptr; c.rot = c.pose = nullptr;
+    CUDA_TRY(cudaMalloc(&c.off, scenes * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.rot, scenes * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.pose, scenes * 2 * sizeof(double)));
+    c.cap_scene = scenes;
   }
-  cudaFree(d_grid); cudaFree(d_off); cudaFree(d_rot); cudaFree(d_pose); cudaFree(d_tab); cudaFree(d_valid); cudaFree(d_free); cudaFree(d_end);
+  if (tsz > c.cap_tab) { cudaFree(c.tab); c.tab = nullptr; CUDA_TRY(cudaMalloc(&c.tab, tsz * sizeof(double))); c.cap_tab = tsz; }
+  if (np > c.cap_out) {
+    cudaFree(c.valid); cudaFree(c.free_cnt); cudaFree(c.endw); c.valid = nullptr; c.free_cnt = nullptr; c.endw = nullptr;
+    CUDA_TRY(cudaMalloc(&c.valid, np)); CUDA_TRY(cudaMalloc(&c.free_cnt, np * sizeof(int32_t))); CUDA_TRY(cudaMalloc(&c.endw, np * 2 * sizeof(float)));
+    c.cap_out = np;
+  }
+  cudaStream_t st = c.stream;
+  CUDA_TRY(cudaMemcpyAsync(c.grid, grid, gsz * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c.off, offset, scenes * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c.rot, rot, scenes * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c.pose, pose_xy, scenes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c.tab, table_xy, tsz * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = f110_collision_check_device(scenes, paths, samples, blocks, discrete, c.grid, c.off, c.rot, c.pose, c.tab, c.valid, c.free_cnt,
+                                       c.endw, st);
   if (rc != F110_OK) return rc;
-  if (e != cudaSuccess) return cuda_fail(e, "f110_collision_check_host");
+  CUDA_TRY(cudaMemcpyAsync(valid, c.valid, np, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(free_count, c.free_cnt, np * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(end_world, c.endw, np * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return F110_OK;
 }
 
