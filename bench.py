@@ -202,7 +202,7 @@ def main_product(args):
         M.collision_check_device(d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free, d_endw, stream=stream)
         sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
         if world > 1:   # the one collective: chosen controls of every rank, in batch order
-            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B)
+            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B, sizes=[B] * world)
 
     def barrier():
         if world > 1:
@@ -227,7 +227,7 @@ def main_product(args):
         sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
         kev[i][1].record()
         if world > 1:   # the one collective: chosen controls of every rank, in batch order
-            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B)
+            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B, sizes=[B] * world)
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

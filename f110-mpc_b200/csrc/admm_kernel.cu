@@ -60,6 +60,96 @@ __device__ __forceinline__ double limit_scaling(double v) {
 }
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return dmin(dmax(v, lo), hi); }
 
+// ---- cross-stage communication ------------------------------------------------------------------------------
+// One stage per thread.  WPQ = warps per QP: 1 -> everything is a warp shuffle; 2 or 4 (horizons 32..127) -> the
+// CTA is the QP, values travel through a double-buffered shared-memory exchange with one barrier per exchange
+// (a thread can only overwrite buffer b after passing the barrier of the exchange on buffer b^1, which every
+// thread reaches only after it has finished reading b).
+template <int WPQ>
+struct Comm;
+
+template <>
+struct Comm<1> {
+  __device__ __forceinline__ Comm(double*, int) {}
+  template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_up_sync(FULL, v[i], h);
+  }
+  template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_down_sync(FULL, v[i], h);
+  }
+  template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lo[i] = __shfl_up_sync(FULL, v[i], h); hi[i] = __shfl_down_sync(FULL, v[i], h); }
+  }
+  __device__ __forceinline__ double rmax(double v) { return wmax(v); }
+  __device__ __forceinline__ double rsum(double v) { return wsum(v); }
+  __device__ __forceinline__ bool any(bool b) { return __any_sync(FULL, b); }
+  __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+template <int WPQ>
+struct Comm {
+  static constexpr int T = 32 * WPQ;
+  static constexpr int KMAX = 9;
+  double* xb;   // [2][KMAX][T] exchange buffers
+  double* rb;   // [2][WPQ] reduction slots
+  int tid, xph = 0, rph = 0;
+  __device__ __forceinline__ Comm(double* smem, int t) : xb(smem), rb(smem + 2 * KMAX * T), tid(t) {}
+  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ; }
+  template <int K> __device__ __forceinline__ double* put(const double* v) {
+    double* b = xb + xph * KMAX * T;
+    xph ^= 1;
+#pragma unroll
+    for (int i = 0; i < K; ++i) b[i * T + tid] = v[i];
+    __syncthreads();
+    return b;
+  }
+  // out-of-range sources return the caller's own value, like a shuffle; callers mask them
+  template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid - h >= 0 ? tid - h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+  }
+  template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid + h < T ? tid + h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+  }
+  template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
+    const double* b = put<K>(v);
+    const int sl = tid - h >= 0 ? tid - h : tid, sh = tid + h < T ? tid + h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lo[i] = b[i * T + sl]; hi[i] = b[i * T + sh]; }
+  }
+  __device__ __forceinline__ double* rslot(double v) {
+    double* r = rb + rph * WPQ;
+    rph ^= 1;
+    if ((tid & 31) == 0) r[tid >> 5] = v;
+    __syncthreads();
+    return r;
+  }
+  __device__ __forceinline__ double rmax(double v) {
+    const double* r = rslot(wmax(v));
+    double m = r[0];
+#pragma unroll
+    for (int w = 1; w < WPQ; ++w) m = dmax(m, r[w]);
+    return m;
+  }
+  __device__ __forceinline__ double rsum(double v) {
+    const double* r = rslot(wsum(v));
+    double m = r[0];
+#pragma unroll
+    for (int w = 1; w < WPQ; ++w) m += r[w];
+    return m;
+  }
+  __device__ __forceinline__ bool any(bool b) { return __syncthreads_or(b) != 0; }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
 // ---- 3x3 helpers (row-major double[9]) ------------------------------------------------------------
 __device__ __forceinline__ void mm3(const double* a, const double* b, double* c) {  // c = a b
 #pragma unroll
@@ -126,23 +216,22 @@ constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22
 
 }  // namespace
 
-// NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N == 31): lane 31 is an active stage, so
-// the "successor" shuffles of the last stage wrap onto itself and need a mask.
-template <int NLEV, bool LASTFULL>
-__global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(const KParams p) {
+// One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
+// NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == 32 WPQ): the last thread is an active
+// stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
+template <int NLEV, int WPQ, bool LASTFULL>
+__global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
   extern __shared__ double smem_all[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int qp = blockIdx.x * ADMM_WARPS + warp;
-  if (qp >= p.B) return;
-  constexpr int SM_COEF = NLEV * 18 * 32;  // alpha(9), gamma(9) per level, element-major, lane fastest
-  constexpr int SM_PER_WARP = SM_COEF + 6 * 32;
-  double* sm_coef = smem_all + (size_t)warp * SM_PER_WARP + lane;
+  constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
+  const int qp = blockIdx.x;
+  const int k = threadIdx.x;
+  constexpr int SM_COEF = NLEV * 18 * T;   // alpha(9), gamma(9) per level, element-major, stage fastest
+  double* sm_coef = smem_all + k;
   double* sm_binv = sm_coef + SM_COEF;
-  double* scr = p.scratch + (size_t)qp * SCRATCH_DOUBLES + lane;
+  Comm<WPQ> cm(smem_all + SM_COEF + 6 * T, k);
+  double* scr = p.scratch + (size_t)qp * (24 * T) + k;
 
   const int N = p.N;
-  const int k = lane;
   const bool act = k <= N;         // lane owns a stage
   const bool actu = k < N;         // stage has an input (and box rows, and a successor)
   const bool hasp = act && k > 0;  // stage has a predecessor
@@ -216,12 +305,16 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     for (int e = 0; e < 6; ++e) ag[e] = fabs(s.gm[e]);
     for (int it = 0; it < p.scaling; ++it) {
       double edn[3], dxp[3], dup[2];
+      {
+        const double snd[5] = {dx[0], dx[1], dx[2], du[0], du[1]};
+        double rcv[5];
+        cm.template dn<3>(ed, edn, 1);
+        cm.template up<5>(snd, rcv, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { edn[i] = __shfl_down_sync(FULL, ed[i], 1); edn[i] = actu ? edn[i] : 0.0; }
+        for (int i = 0; i < 3; ++i) { edn[i] = actu ? edn[i] : 0.0; dxp[i] = hasp ? rcv[i] : 0.0; }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { dxp[j] = __shfl_up_sync(FULL, dx[j], 1); dxp[j] = hasp ? dxp[j] : 0.0; }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { dup[j] = __shfl_up_sync(FULL, du[j], 1); dup[j] = hasp ? dup[j] : 0.0; }
+        for (int j = 0; j < 2; ++j) dup[j] = hasp ? rcv[3 + j] : 0.0;
+      }
       double tx[3], tu[2], td[3], tg[2], tb[2];
       // KKT column of x_k[j]: P, the -1 of dyn row k, column j of A in dyn rows k+1 (A = I + a02/a12 in col 2), gap rows k
 #pragma unroll
@@ -291,17 +384,17 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
 #pragma unroll
         for (int j = 0; j < 2; ++j) { psum += c * du[j] * du[j] * p.R[j]; qn = dmax(qn, fabs(du[j] * qu[j])); }
       }
-      const double mean = wsum(psum) / (double)nvar;
-      const double qinf = limit_scaling(c * wmax(qn));
+      const double mean = cm.rsum(psum) / (double)nvar;
+      const double qinf = limit_scaling(c * cm.rmax(qn));
       const double ct = limit_scaling(dmax(mean, qinf));
       c *= 1.0 / ct;
     }
     cinv = 1.0 / c;
     // park D, E in the scratch line: only the rho estimate, infeasibility tests and the state store read them again
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { scr[(SCR_DX + j) * 32] = dx[j]; scr[(SCR_ED + j) * 32] = ed[j]; }
+    for (int j = 0; j < 3; ++j) { scr[(SCR_DX + j) * T] = dx[j]; scr[(SCR_ED + j) * T] = ed[j]; }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { scr[(SCR_DU + j) * 32] = du[j]; scr[(SCR_EG + j) * 32] = eg[j]; scr[(SCR_EB + j) * 32] = eb[j]; }
+    for (int j = 0; j < 2; ++j) { scr[(SCR_DU + j) * T] = du[j]; scr[(SCR_EG + j) * T] = eg[j]; scr[(SCR_EB + j) * T] = eb[j]; }
     // row classes (OSQP set_rho_vec, on the SCALED bounds); dynamics rows have l = u -> equality
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -327,8 +420,8 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
 #pragma unroll
       for (int j = 0; j < 2; ++j) { a = dmax(a, fabs(qu[j])); b = dmax(b, fabs(du[j] * qu[j])); }
     }
-    nq = wmax(a);
-    snq = c * wmax(b);
+    nq = cm.rmax(a);
+    snq = c * cm.rmax(b);
   }
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
@@ -348,14 +441,14 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     if (act) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const double e = scr[(SCR_ED + j) * 32];
-        s.x[j] = scr[(SCR_DX + j) * 32] * sx_[3 * k + j];
+        const double e = scr[(SCR_ED + j) * T];
+        s.x[j] = scr[(SCR_DX + j) * T] * sx_[3 * k + j];
         s.zd[j] = sz_[3 * k + j] / e;
         s.yd[j] = e * sy_[3 * k + j] * cinv;
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const double e = scr[(SCR_EG + r) * 32];
+        const double e = scr[(SCR_EG + r) * T];
         s.zg[r] = sz_[3 * (N + 1) + 2 * k + r] / e;
         s.yg[r] = e * sy_[3 * (N + 1) + 2 * k + r] * cinv;
       }
@@ -363,8 +456,8 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     if (actu) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const double e = scr[(SCR_EB + j) * 32];
-        s.u[j] = scr[(SCR_DU + j) * 32] * sx_[3 * (N + 1) + 2 * k + j];
+        const double e = scr[(SCR_EB + j) * T];
+        s.u[j] = scr[(SCR_DU + j) * T] * sx_[3 * (N + 1) + 2 * k + j];
         s.zb[j] = sz_[5 * (N + 1) + 2 * k + j] / e;
         s.yb[j] = e * sy_[5 * (N + 1) + 2 * k + j] * cinv;
       }
@@ -394,8 +487,9 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
         s.rg[r] = rg * wg[r]; s.ig[r] = 1.0 / s.rg[r];
         s.rb[r] = rb * wb[r]; s.ib[r] = 1.0 / s.rb[r];
       }
+      cm.template dn<3>(s.rd, s.rdn, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { const double t = __shfl_down_sync(FULL, s.rd[i], 1); s.rdn[i] = actu ? t : 0.0; }
+      for (int i = 0; i < 3; ++i) s.rdn[i] = actu ? s.rdn[i] : 0.0;
       double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.B) W^-1 (rdn.B)'
       {
         const double w00 = p.R[0] + s.su[0] + s.rb[0] + md.b00 * md.b00 * s.rdn[0] + md.b10 * md.b10 * s.rdn[1] + md.b20 * md.b20 * s.rdn[2];
@@ -417,12 +511,10 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
 #pragma unroll
           for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - (MW[2 * i] * M[2 * l] + MW[2 * i + 1] * M[2 * l + 1]);
       }
-      double Rt[9];  // R~_k: from lane k-1, or diag(rho_d) for the x_0 = x_cur rows
+      double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
+      cm.template up<9>(Rn, Rt, 1);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) {
-        const double t = __shfl_up_sync(FULL, Rn[e], 1);
-        Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? t : 0.0);
-      }
+      for (int e = 0; e < 9; ++e) Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? Rt[e] : 0.0);
       double Bm[9], Lm[9], Um[9];
       {
         // Hx = diag(Q + sigma_x) + G' diag(rho_g) G  (+ R~_k)
@@ -468,42 +560,33 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
         inv_spd3(Bm, Bi);
         mm3(Bi, Um, XU);
         mm3(Bi, Lm, XL);
-        double nb[9], t1[9], t2[9];
+        double nlo[9], nhi[9], t1[9], t2[9];
         double alp[9], gam[9], Ln[9], Un[9];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_up_sync(FULL, Bi[e], h);
-        mm3(Lm, nb, alp);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_up_sync(FULL, XU[e], h);
-        mm3(Lm, nb, t1);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_up_sync(FULL, XL[e], h);
-        mm3(Lm, nb, Ln);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_down_sync(FULL, Bi[e], h);
-        mm3(Um, nb, gam);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_down_sync(FULL, XL[e], h);
-        mm3(Um, nb, t2);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) nb[e] = __shfl_down_sync(FULL, XU[e], h);
-        mm3(Um, nb, Un);
+        cm.template both<9>(Bi, nlo, nhi, h);
+        mm3(Lm, nlo, alp);
+        mm3(Um, nhi, gam);
+        cm.template both<9>(XU, nlo, nhi, h);
+        mm3(Lm, nlo, t1);
+        mm3(Um, nhi, Un);
+        cm.template both<9>(XL, nlo, nhi, h);
+        mm3(Lm, nlo, Ln);
+        mm3(Um, nhi, t2);
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
           Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
           Lm[e] = vlo ? -Ln[e] : 0.0;
           Um[e] = vhi ? -Un[e] : 0.0;
-          sm_coef[(lev * 18 + e) * 32] = vlo ? alp[e] : 0.0;
-          sm_coef[(lev * 18 + 9 + e) * 32] = vhi ? gam[e] : 0.0;
+          sm_coef[(lev * 18 + e) * T] = vlo ? alp[e] : 0.0;
+          sm_coef[(lev * 18 + 9 + e) * T] = vhi ? gam[e] : 0.0;
         }
       }
       {
         double Bi[9];
         inv_spd3(Bm, Bi);
-        sm_binv[0 * 32] = Bi[0]; sm_binv[1 * 32] = Bi[1]; sm_binv[2 * 32] = Bi[2];
-        sm_binv[3 * 32] = Bi[4]; sm_binv[4 * 32] = Bi[5]; sm_binv[5 * 32] = Bi[8];
+        sm_binv[0 * T] = Bi[0]; sm_binv[1 * T] = Bi[1]; sm_binv[2 * T] = Bi[2];
+        sm_binv[3 * T] = Bi[4]; sm_binv[4 * T] = Bi[5]; sm_binv[5 * T] = Bi[8];
       }
-      __syncwarp();
+      cm.sync();
     }
 
     const bool last = (iter == p.max_iter);
@@ -514,9 +597,9 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     const bool info_iter = chk || adp || last;
     if (info_iter) {  // the infeasibility tests need delta x, delta y of this iteration
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * 32] = s.x[j]; scr[(SCR_PYD + j) * 32] = s.yd[j]; }
+      for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * 32] = s.u[j]; scr[(SCR_PYG + j) * 32] = s.yg[j]; scr[(SCR_PYB + j) * 32] = s.yb[j]; }
+      for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
     }
 
     // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
@@ -528,10 +611,10 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
 #pragma unroll
       for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
       double sdn[3];
+      cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
+      if (LASTFULL) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        sdn[i] = __shfl_down_sync(FULL, sd[i], 1);  // lanes above N hold zeros, so only N == 31 needs the mask
-        if (LASTFULL) sdn[i] = actu ? sdn[i] : 0.0;
+        for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
       }
       double gx[3], gu[2], t3[3], t2[2];
       At_mul(md, sdn, t3);
@@ -547,54 +630,51 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
       B_mul(md, hh, f);
 #pragma unroll
       for (int i = 0; i < 3; ++i) f[i] *= s.rdn[i];
-      double r[3];
+      double r[3], fp[3];
       At_mul(md, f, t3);
+      cm.template up<3>(f, fp, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double fp = __shfl_up_sync(FULL, f[i], 1);
-        r[i] = gx[i] - t3[i] + (hasp ? fp : 0.0);
-      }
+      for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
       // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
 #pragma unroll
       for (int lev = 0; lev < NLEV; ++lev) {
         const int h = 1 << lev;
         double lo[3], hi[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { lo[i] = __shfl_up_sync(FULL, r[i], h); hi[i] = __shfl_down_sync(FULL, r[i], h); }
-        const double* cf = sm_coef + (lev * 18) * 32;
+        cm.template both<3>(r, lo, hi, h);
+        const double* cf = sm_coef + (lev * 18) * T;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          double acc0 = cf[(3 * i + 0) * 32] * lo[0] + cf[(3 * i + 1) * 32] * lo[1];
-          double acc1 = cf[(9 + 3 * i + 0) * 32] * hi[0] + cf[(9 + 3 * i + 1) * 32] * hi[1];
-          acc0 += cf[(3 * i + 2) * 32] * lo[2];
-          acc1 += cf[(9 + 3 * i + 2) * 32] * hi[2];
+          double acc0 = cf[(3 * i + 0) * T] * lo[0] + cf[(3 * i + 1) * T] * lo[1];
+          double acc1 = cf[(9 + 3 * i + 0) * T] * hi[0] + cf[(9 + 3 * i + 1) * T] * hi[1];
+          acc0 += cf[(3 * i + 2) * T] * lo[2];
+          acc1 += cf[(9 + 3 * i + 2) * T] * hi[2];
           r[i] = r[i] - acc0 - acc1;
         }
       }
       double xt[3];
       {
-        const double b0 = sm_binv[0 * 32], b1 = sm_binv[1 * 32], b2 = sm_binv[2 * 32];
-        const double b4 = sm_binv[3 * 32], b5 = sm_binv[4 * 32], b8 = sm_binv[5 * 32];
+        const double b0 = sm_binv[0 * T], b1 = sm_binv[1 * T], b2 = sm_binv[2 * T];
+        const double b4 = sm_binv[3 * T], b5 = sm_binv[4 * T], b8 = sm_binv[5 * T];
         xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
         xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
         xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
       }
       // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
-      double axt[3], v[3];
+      double axt[3], v[3], xn[3];
       A_mul(md, xt, axt);
+      cm.template dn<3>(xt, xn, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { const double xn = __shfl_down_sync(FULL, xt[i], 1); v[i] = s.rdn[i] * (axt[i] - xn); }
+      for (int i = 0; i < 3; ++i) v[i] = s.rdn[i] * (axt[i] - xn[i]);
       Bt_mul(md, v, t2);
       const double ut[2] = {hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]), hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1])};
       // z~ = A w~ : dynamics rows need the predecessor's prediction
-      double pred[3], ztd[3];
+      double pred[3], ztd[3], pp[3];
       B_mul(md, ut, pred);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        pred[i] += axt[i];
-        const double pp = __shfl_up_sync(FULL, pred[i], 1);
-        ztd[i] = (hasp ? pp : 0.0) - xt[i];
-      }
+      for (int i = 0; i < 3; ++i) pred[i] += axt[i];
+      cm.template up<3>(pred, pp, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? pp[i] : 0.0) - xt[i];
       const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
 #pragma unroll
       for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
@@ -623,28 +703,28 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     // ---------- residuals & norms (OSQP update_info + the norms of compute_rho_estimate) -----------------------
     double n_z, n_Ax, n_Aty, n_Px;                      // unscaled (termination)
     double s_pri, s_dua, s_z, s_Ax, s_Aty, s_Px;        // scaled (rho estimate)
-    const double edv[3] = {scr[(SCR_ED + 0) * 32], scr[(SCR_ED + 1) * 32], scr[(SCR_ED + 2) * 32]};
-    const double egv[2] = {scr[(SCR_EG + 0) * 32], scr[(SCR_EG + 1) * 32]};
-    const double ebv[2] = {scr[(SCR_EB + 0) * 32], scr[(SCR_EB + 1) * 32]};
+    const double edv[3] = {scr[(SCR_ED + 0) * T], scr[(SCR_ED + 1) * T], scr[(SCR_ED + 2) * T]};
+    const double egv[2] = {scr[(SCR_EG + 0) * T], scr[(SCR_EG + 1) * T]};
+    const double ebv[2] = {scr[(SCR_EB + 0) * T], scr[(SCR_EB + 1) * T]};
     {
       double ax[3], pred[3], t3[3], t2[2];
       A_mul(md, s.x, ax);
       B_mul(md, s.u, pred);
-      double Axd[3];
+      double Axd[3], pp[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        pred[i] += ax[i];
-        const double pp = __shfl_up_sync(FULL, pred[i], 1);
-        Axd[i] = (hasp ? pp : 0.0) - s.x[i];
-      }
+      for (int i = 0; i < 3; ++i) pred[i] += ax[i];
+      cm.template up<3>(pred, pp, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Axd[i] = (hasp ? pp[i] : 0.0) - s.x[i];
       const double Axg[2] = {s.gm[0] * s.x[0] + s.gm[1] * s.x[1] + s.gm[2] * s.x[2], s.gm[3] * s.x[0] + s.gm[4] * s.x[1] + s.gm[5] * s.x[2]};
       double ydn[3];
+      cm.template dn<3>(s.yd, ydn, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { const double t = __shfl_down_sync(FULL, s.yd[i], 1); ydn[i] = actu ? t : 0.0; }
+      for (int i = 0; i < 3; ++i) ydn[i] = actu ? ydn[i] : 0.0;
       At_mul(md, ydn, t3);
       Bt_mul(md, ydn, t2);
-      const double dxv[3] = {scr[(SCR_DX + 0) * 32], scr[(SCR_DX + 1) * 32], scr[(SCR_DX + 2) * 32]};
-      const double duv[2] = {scr[(SCR_DU + 0) * 32], scr[(SCR_DU + 1) * 32]};
+      const double dxv[3] = {scr[(SCR_DX + 0) * T], scr[(SCR_DX + 1) * T], scr[(SCR_DX + 2) * T]};
+      const double duv[2] = {scr[(SCR_DU + 0) * T], scr[(SCR_DU + 1) * T]};
       double m_pri = 0, m_z = 0, m_Ax = 0, m_dua = 0, m_Aty = 0, m_Px = 0;
       double q_pri = 0, q_z = 0, q_Ax = 0, q_dua = 0, q_Aty = 0, q_Px = 0, o = 0;
       bool poisoned = false;  // NaN must not hide inside a compare-select max
@@ -689,12 +769,13 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
           o += 0.5 * s.u[j] * Pxu + qu[j] * s.u[j];
         }
       }
-      poisoned = __any_sync(FULL, poisoned);
-      pri_res = poisoned ? 2.0 * OSQP_INFTY : wmax(m_pri); n_z = wmax(m_z); n_Ax = wmax(m_Ax);
-      dua_res = wmax(m_dua); n_Aty = wmax(m_Aty); n_Px = wmax(m_Px);
-      s_pri = wmax(q_pri); s_z = wmax(q_z); s_Ax = wmax(q_Ax);
-      s_dua = c * wmax(q_dua); s_Aty = c * wmax(q_Aty); s_Px = c * wmax(q_Px);
-      obj = wsum(o);
+      poisoned = cm.any(poisoned);
+      pri_res = cm.rmax(m_pri); n_z = cm.rmax(m_z); n_Ax = cm.rmax(m_Ax);
+      if (poisoned) pri_res = 2.0 * OSQP_INFTY;
+      dua_res = cm.rmax(m_dua); n_Aty = cm.rmax(m_Aty); n_Px = cm.rmax(m_Px);
+      s_pri = cm.rmax(q_pri); s_z = cm.rmax(q_z); s_Ax = cm.rmax(q_Ax);
+      s_dua = c * cm.rmax(q_dua); s_Aty = c * cm.rmax(q_Aty); s_Px = c * cm.rmax(q_Px);
+      obj = cm.rsum(o);
     }
 
     // ---------- termination (OSQP check_termination, exact then — on the last iteration — approximate) ---------
@@ -713,11 +794,11 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
           // is_primal_infeasible: delta_y projected on the polar of the recession cone of [l, u]
           double dyd[3], dyg[2], dyb[2];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) dyd[i] = s.yd[i] - scr[(SCR_PYD + i) * 32];   // finite l = u: no projection
+          for (int i = 0; i < 3; ++i) dyd[i] = s.yd[i] - scr[(SCR_PYD + i) * T];   // finite l = u: no projection
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            dyg[r] = s.yg[r] - scr[(SCR_PYG + r) * 32];
-            dyb[r] = s.yb[r] - scr[(SCR_PYB + r) * 32];
+            dyg[r] = s.yg[r] - scr[(SCR_PYG + r) * T];
+            dyb[r] = s.yb[r] - scr[(SCR_PYB + r) * T];
             // upper bound infinite (scaled test): keep the non-positive part, or nothing if the lower is infinite too
             dyg[r] = (egv[r] * s.gl[r] < -INF_THRESH) ? 0.0 : dmin(dyg[r], 0.0);
             const double lbb = ebv[r] * s.bl[r], ubb = ebv[r] * s.bu[r];
@@ -733,11 +814,13 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
             mx = dmax(mx, dmax(fabs(dyg[r]), fabs(dyb[r])));
             lhs += s.gl[r] * dmin(dyg[r], 0.0) + s.bu[r] * dmax(dyb[r], 0.0) + s.bl[r] * dmin(dyb[r], 0.0);
           }
-          const double ndy = wmax(mx);  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
-          if (c * ndy > epi && wsum(lhs) < -epi * ndy) {
+          const double ndy = cm.rmax(mx);  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
+          const double lhs_all = cm.rsum(lhs);
+          if (c * ndy > epi && lhs_all < -epi * ndy) {
             double dn[3], t3[3], t2[2];
+            cm.template dn<3>(dyd, dn, 1);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { const double t = __shfl_down_sync(FULL, dyd[i], 1); dn[i] = actu ? t : 0.0; }
+            for (int i = 0; i < 3; ++i) dn[i] = actu ? dn[i] : 0.0;
             At_mul(md, dn, t3);
             Bt_mul(md, dn, t2);
             double m2 = 0.0;
@@ -745,16 +828,16 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
             for (int j = 0; j < 3; ++j) m2 = dmax(m2, fabs(-dyd[j] + t3[j] + s.gm[j] * dyg[0] + s.gm[3 + j] * dyg[1]));
 #pragma unroll
             for (int j = 0; j < 2; ++j) m2 = dmax(m2, fabs(t2[j] + dyb[j]));
-            pinf = wmax(m2) < epi * ndy;
+            pinf = cm.rmax(m2) < epi * ndy;
           }
         }
         if (!dual_ok) {
           // is_dual_infeasible
           double ddx[3], ddu[2];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) ddx[j] = s.x[j] - scr[(SCR_PX + j) * 32];
+          for (int j = 0; j < 3; ++j) ddx[j] = s.x[j] - scr[(SCR_PX + j) * T];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) ddu[j] = s.u[j] - scr[(SCR_PU + j) * 32];
+          for (int j = 0; j < 2; ++j) ddu[j] = s.u[j] - scr[(SCR_PU + j) * T];
           double mx = 0.0, qd = 0.0, mp = 0.0;
 #pragma unroll
           for (int j = 0; j < 3; ++j) { mx = dmax(mx, fabs(ddx[j])); qd += s.qx[j] * ddx[j]; mp = dmax(mp, fabs(p.Q[j] * ddx[j])); }
@@ -762,18 +845,21 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
 #pragma unroll
             for (int j = 0; j < 2; ++j) { mx = dmax(mx, fabs(ddu[j])); qd += qu[j] * ddu[j]; mp = dmax(mp, fabs(p.R[j] * ddu[j])); }
           }
-          const double ndx = wmax(mx);
-          if (ndx > edi && wsum(qd) < -edi * ndx && wmax(mp) < edi * ndx) {
+          const double ndx = cm.rmax(mx);
+          const double qd_all = cm.rsum(qd), mp_all = cm.rmax(mp);
+          if (ndx > edi && qd_all < -edi * ndx && mp_all < edi * ndx) {
             double ax[3], pred[3];
             A_mul(md, ddx, ax);
             B_mul(md, ddu, pred);
             bool bad = false;
             const double th = edi * ndx;
 #pragma unroll
+            for (int i = 0; i < 3; ++i) pred[i] += ax[i];
+            double pp[3];
+            cm.template up<3>(pred, pp, 1);
+#pragma unroll
             for (int i = 0; i < 3; ++i) {  // equality rows: both sides finite
-              pred[i] += ax[i];
-              const double pp = __shfl_up_sync(FULL, pred[i], 1);
-              const double a = (hasp ? pp : 0.0) - ddx[i];
+              const double a = (hasp ? pp[i] : 0.0) - ddx[i];
               if (act && (a > th || a < -th)) bad = true;
             }
 #pragma unroll
@@ -783,7 +869,7 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
               const double b = ddu[r];
               if (actu && ((ebv[r] * s.bu[r] < INF_THRESH && b > th) || (ebv[r] * s.bl[r] > -INF_THRESH && b < -th))) bad = true;
             }
-            dinf = !__any_sync(FULL, bad);
+            dinf = !cm.any(bad);
           }
         }
         if (prim_ok && dual_ok) { status = approximate ? ST_SOLVED_INACC : ST_SOLVED; finished = true; }
@@ -839,7 +925,7 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
       for (int j = 0; j < 2; ++j) yo[5 * (N + 1) + 2 * k + j] = has_sol ? s.yb[j] : qnan;
     }
   }
-  if (lane == 0) {
+  if (k == 0) {
     if (p.u0_out) { p.u0_out[2 * (size_t)qp] = has_sol ? s.u[0] : qnan; p.u0_out[2 * (size_t)qp + 1] = has_sol ? s.u[1] : qnan; }
     if (p.status) p.status[qp] = status;
     if (p.iters) p.iters[qp] = iter;
@@ -857,14 +943,14 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     if (act) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const double e = scr[(SCR_ED + j) * 32];
-        sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * 32] : 0.0;
+        const double e = scr[(SCR_ED + j) * T];
+        sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * T] : 0.0;
         sz_[3 * k + j] = has_sol ? e * s.zd[j] : 0.0;
         sy_[3 * k + j] = has_sol ? c * s.yd[j] / e : 0.0;
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const double e = scr[(SCR_EG + r) * 32];
+        const double e = scr[(SCR_EG + r) * T];
         sz_[3 * (N + 1) + 2 * k + r] = has_sol ? e * s.zg[r] : 0.0;
         sy_[3 * (N + 1) + 2 * k + r] = has_sol ? c * s.yg[r] / e : 0.0;
       }
@@ -872,25 +958,26 @@ __global__ void __launch_bounds__(32 * ADMM_WARPS, ADMM_MIN_BLOCKS) admm_kernel(
     if (actu) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const double e = scr[(SCR_EB + j) * 32];
-        sx_[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] / scr[(SCR_DU + j) * 32] : 0.0;
+        const double e = scr[(SCR_EB + j) * T];
+        sx_[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] / scr[(SCR_DU + j) * T] : 0.0;
         sz_[5 * (N + 1) + 2 * k + j] = has_sol ? e * s.zb[j] : 0.0;
         sy_[5 * (N + 1) + 2 * k + j] = has_sol ? c * s.yb[j] / e : 0.0;
       }
     }
-    if (lane == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
+    if (k == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
   }
 }
 
-template <int NLEV, bool LASTFULL>
+template <int NLEV, int WPQ, bool LASTFULL>
 static cudaError_t launch_one(const KParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t)ADMM_WARPS * (NLEV * 18 + 6) * 32 * sizeof(double);
+  constexpr int T = 32 * WPQ;
+  size_t smem = (size_t)(NLEV * 18 + 6) * T * sizeof(double);
+  if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = (p.B + ADMM_WARPS - 1) / ADMM_WARPS;
-  admm_kernel<NLEV, LASTFULL><<<grid, 32 * ADMM_WARPS, smem, stream>>>(p);
+  admm_kernel<NLEV, WPQ, LASTFULL><<<p.B, T, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -899,11 +986,13 @@ cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {
   while ((1 << nlev) <= p.N) ++nlev;
   if (launches) *launches = 1;
   switch (nlev) {
-    case 1: return launch_one<1, false>(p, stream);
-    case 2: return launch_one<2, false>(p, stream);
-    case 3: return launch_one<3, false>(p, stream);
-    case 4: return launch_one<4, false>(p, stream);
-    case 5: return (p.N == 31) ? launch_one<5, true>(p, stream) : launch_one<5, false>(p, stream);
+    case 1: return launch_one<1, 1, false>(p, stream);
+    case 2: return launch_one<2, 1, false>(p, stream);
+    case 3: return launch_one<3, 1, false>(p, stream);
+    case 4: return launch_one<4, 1, false>(p, stream);
+    case 5: return (p.N == 31) ? launch_one<5, 1, true>(p, stream) : launch_one<5, 1, false>(p, stream);
+    case 6: return (p.N == 63) ? launch_one<6, 2, true>(p, stream) : launch_one<6, 2, false>(p, stream);
+    case 7: return (p.N == 127) ? launch_one<7, 4, true>(p, stream) : launch_one<7, 4, false>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -3,9 +3,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#ifndef ADMM_WARPS
-#define ADMM_WARPS 1        // QPs (warps) per CTA
-#endif
 #ifndef ADMM_MIN_BLOCKS
 #define ADMM_MIN_BLOCKS 8   // resident CTAs per SM the register allocation must allow
 #endif
@@ -13,7 +10,7 @@
 namespace f110 {
 
 // per-QP scratch line in global memory: D, E (12) + previous iterate (12), one column per lane
-constexpr int SCRATCH_DOUBLES = 24 * 32;
+constexpr int SCRATCH_DOUBLES = 24 * 128;  // sized for 4 warps per QP (horizon <= 127)
 
 struct KParams {
   // problem family (f110_mpc_config)

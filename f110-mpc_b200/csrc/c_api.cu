@@ -82,7 +82,6 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
                     f110_mpc_solver** out) {
   if (!cfg || !st || !out || max_batch <= 0) return fail(F110_ERR_ARG, "f110_mpc_create: null argument or max_batch <= 0");
   if (cfg->horizon < 1 || cfg->horizon > F110_MAX_HORIZON) return fail(F110_ERR_ARG, "f110_mpc_create: horizon out of range");
-  if (cfg->horizon > 31) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: horizons above 31 are not built yet");
   if (st->scaled_termination) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: scaled_termination = 1 is not supported");
   if (st->max_iter < 1 || st->check_termination < 0 || st->scaling < 0) return fail(F110_ERR_ARG, "f110_mpc_create: bad settings");
   int ndev = 0;
@@ -100,7 +99,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   const size_t ssz = (size_t)max_batch * f110::state_doubles(N) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * f110::SCRATCH_DOUBLES * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * 24 * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);

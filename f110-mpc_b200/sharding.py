@@ -28,14 +28,16 @@ def pack_result(u0, status, iters):
     return out
 
 
-def gather_results(local, world, max_rows=None):
-    """All-gather per-rank result rows (possibly ragged) into batch order.  `local`: (b_r, 4) f64."""
+def gather_results(local, world, max_rows=None, sizes=None):
+    """All-gather per-rank result rows (possibly ragged) into batch order.  `local`: (b_r, 4) f64.
+    Pass `sizes` (rows per rank) when they are known up front: it saves the size exchange and its host sync."""
     if world == 1:
         return local
-    counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts)
-    sizes = [int(c.item()) for c in all_counts]
+    if sizes is None:
+        counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        all_counts = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(all_counts, counts)
+        sizes = [int(c.item()) for c in all_counts]
     width = max_rows or max(sizes)
     padded = torch.zeros(width, local.shape[1], dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local

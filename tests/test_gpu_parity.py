@@ -37,6 +37,30 @@ def test_cold_batch_matches_oracle(pkg, oracle, workloads, N, eps):
     np.testing.assert_array_equal(g["iters"], o["iters"])        # same algorithm -> same iteration counts
 
 
+@pytest.mark.parametrize("N", [32, 50, 63, 64, 100, 127])
+def test_long_horizons_match_oracle(pkg, oracle, workloads, N):
+    # horizons above 31: the QP spans 2 or 4 warps of one CTA (config 5 of BASELINE.json: N = 50, 100)
+    B, eps = 96, 1e-4
+    recs = workloads.tracking_batch(B, N, seed=200 + N)
+    g = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])
+
+
+def test_long_horizon_gap_mode_and_warm_start(pkg, oracle, workloads):
+    N, B, eps = 50, 64, 1e-4
+    recs = workloads.tracking_batch(B, N, seed=51, gaps=True)
+    sol = pkg.MpcSolver(pkg.default_config(N, 1), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=1), B)
+    mb = oracle.MpcBatch(oracle.default_cfg(N, 1), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=1), B)
+    for step in range(3):
+        g = sol.solve_host(recs)
+        o = mb.solve(recs, warm=True)
+        assert_solution_parity(g, o, N)
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        recs = recs.copy(); recs[:, 0] += 0.01; recs[:, 4] *= 0.9
+
+
 def test_gap_enabled_mode_including_infeasible(pkg, oracle, workloads):
     N, B, eps = 30, 256, 1e-4
     recs = workloads.tracking_batch(B, N, gaps=True)
