@@ -332,6 +332,192 @@ def main_product(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# --configs: the five BASELINE.json configurations, each measured on the GPU with the CPU oracle beside it.
+# Not the default bench line: writes a JSON report (profiles/configs_rNN.json).
+def run_configs(args):
+    import torch
+    M = importlib.import_module("f110-mpc_b200")
+    W = importlib.import_module("f110-mpc_b200.workloads")
+    from oracle import oracle_py as O
+    M.build(); O.build()
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    amin, amax, inc = W.SCAN_ANGLE_MIN, W.SCAN_ANGLE_MAX, W.SCAN_ANGLE_INC
+    report = {"gpu": torch.cuda.get_device_name(0), "host_threads": os.cpu_count(),
+              "note": "CPU numbers: oracle/ (OSQP-algorithm restatement, not the OSQP binary). Parity UNPINNED by the reference."}
+
+    def gpu_batch_time(N, recs, gap_mode=0, reps=10, **st):
+        B = recs.shape[0]
+        sol = M.MpcSolver(M.default_config(N, gap_mode), M.default_settings(warm_start=0, **st), max_batch=B)
+        r = torch.from_numpy(np.ascontiguousarray(recs)).to(dev)
+        u0 = torch.empty(B, 2, dtype=torch.float64, device=dev); stt = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev); ru = torch.empty(B, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            sol.solve_device(r, None, None, u0, stt, it, ru, None, stream=stream)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); sol.solve_device(r, None, None, u0, stt, it, ru, None, stream=stream); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        return dict(ms=ms, solves_per_s=B / (ms * 1e-3), status=stt.cpu().numpy(), iters=it.cpu().numpy(), rho_updates=ru.cpu().numpy(),
+                    u0=u0.cpu().numpy())
+
+    def cpu_batch(N, recs, gap_mode=0, **st):
+        mb = O.MpcBatch(O.default_cfg(N, gap_mode), O.default_settings(warm_start=0, **st), recs.shape[0])
+        mb.solve(recs[: min(256, len(recs))], want_xy=False)
+        r = mb.solve(recs, want_xy=True)
+        return r, mb.threads
+
+    def parity(g, o, N):
+        ok = o["status"] > 0
+        u0o = o["x"][:, 3 * (N + 1):3 * (N + 1) + 2]
+        return {"status_equal": bool((g["status"] == o["status"]).all()), "iters_equal": bool((g["iters"] == o["iters"]).all()),
+                "max_abs_du0": float(np.abs(g["u0"][ok] - u0o[ok]).max()) if ok.any() else None, "n": int(len(ok)), "n_solved": int(ok.sum())}
+
+    # ---- config 1: single QP following skirk, full pipeline per cycle, sequential, warm start ------------------
+    xy, ori = W.skirk_waypoints()
+    n1 = 500 if not args.quick else 60
+    free_scan = np.full(W.SCAN_BEAMS, 10.0, dtype=np.float32)
+    mpc = M.HostMPC(N_HORIZON)
+    mpc.update_scan(amin, amax, inc, free_scan)
+    orc = O.MpcBatch(O.default_cfg(N_HORIZON), O.default_settings(warm_start=1), 1, 1)
+    lat_g, lat_c, lat_plan, du0, steer_g, steer_c = [], [], [], [], 0.0, 0.0
+    for i in range(n1):
+        pose = W.yaw_pose(float(xy[i, 0]), float(xy[i, 1]), float(ori[i]))
+        t0 = time.perf_counter()
+        idx, path, valid, bg = M.host_plan(pose, amin, amax, inc, free_scan, xy)
+        lat_plan.append((time.perf_counter() - t0) * 1e6)
+        if idx < 0:
+            continue
+        state = np.array([pose[0], pose[1], float(ori[i])])
+        t0 = time.perf_counter()
+        g = mpc.update(state, [4.5, steer_g], path)
+        lat_g.append((time.perf_counter() - t0) * 1e6)
+        rec = np.concatenate([state, [4.5, steer_c], g["l1"], g["l2"], path[:N_HORIZON].reshape(-1)])[None, :]
+        t0 = time.perf_counter()
+        o = orc.solve(rec, warm=True)
+        lat_c.append((time.perf_counter() - t0) * 1e6)
+        uo = o["x"][0][3 * (N_HORIZON + 1):3 * (N_HORIZON + 1) + 2]
+        if g["status"] == 1 and o["status"][0] == 1:
+            du0.append(np.abs(g["inputs"][0] - uo).max())
+            steer_g, steer_c = float(g["inputs"][0, 1]), float(uo[1])
+    pct = lambda a: {"p50": float(np.percentile(a, 50)), "p90": float(np.percentile(a, 90)), "p99": float(np.percentile(a, 99))}
+    report["config1_single_qp_skirk"] = {"cycles": len(lat_g), "gpu_MPC_Update_us": pct(lat_g[5:]), "cpu_oracle_solve_us": pct(lat_c[5:]),
+                                         "plan_cycle_us (grid fill host + collision check GPU + selection)": pct(lat_plan[5:]),
+                                         "max_abs_du0_vs_oracle": float(np.max(du0)) if du0 else None,
+                                         "note": "GPU = C++ MPC::Update through f110_mpc_solve_host (B=1, H2D+kernel+D2H+sync); CPU = oracle update+solve only"}
+
+    # ---- config 2: 20 mini-paths + grid check + QP per surviving path (and the 10 CSV paths) --------------------
+    S2 = 256 if not args.quick else 32
+    poses, yaws, scans = W.scene_batch(S2, seed=20240902)
+    grids = np.zeros((S2, 10000), dtype=np.float32); offs = np.zeros((S2, 2), dtype=np.float32); rots = np.zeros((S2, 4))
+    for s_ in range(S2):
+        grids[s_], offs[s_] = M.host_fill_grid(poses[s_], amin, amax, inc, scans[s_])
+        rots[s_] = M.host_car_to_world_R(poses[s_])
+    c2 = {}
+    for name, table in (("steer19_P20", np.ascontiguousarray(W.traj_table(steer_discrete=19)[:, :, :2])),
+                        ("csv10 (local_traj_50.csv, axes swapped to x-forward)", np.ascontiguousarray(W.reference_data()["local_traj10_xy"]))):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dg, do, dr, dp, dt_ = t(grids), t(offs), t(rots), t(poses[:, :2].copy()), t(table)
+        P = table.shape[0]
+        dv = torch.empty(S2, P, dtype=torch.uint8, device=dev); df = torch.empty(S2, P, dtype=torch.int32, device=dev)
+        de = torch.empty(S2, P, 2, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            M.collision_check_device(dg, do, dr, dp, dt_, dv, df, de, stream=stream)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            M.collision_check_device(dg, do, dr, dp, dt_, dv, df, de, stream=stream)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        valid = dv.cpu().numpy(); endw = de.cpu().numpy()
+        mism = 0
+        t0 = time.perf_counter()
+        for s_ in range(S2):
+            v, f, e = O.collision_check(grids[s_], 100, 0.1, offs[s_], rots[s_], poses[s_, :2], table)
+            mism += int((v != valid[s_]).sum()) + int((e.view(np.uint32) != endw[s_].view(np.uint32)).sum())
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        c2[name] = {"scenes": S2, "paths": P, "valid_paths": int(valid.sum()), "bit_mismatches_vs_oracle": mism, "gpu_check_ms": ms,
+                    "cpu_oracle_check_ms_1thread": cpu_ms, "algorithmic_bytes": int(S2 * P * 50 * 20 + S2 * P * 13),
+                    "achieved_GBps": (S2 * P * 50 * 20 + S2 * P * 13) / (ms * 1e-3) / 1e9}
+        if name.startswith("steer19"):
+            recs = []
+            for s_ in range(S2):
+                for pidx in np.nonzero(valid[s_])[0]:
+                    ref = np.zeros((N_HORIZON, 3)); ref[:, :2] = W.path_to_world(table[pidx, :N_HORIZON], poses[s_, 0], poses[s_, 1], yaws[s_])
+                    recs.append(np.concatenate([[poses[s_, 0], poses[s_, 1], yaws[s_]], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
+            recs = np.array(recs)
+            g = gpu_batch_time(N_HORIZON, recs)
+            o, thr = cpu_batch(N_HORIZON, recs)
+            c2[name]["qp_per_surviving_path"] = {"qps": len(recs), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"],
+                                                 "cpu_solves_per_s": len(recs) / o["seconds"], "cpu_threads": thr, "parity": parity(g, o, N_HORIZON)}
+    report["config2_minipaths_grid_check"] = c2
+
+    # ---- config 3: laser-gap half-plane constrained, B = 1024 ------------------------------------------------------
+    B3 = 1024 if not args.quick else 128
+    rng = np.random.default_rng(20240903)
+    recs3 = W.tracking_batch(B3, N_HORIZON, seed=20240903)
+    n_gap = 0
+    for b_ in range(B3):
+        r = rng.uniform(0.5, 2.8, W.SCAN_BEAMS).astype(np.float32)
+        for _ in range(rng.integers(1, 4)):
+            a = rng.integers(150, 880); w = rng.integers(8, 201)
+            r[a:a + w] = rng.uniform(3.5, 10.0)
+        ok, l1, l2, _ = M.host_find_half_spaces(recs3[b_, :3], amin, amax, inc, r)
+        if ok:
+            recs3[b_, 5:8] = l1; recs3[b_, 8:11] = l2; n_gap += 1
+    c3 = {"B": B3, "scans_with_gap": n_gap}
+    for mode, label in ((0, "as_shipped (gap bounds +-1e30)"), (1, "gap_enabled (lower = -l(2))")):
+        g = gpu_batch_time(N_HORIZON, recs3, gap_mode=mode)
+        o, thr = cpu_batch(N_HORIZON, recs3, gap_mode=mode)
+        c3[label] = {"gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B3 / o["seconds"], "cpu_threads": thr,
+                     "parity": parity(g, o, N_HORIZON), "status_hist": {str(k): int(v) for k, v in zip(*np.unique(g["status"], return_counts=True))}}
+    report["config3_gap_constrained"] = c3
+
+    # ---- config 4: 7 lanes x 20 paths x 64 scenarios = 8960 QPs (1 GPU here; bench.py --gpus N shards) ------------
+    head = W.reference_data()["skirk_heading"]
+    table20 = W.traj_table(steer_discrete=19)
+    recs4 = []
+    n_sc = 64 if not args.quick else 8
+    for sc in range(n_sc):
+        i = int(sc * (500 / 64))
+        for lane in range(7):
+            nx, ny = -np.sin(head[i]), np.cos(head[i])
+            x, y, yaw = float(xy[i, 0]) + lane * 0.25 * nx, float(xy[i, 1]) + lane * 0.25 * ny, float(ori[i])
+            for pidx in range(20):
+                ref = np.zeros((N_HORIZON, 3)); ref[:, :2] = W.path_to_world(table20[pidx, :N_HORIZON, :2], x, y, yaw)
+                recs4.append(np.concatenate([[x, y, yaw], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
+    recs4 = np.array(recs4)
+    g = gpu_batch_time(N_HORIZON, recs4)
+    o, thr = cpu_batch(N_HORIZON, recs4)
+    report["config4_7lanes_20paths_64scenarios"] = {"qps": len(recs4), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"],
+                                                    "cpu_solves_per_s": len(recs4) / o["seconds"], "cpu_threads": thr, "parity": parity(g, o, N_HORIZON)}
+
+    # ---- config 5: horizon sweep, 4096 QPs per GPU ----------------------------------------------------------------------
+    peak = M.fp64_fma_peak_tflops(0)
+    c5 = {"fp64_fma_peak_tflops_measured": peak}
+    B5 = 4096 if not args.quick else 512
+    for N in (10, 20, 30, 50, 100):
+        recs5 = W.tracking_batch(B5, N, seed=20240905)
+        g = gpu_batch_time(N, recs5)
+        o, thr = cpu_batch(N, recs5)
+        fl = float(flops_per_qp(N, g["iters"], g["rho_updates"]).sum())
+        c5["N=%d" % N] = {"qps": B5, "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B5 / o["seconds"],
+                          "cpu_threads": thr, "speedup_vs_host": g["solves_per_s"] / (B5 / o["seconds"]), "mean_iters": float(g["iters"].mean()),
+                          "algorithmic_tflops": fl / (g["ms"] * 1e-3) / 1e12, "fp64_roofline_frac": fl / (g["ms"] * 1e-3) / 1e12 / peak,
+                          "parity": parity(g, o, N)}
+    report["config5_horizon_sweep"] = c5
+    out = args.configs_out or os.path.join(ROOT, "gpurun_out", "configs.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(report, open(out, "w"), indent=1)
+    print(json.dumps({"configs_report": out}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,7 +526,12 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--skip-extras", action="store_true",
                     help="only the device-timed region (no e2e / latency / CPU-baseline legs): the command ncu wraps")
+    ap.add_argument("--configs", action="store_true", help="measure the five BASELINE.json configs (report file, not the bench line)")
+    ap.add_argument("--configs-out", default=None)
+    ap.add_argument("--quick", action="store_true", help="smaller --configs run")
     args = ap.parse_args()
+    if args.configs:
+        return run_configs(args)
     if args.impl == "reference":
         return main_reference(args)
     return main_product(args)

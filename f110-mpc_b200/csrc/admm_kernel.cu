@@ -58,6 +58,16 @@ __device__ __forceinline__ double limit_scaling(double v) {
   v = v < MIN_SCALING ? 1.0 : v;
   return v > MAX_SCALING ? MAX_SCALING : v;
 }
+// 1/sqrt(x) for x in [1e-4, 1e4] (the range limit_scaling leaves): float seed + two Newton steps, no special cases.
+// Within ~2 ulp of 1.0 / sqrt(x), which is all the Ruiz scaling vectors need.
+__device__ __forceinline__ double rsqrt_scaling(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return dmin(dmax(v, lo), hi); }
 
 // ---- cross-stage communication ------------------------------------------------------------------------------
@@ -221,13 +231,12 @@ constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
 template <int NLEV, int WPQ, bool LASTFULL>
 __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
-  extern __shared__ double smem_all[];
+  extern __shared__ __align__(16) double smem_all[];
   constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
   const int qp = blockIdx.x;
   const int k = threadIdx.x;
-  constexpr int SM_COEF = NLEV * 18 * T;   // alpha(9), gamma(9) per level, element-major, stage fastest
-  double* sm_coef = smem_all + k;
-  double* sm_binv = sm_coef + SM_COEF;
+  constexpr int SM_COEF = NLEV * 18 * T;   // -alpha(9), -gamma(9) per level as 9 double2 pairs, pair-major, stage fastest
+  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;   // + 3 pairs for the final block inverse
   Comm<WPQ> cm(smem_all + SM_COEF + 6 * T, k);
   double* scr = p.scratch + (size_t)qp * (24 * T) + k;
 
@@ -247,14 +256,15 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   {
     // Model::Linearize, model.cpp:42-55 (operation order kept)
     const double L = p.wheelbase, dt = p.dt;
-    const double so = sin(x0[2]), co = cos(x0[2]);
-    const double cs = cos(slin);
-    const double pw = pow(cs, -2.0);
+    double so, co, ss, cs;
+    sincos(x0[2], &so, &co);
+    sincos(slin, &ss, &cs);
+    const double pw = 1.0 / (cs * cs);   // pow(cos, -2) of model.cpp:51,55 to within 1 ulp
     md.a02 = -1.0 * vlin * so * dt;
     md.a12 = vlin * co * dt;
     md.b00 = co * dt;
     md.b10 = so * dt;
-    md.b20 = tan(slin) * dt / L;
+    md.b20 = (ss / cs) * dt / L;         // tan(steer), model.cpp:50, to within 1 ulp
     md.b21 = vlin * pw * dt / L;
     Cv[0] = vlin * x0[2] * so * dt;
     Cv[1] = -1.0 * vlin * x0[2] * co * dt;
@@ -365,15 +375,15 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         for (int j = 0; j < 2; ++j) { tu[j] = 1.0; tb[j] = 1.0; }
       }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) dx[j] *= rsqrt(limit_scaling(tx[j]));
+      for (int j = 0; j < 3; ++j) dx[j] *= rsqrt_scaling(limit_scaling(tx[j]));
 #pragma unroll
-      for (int j = 0; j < 2; ++j) du[j] *= rsqrt(limit_scaling(tu[j]));
+      for (int j = 0; j < 2; ++j) du[j] *= rsqrt_scaling(limit_scaling(tu[j]));
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ed[i] *= rsqrt(limit_scaling(td[i]));
+      for (int i = 0; i < 3; ++i) ed[i] *= rsqrt_scaling(limit_scaling(td[i]));
 #pragma unroll
-      for (int r = 0; r < 2; ++r) eg[r] *= rsqrt(limit_scaling(tg[r]));
+      for (int r = 0; r < 2; ++r) eg[r] *= rsqrt_scaling(limit_scaling(tg[r]));
 #pragma unroll
-      for (int j = 0; j < 2; ++j) eb[j] *= rsqrt(limit_scaling(tb[j]));
+      for (int j = 0; j < 2; ++j) eb[j] *= rsqrt_scaling(limit_scaling(tb[j]));
       // cost normalisation: c_temp = 1 / max(mean column norm of P, ||q||_inf)
       double psum = 0.0, qn = 0.0;
       if (act) {
@@ -576,15 +586,23 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
           Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
           Lm[e] = vlo ? -Ln[e] : 0.0;
           Um[e] = vhi ? -Un[e] : 0.0;
-          sm_coef[(lev * 18 + e) * T] = vlo ? alp[e] : 0.0;
-          sm_coef[(lev * 18 + 9 + e) * T] = vhi ? gam[e] : 0.0;
+          alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
+          gam[e] = vhi ? -gam[e] : 0.0;
+        }
+        // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+          sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+          sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
         }
       }
       {
         double Bi[9];
         inv_spd3(Bm, Bi);
-        sm_binv[0 * T] = Bi[0]; sm_binv[1 * T] = Bi[1]; sm_binv[2 * T] = Bi[2];
-        sm_binv[3 * T] = Bi[4]; sm_binv[4 * T] = Bi[5]; sm_binv[5 * T] = Bi[8];
+        sm_pair[(NLEV * 9 + 0) * T] = make_double2(Bi[0], Bi[1]);
+        sm_pair[(NLEV * 9 + 1) * T] = make_double2(Bi[2], Bi[4]);
+        sm_pair[(NLEV * 9 + 2) * T] = make_double2(Bi[5], Bi[8]);
       }
       cm.sync();
     }
@@ -641,20 +659,23 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         const int h = 1 << lev;
         double lo[3], hi[3];
         cm.template both<3>(r, lo, hi, h);
-        const double* cf = sm_coef + (lev * 18) * T;
+        const double2* cf = sm_pair + (lev * 9) * T;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          double acc0 = cf[(3 * i + 0) * T] * lo[0] + cf[(3 * i + 1) * T] * lo[1];
-          double acc1 = cf[(9 + 3 * i + 0) * T] * hi[0] + cf[(9 + 3 * i + 1) * T] * hi[1];
-          acc0 += cf[(3 * i + 2) * T] * lo[2];
-          acc1 += cf[(9 + 3 * i + 2) * T] * hi[2];
-          r[i] = r[i] - acc0 - acc1;
+          const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
+          double a = fma(c0.x, lo[0], r[i]);
+          double b = c1.y * hi[0];
+          a = fma(c0.y, lo[1], a);
+          b = fma(c2.x, hi[1], b);
+          a = fma(c1.x, lo[2], a);
+          b = fma(c2.y, hi[2], b);
+          r[i] = a + b;
         }
       }
       double xt[3];
       {
-        const double b0 = sm_binv[0 * T], b1 = sm_binv[1 * T], b2 = sm_binv[2 * T];
-        const double b4 = sm_binv[3 * T], b5 = sm_binv[4 * T], b8 = sm_binv[5 * T];
+        const double2 q0 = sm_pair[(NLEV * 9 + 0) * T], q1 = sm_pair[(NLEV * 9 + 1) * T], q2 = sm_pair[(NLEV * 9 + 2) * T];
+        const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
         xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
         xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
         xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
