@@ -31,13 +31,12 @@ struct f110_mpc_solver {
   int last_launches = 0;
   double* d_state = nullptr;    // warm-start slots
   double* d_scratch = nullptr;  // per-QP scratch lines (scaling vectors, previous iterate)
-  // staging for the host-buffer entry
+  // staging for the host-buffer entry: one device block [u0 | status | iters | x | y] so results come back in
+  // one copy, plus a small pinned mirror used for latency-critical small batches
   double* d_recs = nullptr;
-  double* d_x = nullptr;
-  double* d_y = nullptr;
-  double* d_u0 = nullptr;
-  int32_t* d_status = nullptr;
-  int32_t* d_iters = nullptr;
+  unsigned char* d_out = nullptr;
+  unsigned char* h_pin = nullptr;   // pinned: records of <= kSmallBatch QPs, then their outputs
+  size_t out_bytes = 0;
   cudaStream_t stream = nullptr;
 };
 
@@ -114,8 +113,8 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaSetDevice(s->device);
   cudaFree(s->d_state);
   cudaFree(s->d_scratch);
-  cudaFree(s->d_recs); cudaFree(s->d_x); cudaFree(s->d_y); cudaFree(s->d_u0);
-  cudaFree(s->d_status); cudaFree(s->d_iters);
+  cudaFree(s->d_recs); cudaFree(s->d_out);
+  if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -162,28 +161,56 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_host: count exceeds max_batch");
   if (count == 0) return F110_OK;
   const int N = s->cfg.horizon, n = 5 * N + 3, m = 7 * N + 5;
-  CUDA_TRY(cudaSetDevice(s->device));
-  if (!s->d_recs) {
-    const size_t B = s->max_batch;
-    CUDA_TRY(cudaMalloc(&s->d_recs, B * f110_mpc_record_doubles(N) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&s->d_x, B * n * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&s->d_y, B * m * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&s->d_u0, B * 2 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&s->d_status, B * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_iters, B * sizeof(int32_t)));
-  }
   const int rd = f110_mpc_record_doubles(N);
   if (rec_stride < rd) return fail(F110_ERR_ARG, "f110_mpc_solve_host: record stride too small");
-  CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rd * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
-                             cudaMemcpyHostToDevice, s->stream));
-  int rc = f110_mpc_solve_device(s, count, s->d_recs, rd, x ? s->d_x : nullptr, y ? s->d_y : nullptr, s->d_u0, s->d_status,
-                                 s->d_iters, nullptr, nullptr, s->stream);
+  constexpr int kSmallBatch = 16;
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->d_recs) {
+    const size_t B = s->max_batch > kSmallBatch ? s->max_batch : kSmallBatch;  // the compact small-batch layout needs kSmallBatch slots
+    s->out_bytes = B * (2 * sizeof(double) + 2 * sizeof(int32_t)) + 16 + B * (size_t)(n + m) * sizeof(double);
+    CUDA_TRY(cudaMalloc(&s->d_recs, B * rd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_out, s->out_bytes));
+    CUDA_TRY(cudaHostAlloc(&s->h_pin, kSmallBatch * (size_t)(rd + 2 + 1 + n + m) * sizeof(double) + 64, cudaHostAllocDefault));
+  }
+  const bool small = count <= kSmallBatch;
+  // small batches use a compact layout sized for kSmallBatch so the whole result is ONE device-to-host copy
+  const size_t cap = small ? (size_t)kSmallBatch : (size_t)s->max_batch;
+  const size_t o_status = cap * 2 * sizeof(double), o_iters = o_status + cap * sizeof(int32_t);
+  const size_t o_x = (o_iters + cap * sizeof(int32_t) + 15) / 16 * 16, o_y = o_x + cap * n * sizeof(double);
+  double* d_u0 = reinterpret_cast<double*>(s->d_out);
+  int32_t* d_status = reinterpret_cast<int32_t*>(s->d_out + o_status);
+  int32_t* d_iters = reinterpret_cast<int32_t*>(s->d_out + o_iters);
+  double* d_x = reinterpret_cast<double*>(s->d_out + o_x);
+  double* d_y = reinterpret_cast<double*>(s->d_out + o_y);
+  if (small) {
+    // latency path: records staged through pinned memory (true async DMA)
+    double* hp = reinterpret_cast<double*>(s->h_pin);
+    for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rd, recs + (size_t)b * rec_stride, rd * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(s->d_recs, hp, (size_t)count * rd * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  } else {
+    CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rd * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
+                               cudaMemcpyHostToDevice, s->stream));
+  }
+  int rc = f110_mpc_solve_device(s, count, s->d_recs, rd, x ? d_x : nullptr, y ? d_y : nullptr, d_u0, d_status, d_iters, nullptr, nullptr,
+                                 s->stream);
   if (rc) return rc;
-  if (x) CUDA_TRY(cudaMemcpyAsync(x, s->d_x, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (y) CUDA_TRY(cudaMemcpyAsync(y, s->d_y, (size_t)count * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (u0) CUDA_TRY(cudaMemcpyAsync(u0, s->d_u0, (size_t)count * 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (status) CUDA_TRY(cudaMemcpyAsync(status, s->d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
-  if (iters) CUDA_TRY(cudaMemcpyAsync(iters, s->d_iters, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (small) {
+    unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rd * sizeof(double);
+    const size_t bytes = y ? o_y + (size_t)count * m * sizeof(double) : (x ? o_x + (size_t)count * n * sizeof(double) : o_x);
+    CUDA_TRY(cudaMemcpyAsync(ho, s->d_out, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (u0) std::memcpy(u0, ho, (size_t)count * 2 * sizeof(double));
+    if (status) std::memcpy(status, ho + o_status, (size_t)count * sizeof(int32_t));
+    if (iters) std::memcpy(iters, ho + o_iters, (size_t)count * sizeof(int32_t));
+    if (x) std::memcpy(x, ho + o_x, (size_t)count * n * sizeof(double));
+    if (y) std::memcpy(y, ho + o_y, (size_t)count * m * sizeof(double));
+    return F110_OK;
+  }
+  if (x) CUDA_TRY(cudaMemcpyAsync(x, d_x, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (y) CUDA_TRY(cudaMemcpyAsync(y, d_y, (size_t)count * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (u0) CUDA_TRY(cudaMemcpyAsync(u0, d_u0, (size_t)count * 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (iters) CUDA_TRY(cudaMemcpyAsync(iters, d_iters, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return F110_OK;
 }
