@@ -93,6 +93,10 @@ struct Comm<1> {
 #pragma unroll
     for (int i = 0; i < K; ++i) { lo[i] = __shfl_up_sync(FULL, v[i], h); hi[i] = __shfl_down_sync(FULL, v[i], h); }
   }
+  template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {  // partner k ^ h
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_xor_sync(FULL, v[i], h);
+  }
   __device__ __forceinline__ double rmax(double v) { return wmax(v); }
   __device__ __forceinline__ double rsum(double v) { return wsum(v); }
   __device__ __forceinline__ bool any(bool b) { return __any_sync(FULL, b); }
@@ -134,6 +138,12 @@ struct Comm {
     const int sl = tid - h >= 0 ? tid - h : tid, sh = tid + h < T ? tid + h : tid;
 #pragma unroll
     for (int i = 0; i < K; ++i) { lo[i] = b[i * T + sl]; hi[i] = b[i * T + sh]; }
+  }
+  template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid ^ h;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
   }
   __device__ __forceinline__ double* rslot(double v) {
     double* r = rb + rph * WPQ;
@@ -235,9 +245,11 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
   const int qp = blockIdx.x;
   const int k = threadIdx.x;
-  constexpr int SM_COEF = NLEV * 18 * T;   // -alpha(9), -gamma(9) per level as 9 double2 pairs, pair-major, stage fastest
-  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;   // + 3 pairs for the final block inverse
-  Comm<WPQ> cm(smem_all + SM_COEF + 6 * T, k);
+  // PCR multipliers as double2 pairs, pair-major, stage fastest: 9 pairs (-alpha, -gamma) for each of the first
+  // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
+  constexpr int SM_PAIRS = NLEV * 9 - 1;
+  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;
+  Comm<WPQ> cm(smem_all + 2 * SM_PAIRS * T, k);
   double* scr = p.scratch + (size_t)qp * (24 * T) + k;
 
   const int N = p.N;
@@ -589,20 +601,31 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
           alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
           gam[e] = vhi ? -gam[e] : 0.0;
         }
-        // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+        if (lev < NLEV - 1) {
+          // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
-          sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
-          sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+          for (int i = 0; i < 3; ++i) {
+            sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+            sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+            sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+          }
+        } else {
+          // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
+          // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
+          double one[10];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
+          one[9] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) sm_pair[(lev * 9 + q) * T] = make_double2(one[2 * q], one[2 * q + 1]);
         }
       }
       {
         double Bi[9];
         inv_spd3(Bm, Bi);
-        sm_pair[(NLEV * 9 + 0) * T] = make_double2(Bi[0], Bi[1]);
-        sm_pair[(NLEV * 9 + 1) * T] = make_double2(Bi[2], Bi[4]);
-        sm_pair[(NLEV * 9 + 2) * T] = make_double2(Bi[5], Bi[8]);
+        sm_pair[(NLEV * 9 - 4 + 0) * T] = make_double2(Bi[0], Bi[1]);
+        sm_pair[(NLEV * 9 - 4 + 1) * T] = make_double2(Bi[2], Bi[4]);
+        sm_pair[(NLEV * 9 - 4 + 2) * T] = make_double2(Bi[5], Bi[8]);
       }
       cm.sync();
     }
@@ -655,7 +678,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
       // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
 #pragma unroll
-      for (int lev = 0; lev < NLEV; ++lev) {
+      for (int lev = 0; lev < NLEV - 1; ++lev) {
         const int h = 1 << lev;
         double lo[3], hi[3];
         cm.template both<3>(r, lo, hi, h);
@@ -672,9 +695,19 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
           r[i] = a + b;
         }
       }
+      {  // top level: single neighbour k ^ h
+        constexpr int h = 1 << (NLEV - 1);
+        double nb[3];
+        cm.template xr<3>(r, nb, h);
+        const double2* cf = sm_pair + ((NLEV - 1) * 9) * T;
+        const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
+        r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
+        r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
+        r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
+      }
       double xt[3];
       {
-        const double2 q0 = sm_pair[(NLEV * 9 + 0) * T], q1 = sm_pair[(NLEV * 9 + 1) * T], q2 = sm_pair[(NLEV * 9 + 2) * T];
+        const double2 q0 = sm_pair[(NLEV * 9 - 4 + 0) * T], q1 = sm_pair[(NLEV * 9 - 4 + 1) * T], q2 = sm_pair[(NLEV * 9 - 4 + 2) * T];
         const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
         xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
         xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
@@ -992,7 +1025,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 template <int NLEV, int WPQ, bool LASTFULL>
 static cudaError_t launch_one(const KParams& p, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
-  size_t smem = (size_t)(NLEV * 18 + 6) * T * sizeof(double);
+  size_t smem = (size_t)(2 * (NLEV * 9 - 1)) * T * sizeof(double);
   if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
