@@ -195,14 +195,15 @@ def main_product(args):
     d_valid = torch.empty(S, PATHS, dtype=torch.uint8, device=dev)
     d_free = torch.empty(S, PATHS, dtype=torch.int32, device=dev)
     d_endw = torch.empty(S, PATHS, 2, dtype=torch.float32, device=dev)
+    d_packed = torch.empty(B, 4, dtype=torch.float64, device=dev) if world > 1 else None   # row gathered across GPUs
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         M.collision_check_device(d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free, d_endw, stream=stream)
-        sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
+        sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream, packed=d_packed)
         if world > 1:   # the one collective: chosen controls of every rank, in batch order
-            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B, sizes=[B] * world)
+            SH.gather_results(d_packed, world, max_rows=B, sizes=[B] * world)
 
     def barrier():
         if world > 1:
@@ -224,10 +225,10 @@ def main_product(args):
         ev[i][0].record()
         M.collision_check_device(d_grid, d_off, d_rot, d_pose, d_tab, d_valid, d_free, d_endw, stream=stream)
         kev[i][0].record()
-        sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream)
+        sol.solve_device(d_recs, None, None, d_u0, d_status, d_iters, d_rhoup, None, stream=stream, packed=d_packed)
         kev[i][1].record()
         if world > 1:   # the one collective: chosen controls of every rank, in batch order
-            SH.gather_results(SH.pack_result(d_u0, d_status, d_iters), world, max_rows=B, sizes=[B] * world)
+            SH.gather_results(d_packed, world, max_rows=B, sizes=[B] * world)
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

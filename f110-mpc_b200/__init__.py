@@ -41,7 +41,7 @@ class SolverSettings(C.Structure):
 EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
            "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
-           "f110_mpc_last_launches", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma"]
+           "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma"]
 
 
 def build(force=False, verbose=False):
@@ -78,6 +78,7 @@ def lib():
         L.f110_mpc_destroy.argtypes = [vp]
         L.f110_mpc_reset.argtypes = [vp]
         L.f110_mpc_last_launches.argtypes = [vp]
+        L.f110_mpc_set_packed_output.argtypes = [vp, vp]
         L.f110_mpc_solve_host.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip]
         L.f110_mpc_solve_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.f110_collision_check_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 9
@@ -157,9 +158,12 @@ class MpcSolver:
         return dict(x=x, y=y, u0=u0, status=status, iters=iters)
 
     def solve_device(self, recs, x=None, y=None, u0=None, status=None, iters=None, rho_updates=None, info=None,
-                     stream=None, count=None):
-        """recs etc. are torch CUDA tensors (float64 / int32, contiguous)."""
+                     stream=None, count=None, packed=None):
+        """recs etc. are torch CUDA tensors (float64 / int32, contiguous).  packed: optional (B,4) f64 rows
+        (u0_v, u0_steer, status, iters) written by the solve kernel for the multi-GPU gather."""
         B = recs.shape[0] if count is None else count
+        if packed is not None:
+            _check(lib().f110_mpc_set_packed_output(self._h, _tp(packed)), "f110_mpc_set_packed_output")
         sp = C.c_void_p(stream) if stream else None
         _check(lib().f110_mpc_solve_device(self._h, B, _tp(recs), recs.stride(0), _tp(x), _tp(y), _tp(u0), _tp(status),
                                            _tp(iters), _tp(rho_updates), _tp(info), sp), "f110_mpc_solve_device")

@@ -988,6 +988,10 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       double* io = p.info + 4 * (size_t)qp;
       io[0] = obj; io[1] = pri_res; io[2] = dua_res; io[3] = rho_bar;
     }
+    if (p.packed) {
+      double* po = p.packed + 4 * (size_t)qp;
+      po[0] = has_sol ? s.u[0] : qnan; po[1] = has_sol ? s.u[1] : qnan; po[2] = (double)status; po[3] = (double)iter;
+    }
   }
   if (slot) {
     // scaled iterates for the next warm start; zeros (cold start) when there is no solution

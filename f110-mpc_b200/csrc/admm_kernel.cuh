@@ -29,6 +29,7 @@ struct KParams {
   int32_t* iters;     // [B] or null
   int32_t* rho_updates;  // [B] or null
   double* info;       // [B][4] or null
+  double* packed;     // [B][4] = (u0_v, u0_steer, status, iters) as doubles, the row that is gathered across GPUs; or null
   double* state;      // [B][state_doubles(N)] warm-start slots (scaled iterates x, z, y + rho + flag) or null
   double* scratch;    // [B][SCRATCH_DOUBLES]
 };

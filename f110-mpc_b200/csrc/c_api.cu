@@ -37,6 +37,7 @@ struct f110_mpc_solver {
   unsigned char* d_out = nullptr;
   unsigned char* h_pin = nullptr;   // pinned: records of <= kSmallBatch QPs, then their outputs
   size_t out_bytes = 0;
+  double* d_packed_next = nullptr;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
   cudaStream_t stream = nullptr;
 };
 
@@ -128,6 +129,12 @@ int f110_mpc_reset(f110_mpc_solver* s) {
 
 int f110_mpc_last_launches(const f110_mpc_solver* s) { return s ? s->last_launches : 0; }
 
+int f110_mpc_set_packed_output(f110_mpc_solver* s, double* d_packed) {
+  if (!s) return fail(F110_ERR_ARG, "f110_mpc_set_packed_output: null solver");
+  s->d_packed_next = d_packed;
+  return F110_OK;
+}
+
 int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
                           double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
                           void* cuda_stream) {
@@ -146,7 +153,8 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
   p.max_iter = s->st.max_iter; p.check_termination = s->st.check_termination; p.scaling = s->st.scaling;
   p.adaptive_rho = s->st.adaptive_rho; p.adaptive_rho_interval = s->st.adaptive_rho_interval; p.warm_start = s->st.warm_start;
   p.recs = d_recs; p.x_out = d_x; p.y_out = d_y; p.u0_out = d_u0; p.status = d_status; p.iters = d_iters;
-  p.rho_updates = d_rho_updates; p.info = d_info;
+  p.rho_updates = d_rho_updates; p.info = d_info; p.packed = s->d_packed_next;
+  s->d_packed_next = nullptr;
   p.state = s->st.warm_start ? s->d_state : nullptr;
   p.scratch = s->d_scratch;
   CUDA_TRY(cudaSetDevice(s->device));

@@ -39,8 +39,13 @@ def gather_results(local, world, max_rows=None, sizes=None):
         dist.all_gather(all_counts, counts)
         sizes = [int(c.item()) for c in all_counts]
     width = max_rows or max(sizes)
-    padded = torch.zeros(width, local.shape[1], dtype=local.dtype, device=local.device)
-    padded[: local.shape[0]] = local
+    if local.shape[0] == width and local.is_contiguous():
+        padded = local                      # equal shards: gather straight from the kernel's output rows
+    else:
+        padded = torch.zeros(width, local.shape[1], dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
     buf = torch.empty(world * width, local.shape[1], dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf, padded)
+    if all(sz == width for sz in sizes):
+        return buf
     return torch.cat([buf[r * width: r * width + sizes[r]] for r in range(world)], dim=0)

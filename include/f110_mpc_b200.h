@@ -111,6 +111,10 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
 
 /* Forget the warm-start state of every slot (next solve starts from x = z = y = 0, rho = settings.rho). */
 int f110_mpc_reset(f110_mpc_solver* s);
+/* Multi-GPU helper: the NEXT f110_mpc_solve_device call also writes count x 4 doubles
+ * (u0_v, u0_steer, status, iters) to d_packed — the row each rank contributes to the final gather of the
+ * chosen controls, produced by the solve kernel itself so no packing kernel is needed.  One-shot. */
+int f110_mpc_set_packed_output(f110_mpc_solver* s, double* d_packed);
 /* Number of kernels the last solve call launched (for launch accounting). */
 int f110_mpc_last_launches(const f110_mpc_solver* s);
 
