@@ -38,10 +38,19 @@ class SolverSettings(C.Structure):
                 ("warm_start", C.c_int32), ("scaled_termination", C.c_int32), ("reserved", C.c_int32)]
 
 
+class CycleConfig(C.Structure):
+    """f110_cycle_config"""
+    _fields_ = [("n_beams", C.c_int32), ("angle_min", C.c_float), ("angle_max", C.c_float), ("angle_increment", C.c_float),
+                ("occ_size", C.c_int32), ("occ_discrete", C.c_float), ("occ_dilation", C.c_float),
+                ("follow_gap_thresh", C.c_float), ("fov_divider", C.c_float), ("buffer", C.c_float), ("lookahead", C.c_float),
+                ("use_half_spaces", C.c_int32), ("v_lin", C.c_double)]
+
+
 EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
            "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
-           "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma"]
+           "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma", "f110_cycle_default_config",
+           "f110_cycle_device", "f110_cycle_buffers"]
 
 
 def build(force=False, verbose=False):
@@ -84,6 +93,10 @@ def lib():
         L.f110_collision_check_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 9
         L.f110_collision_check_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [vp] * 8 + [C.c_int]
         L.f110_bench_fp64_fma.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.f110_cycle_default_config.argtypes = [C.POINTER(CycleConfig)]
+        L.f110_cycle_device.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int,
+                                        vp, vp, vp, vp, vp, vp]
+        L.f110_cycle_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
         _lib = L
     return _lib
 
@@ -98,6 +111,16 @@ def default_config(horizon=30, gap_mode=0):
     lib().f110_mpc_default_config(C.byref(c))
     c.horizon = horizon
     c.gap_mode = gap_mode
+    return c
+
+
+def default_cycle_config(**kw):
+    c = CycleConfig()
+    lib().f110_cycle_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
     return c
 
 
@@ -167,6 +190,32 @@ class MpcSolver:
         sp = C.c_void_p(stream) if stream else None
         _check(lib().f110_mpc_solve_device(self._h, B, _tp(recs), recs.stride(0), _tp(x), _tp(y), _tp(u0), _tp(status),
                                            _tp(iters), _tp(rho_updates), _tp(info), sp), "f110_mpc_solve_device")
+
+    def cycle_device(self, cc, pose7, ranges, prev_steer, table_xy, wp_xy, u0, status, iters, chosen, valid=None, stream=None):
+        """Whole planning + control cycle on the device (f110_cycle_device); all arguments are torch CUDA tensors."""
+        S = pose7.shape[0]
+        sp = C.c_void_p(stream) if stream else None
+        _check(lib().f110_cycle_device(self._h, C.byref(cc), S, _tp(pose7), _tp(ranges), _tp(prev_steer), _tp(table_xy),
+                                       table_xy.shape[0], table_xy.shape[1], _tp(wp_xy), wp_xy.shape[0], _tp(u0), _tp(status),
+                                       _tp(iters), _tp(chosen), _tp(valid), sp), "f110_cycle_device")
+
+    def cycle_buffers(self, scenes):
+        """Torch views (no copy) of the device buffers the last cycle filled:
+        dict(grid (S, blocks^2) f32, offset (S,2) f32, l1l2 (S,6) f64, recs (S, 11+3N) f64, best_global (S,) i32)."""
+        import torch
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _check(lib().f110_cycle_buffers(self._h, *[C.byref(p) for p in ptrs]), "f110_cycle_buffers")
+
+        class _Dev:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def view(ptr, shape, typestr):
+            return torch.as_tensor(_Dev(ptr.value, shape, typestr), device="cuda:%d" % self.device)
+        blocks2 = 100 * 100
+        return dict(grid=view(ptrs[0], (scenes, blocks2), "<f4"), offset=view(ptrs[1], (scenes, 2), "<f4"),
+                    l1l2=view(ptrs[2], (scenes, 6), "<f8"), recs=view(ptrs[3], (scenes, record_doubles(self.N)), "<f8"),
+                    best_global=view(ptrs[4], (scenes,), "<i4"))
 
     def reset(self):
         _check(lib().f110_mpc_reset(self._h), "f110_mpc_reset")

@@ -263,6 +263,19 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   const double* rec = p.recs + (size_t)qp * p.stride;
   const double x0[3] = {rec[0], rec[1], rec[2]};
   const double vlin = rec[3], slin = rec[4];
+  if (!(vlin == vlin)) {
+    // NaN linearisation speed marks an empty slot (the planning stage found no valid mini-path for this scene,
+    // project.cpp:115-119): nothing to solve, status stays UNSOLVED
+    if (k == 0) {
+      const double qn = __longlong_as_double(0x7ff8000000000000LL);
+      if (p.u0_out) { p.u0_out[2 * (size_t)qp] = qn; p.u0_out[2 * (size_t)qp + 1] = qn; }
+      if (p.status) p.status[qp] = ST_UNSOLVED;
+      if (p.iters) p.iters[qp] = 0;
+      if (p.rho_updates) p.rho_updates[qp] = 0;
+      if (p.packed) { double* po = p.packed + 4 * (size_t)qp; po[0] = qn; po[1] = qn; po[2] = (double)ST_UNSOLVED; po[3] = 0.0; }
+    }
+    return;
+  }
   Model md;
   double Cv[3];
   {

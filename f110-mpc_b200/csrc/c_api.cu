@@ -37,7 +37,20 @@ struct f110_mpc_solver {
   unsigned char* d_out = nullptr;
   unsigned char* h_pin = nullptr;   // pinned: records of <= kSmallBatch QPs, then their outputs
   size_t out_bytes = 0;
-  double* d_packed_next = nullptr;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
+  double* d_packed_next = nullptr;
+  // f110_cycle_device scratch (allocated on first use, sized for max_batch scenes)
+  struct Cycle {
+    int blocks = 0, paths = 0;
+    float *grid = nullptr, *offset = nullptr, *endw = nullptr;
+    double *rot = nullptr, *pose_xy = nullptr, *state3 = nullptr, *l1l2 = nullptr, *recs = nullptr;
+    uint8_t* valid = nullptr;
+    int32_t *free_cnt = nullptr, *gap = nullptr, *best_global = nullptr;
+    void release() {
+      cudaFree(grid); cudaFree(offset); cudaFree(endw); cudaFree(rot); cudaFree(pose_xy); cudaFree(state3); cudaFree(l1l2);
+      cudaFree(recs); cudaFree(valid); cudaFree(free_cnt); cudaFree(gap); cudaFree(best_global);
+      *this = Cycle();
+    }
+  } cyc;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
   cudaStream_t stream = nullptr;
 };
 
@@ -115,6 +128,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaFree(s->d_state);
   cudaFree(s->d_scratch);
   cudaFree(s->d_recs); cudaFree(s->d_out);
+  s->cyc.release();
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -220,6 +234,81 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   if (iters) CUDA_TRY(cudaMemcpyAsync(iters, d_iters, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return F110_OK;
+}
+
+void f110_cycle_default_config(f110_cycle_config* c) {
+  c->n_beams = 1080;                       // f1tenth simulator convention
+  c->angle_min = -2.35f; c->angle_increment = 4.7f / 1079; c->angle_max = c->angle_min + 1079 * c->angle_increment;
+  c->occ_size = 10; c->occ_discrete = 0.1f; c->occ_dilation = 0.15f;
+  c->follow_gap_thresh = 3.0f; c->fov_divider = 1.5f; c->buffer = 3.0f;
+  c->lookahead = 2.5f;
+  c->use_half_spaces = 1;
+  c->v_lin = 4.5;
+}
+
+int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* d_pose7, const float* d_ranges,
+                      const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy, int n_wp,
+                      double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid, void* cuda_stream) {
+  if (!s || !cc || !d_pose7 || !d_ranges || !d_table_xy || !d_wp_xy || !d_chosen) return fail(F110_ERR_ARG, "f110_cycle_device: null argument");
+  if (scenes < 0 || scenes > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: scenes exceed max_batch");
+  if (paths <= 0 || samples <= 0 || n_wp <= 0 || cc->n_beams <= 0) return fail(F110_ERR_ARG, "f110_cycle_device: bad sizes");
+  s->last_launches = 0;
+  if (scenes == 0) return F110_OK;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int blocks = (int)(cc->occ_size / cc->occ_discrete);           // occupancy_grid.cpp:9
+  const int N = s->cfg.horizon, rd = f110_mpc_record_doubles(N);
+  auto& c = s->cyc;
+  if (c.blocks != blocks || c.paths < paths) {
+    c.release();
+    const size_t B = s->max_batch;
+    CUDA_TRY(cudaMalloc(&c.grid, B * blocks * blocks * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.offset, B * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.endw, B * paths * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.rot, B * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.pose_xy, B * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.state3, B * 3 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.l1l2, B * 6 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.recs, B * rd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.valid, B * paths));
+    CUDA_TRY(cudaMalloc(&c.free_cnt, B * paths * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&c.gap, B * 2 * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&c.best_global, B * sizeof(int32_t)));
+    c.blocks = blocks; c.paths = paths;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // beam count from the float expression of occupancy_grid.cpp:66 / constraints.cpp:118
+  const int num_scans = (int)((cc->angle_max - cc->angle_min) / cc->angle_increment + 1);
+  uint8_t* valid = d_valid ? d_valid : c.valid;
+  cudaError_t e = f110::launch_fill_grid(scenes, blocks, cc->occ_discrete, cc->occ_dilation, cc->n_beams, num_scans, cc->angle_min,
+                                         cc->angle_increment, d_pose7, d_ranges, c.grid, c.offset, st);
+  if (e == cudaSuccess) e = f110::launch_rotation(scenes, d_pose7, c.rot, c.pose_xy, st);
+  if (e == cudaSuccess) e = f110::launch_collision(scenes, paths, samples, blocks, cc->occ_discrete, c.grid, c.offset, c.rot, c.pose_xy,
+                                                   d_table_xy, valid, c.free_cnt, c.endw, st);
+  int launches = 3;
+  if (e == cudaSuccess && cc->use_half_spaces) {
+    e = f110::launch_state_from_pose(scenes, d_pose7, c.state3, st);
+    if (e == cudaSuccess) e = f110::launch_half_spaces(scenes, cc->n_beams, num_scans, cc->angle_min, cc->angle_increment, cc->follow_gap_thresh,
+                                                       cc->fov_divider, cc->buffer, c.state3, d_ranges, c.l1l2, c.gap, st);
+    launches += 2;
+  }
+  if (e == cudaSuccess) e = f110::launch_select_build(scenes, paths, samples, N, rd, n_wp, cc->lookahead, cc->v_lin, d_pose7, c.rot, d_wp_xy,
+                                                      valid, c.endw, d_table_xy, d_prev_steer, cc->use_half_spaces ? c.l1l2 : nullptr, c.recs,
+                                                      d_chosen, c.best_global, st);
+  ++launches;
+  if (e != cudaSuccess) return cuda_fail(e, "f110_cycle_device: kernel launch");
+  const int rc = f110_mpc_solve_device(s, scenes, c.recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
+  s->last_launches += launches;
+  return rc;
+}
+
+int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs, int32_t** d_best_global) {
+  if (!s) return fail(F110_ERR_ARG, "f110_cycle_buffers: null solver");
+  if (d_grid) *d_grid = s->cyc.grid;
+  if (d_offset) *d_offset = s->cyc.offset;
+  if (d_l1l2) *d_l1l2 = s->cyc.l1l2;
+  if (d_recs) *d_recs = s->cyc.recs;
+  if (d_best_global) *d_best_global = s->cyc.best_global;
   return F110_OK;
 }
 

@@ -1,0 +1,269 @@
+// Perception / planning kernels that feed the two hot kernels without a host round trip:
+//
+//   fill_grid_kernel        OccGrid::FillOccGrid                      reference src/occupancy_grid.cpp:55-88
+//   half_spaces_kernel      Constraints::FindHalfSpaces               reference src/constraints.cpp:116-265
+//   select_build_kernel     Trajectory::get_best_global_idx           reference src/trajectory.cpp:81-108
+//                           + best-path argmin + mini-path -> world   reference src/project.cpp:121-149
+//                           + the parameter record MPC::Update gets   reference src/mpc.cpp:69-80
+//
+// This translation unit is compiled with -fmad=false: every float/double expression below is evaluated in the
+// reference's order with IEEE round-to-nearest and no FMA contraction (the reference targets baseline x86-64).
+// The only operations that are NOT bit-reproducible against glibc are the transcendental calls; cosf/sinf/atan2f
+// on float arguments are computed here in double precision and rounded once to float, which is the correctly
+// rounded float result up to a ~1e-8 double-rounding probability (glibc's own float routines are within 0.56 ulp).
+// Parity for these kernels is therefore stated as a cell / index mismatch COUNT against the oracle, not bit-exact.
+#include "admm_kernel.cuh"
+
+namespace f110 {
+
+namespace {
+
+__device__ __forceinline__ float cosf_cr(float a) { return (float)cos((double)a); }
+__device__ __forceinline__ float sinf_cr(float a) { return (float)sin((double)a); }
+__device__ __forceinline__ int trunc_x86(float v) {  // cvttss2si
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return (int)0x80000000;
+  return __float2int_rz(v);
+}
+
+// ---- OccGrid::FillOccGrid --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_grid_kernel(int scenes, int blocks, float discrete, float dilation, int n_beams,
+                                                        int num_scans, float angle_min, float angle_inc,
+                                                        const double* __restrict__ pose7, const float* __restrict__ ranges,
+                                                        float* __restrict__ grid, float* __restrict__ offset) {
+  const int sc = blockIdx.x;
+  if (sc >= scenes) return;
+  float* g = grid + (size_t)sc * blocks * blocks;
+  for (int i = threadIdx.x; i < blocks * blocks; i += blockDim.x) g[i] = 0.f;  // grid_ = Zero (occupancy_grid.cpp:57)
+  const double* p = pose7 + 7 * (size_t)sc;
+  const double qz = p[5], qw = p[6];
+  const float yaw = (float)atan2(2 * qw * qz, 1 - 2 * qz * qz);                 // :60
+  const float offx = (float)(p[0] + 0.275 * cosf_cr(yaw));                      // :63
+  const float offy = (float)(p[1] + 0.275 * sinf_cr(yaw));                      // :64
+  if (threadIdx.x == 0) { offset[2 * sc] = offx; offset[2 * sc + 1] = offy; }
+  __syncthreads();
+  const float* r = ranges + (size_t)sc * n_beams;
+  const float half = (float)(blocks / 2);
+  const int nb = num_scans < n_beams ? num_scans : n_beams;
+  for (int ii = threadIdx.x; ii < nb; ii += blockDim.x) {
+    const float angle = angle_min + ii * angle_inc + yaw;                       // :71
+    float cx = r[ii] * cosf_cr(angle);                                          // :50
+    float cy = r[ii] * sinf_cr(angle);                                          // :51
+    cx += offx;                                                                 // :73
+    cy += offy;                                                                 // :74
+    for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {       // :76
+      for (float y_off = -dilation; y_off <= dilation; y_off += discrete) {     // :78
+        const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);     // :80 -> :30
+        const int row = trunc_x86(((cy + y_off) - offy) / discrete + half);     // :31
+        if (col >= 0 && col < blocks && row >= 0 && row < blocks) g[(size_t)row + (size_t)col * blocks] = 1.f;  // :83
+      }
+    }
+  }
+}
+
+// ---- Constraints::FindHalfSpaces: one thread per scene, the run-length scan kept sequential and literal ------------
+__global__ void __launch_bounds__(64) half_spaces_kernel(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc,
+                                                         float ftg_thresh, float divider, float buffer,
+                                                         const double* __restrict__ state3, const float* __restrict__ ranges,
+                                                         double* __restrict__ l1l2, int32_t* __restrict__ gap) {
+  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sc >= scenes) return;
+  const float* r = ranges + (size_t)sc * n_beams;
+  const int nb = num_scans < n_beams ? num_scans : n_beams;
+  const float half_fov = 1.571f / divider;
+  int widest = -1, lo = -1, hi = -1, best_lo = 0, best_hi = 0;
+  bool inside = false;
+  for (int i = 0; i < nb; ++i) {
+    const float bearing = angle_min + i * angle_inc;                            // constraints.cpp:133
+    if (!(bearing > -half_fov && bearing < half_fov)) continue;                 // :135
+    if (r[i] > ftg_thresh) {                                                    // :138
+      if (inside) hi = i; else { lo = i; inside = true; }                       // hi is not reset (SURVEY a13')
+    } else {
+      inside = false;
+      if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+    }
+    if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+  }
+  if ((float)(best_hi - best_lo) > 2 * buffer) {                                // :173
+    best_hi = (int)((float)best_hi - buffer);
+    best_lo = (int)((float)best_lo + buffer);
+  }
+  gap[2 * sc] = best_lo; gap[2 * sc + 1] = best_hi;
+  double* out = l1l2 + 6 * (size_t)sc;
+  if (best_lo < 0 || best_hi < 0 || best_lo >= n_beams || best_hi >= n_beams) {  // the reference reads ranges[-1] here
+    for (int j = 0; j < 6; ++j) out[j] = 0.0;
+    gap[2 * sc] = -1; gap[2 * sc + 1] = -1;
+    return;
+  }
+  const double px = state3[3 * sc], py = state3[3 * sc + 1];
+  const float heading = (float)state3[3 * sc + 2];                              // :127
+  const float a_lo = angle_min + best_lo * angle_inc + heading;                 // :179
+  const float a_hi = angle_min + best_hi * angle_inc + heading;                 // :180
+  const float p1x = (float)(r[best_lo] * cosf_cr(a_lo) + px), p1y = (float)(r[best_lo] * sinf_cr(a_lo) + py);  // :182-183
+  const float p2x = (float)(r[best_hi] * cosf_cr(a_hi) + px), p2y = (float)(r[best_hi] * sinf_cr(a_hi) + py);  // :185-186
+  const float qx = (float)px, qy = (float)py;                                   // :188-189
+  float a1 = qy - p1y, b1 = p1x - qx, c1 = qx * p1y - qy * p1x;                 // :233-235
+  if (a1 * p2x + b1 * p2y + c1 < 0) { a1 = -a1; b1 = -b1; c1 = -c1; }           // :237
+  float a2 = qy - p2y, b2 = p2x - qx, c2 = qx * p2y - qy * p2x;                 // :244-246
+  if (a2 * p1x + b2 * p1y + c2 < 0) { a2 = -a2; b2 = -b2; c2 = -c2; }           // :248
+  out[0] = a1; out[1] = b1; out[2] = c1 + 0.5;                                  // :258-260
+  out[3] = a2; out[4] = b2; out[5] = c2 + 0.5;                                  // :262-264
+}
+
+// ---- tf2 restated (see host/transforms.cpp) ---------------------------------------------------------------------------
+struct Basis { double m[3][3]; };
+__device__ Basis basis_of(double x, double y, double z, double w) {
+  const double n2 = x * x + y * y + z * z + w * w;
+  const double s = 2.0 / n2;
+  const double xs = x * s, ys = y * s, zs = z * s;
+  const double wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+  Basis b;
+  b.m[0][0] = 1.0 - (yy + zz); b.m[0][1] = xy - wz;         b.m[0][2] = xz + wy;
+  b.m[1][0] = xy + wz;         b.m[1][1] = 1.0 - (xx + zz); b.m[1][2] = yz - wx;
+  b.m[2][0] = xz - wy;         b.m[2][1] = yz + wx;         b.m[2][2] = 1.0 - (xx + yy);
+  return b;
+}
+__device__ void quaternion_of(const Basis& b, double* q) {
+  const double trace = b.m[0][0] + b.m[1][1] + b.m[2][2];
+  if (trace > 0.0) {
+    double s = sqrt(trace + 1.0);
+    q[3] = s * 0.5;
+    s = 0.5 / s;
+    q[0] = (b.m[2][1] - b.m[1][2]) * s; q[1] = (b.m[0][2] - b.m[2][0]) * s; q[2] = (b.m[1][0] - b.m[0][1]) * s;
+  } else {
+    const int i = b.m[0][0] < b.m[1][1] ? (b.m[1][1] < b.m[2][2] ? 2 : 1) : (b.m[0][0] < b.m[2][2] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(b.m[i][i] - b.m[j][j] - b.m[k][k] + 1.0);
+    q[i] = s * 0.5;
+    s = 0.5 / s;
+    q[3] = (b.m[k][j] - b.m[j][k]) * s; q[j] = (b.m[j][i] + b.m[i][j]) * s; q[k] = (b.m[k][i] + b.m[i][k]) * s;
+  }
+}
+
+// Car -> world rotation rows (what CarPointToWorldPoint applies after its tf2 round trip), one thread per scene.
+__global__ void __launch_bounds__(64) rotation_kernel(int scenes, const double* __restrict__ pose7, double* __restrict__ rot,
+                                                      double* __restrict__ pose_xy) {
+  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sc >= scenes) return;
+  const double* p = pose7 + 7 * (size_t)sc;
+  double q[4];
+  quaternion_of(basis_of(p[3], p[4], p[5], p[6]), q);
+  const Basis b = basis_of(q[0], q[1], q[2], q[3]);
+  rot[4 * sc] = b.m[0][0]; rot[4 * sc + 1] = b.m[0][1]; rot[4 * sc + 2] = b.m[1][0]; rot[4 * sc + 3] = b.m[1][1];
+  pose_xy[2 * sc] = p[0]; pose_xy[2 * sc + 1] = p[1];
+}
+
+// state3 = (px, py, float yaw) per scene: the State project.cpp:163-164 builds from the pose
+__global__ void __launch_bounds__(128) state_from_pose_kernel(int scenes, const double* __restrict__ pose7, double* __restrict__ state3) {
+  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sc >= scenes) return;
+  const double* p = pose7 + 7 * (size_t)sc;
+  state3[3 * sc] = p[0]; state3[3 * sc + 1] = p[1];
+  state3[3 * sc + 2] = (double)(float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);
+}
+
+// ---- look-ahead point, best surviving path, parameter record: one thread per scene, sequential like the reference ----
+__global__ void __launch_bounds__(64) select_build_kernel(int scenes, int paths, int samples, int N, int stride, int n_wp,
+                                                          float lookahead, double v_lin,
+                                                          const double* __restrict__ pose7, const double* __restrict__ rot,
+                                                          const float* __restrict__ wp_xy, const uint8_t* __restrict__ valid,
+                                                          const float* __restrict__ end_world, const double* __restrict__ table_xy,
+                                                          const double* __restrict__ prev_steer, const double* __restrict__ l1l2,
+                                                          double* __restrict__ recs, int32_t* __restrict__ chosen,
+                                                          int32_t* __restrict__ best_global) {
+  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sc >= scenes) return;
+  const double* p = pose7 + 7 * (size_t)sc;
+  double* rec = recs + (size_t)sc * stride;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  chosen[sc] = -1; best_global[sc] = -1;
+  rec[3] = qnan;  // "no problem in this slot": the solve kernel reports F110_UNSOLVED for it
+  // any valid path? (project.cpp:115-119)
+  bool any_valid = false;
+  for (int i = 0; i < paths; ++i) any_valid |= valid[(size_t)sc * paths + i] != 0;
+  if (!any_valid) return;
+  // Transforms::WorldToCarTransform (transforms.cpp:22-31) then TransformPoint per waypoint (:33-44)
+  const Basis b = basis_of(p[3], p[4], p[5], p[6]);
+  Basis inv;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) inv.m[r][c] = b.m[c][r];
+  const double ox = -p[0], oy = -p[1], oz = -p[2];
+  const double tx = inv.m[0][0] * ox + inv.m[0][1] * oy + inv.m[0][2] * oz;
+  const double ty = inv.m[1][0] * ox + inv.m[1][1] * oy + inv.m[1][2] * oz;
+  double q[4];
+  quaternion_of(inv, q);
+  const Basis w2c = basis_of(q[0], q[1], q[2], q[3]);
+  float best = 3.402823466e+38f;  // numeric_limits<float>::max()
+  int best_idx = -1;
+  for (int i = 0; i < n_wp; ++i) {                                              // trajectory.cpp:93
+    const double wx = (double)wp_xy[2 * i], wy = (double)wp_xy[2 * i + 1];
+    const float fx = (float)((w2c.m[0][0] * wx + w2c.m[0][1] * wy + w2c.m[0][2] * 0.0) + tx);
+    const float fy = (float)((w2c.m[1][0] * wx + w2c.m[1][1] * wy + w2c.m[1][2] * 0.0) + ty);
+    if (fx < 0) continue;                                                       // :100
+    const double dist = sqrt((double)fx * (double)fx + (double)fy * (double)fy);  // pow(pow(x,2)+pow(y,2), 0.5)
+    const double off = fabs(dist - (double)lookahead);                          // :102
+    if (off < (double)best) { best = (float)off; best_idx = i; }                // :103-107 (float minDistance)
+  }
+  best_global[sc] = best_idx;
+  if (best_idx < 0) return;
+  const double gx = (double)wp_xy[2 * best_idx], gy = (double)wp_xy[2 * best_idx + 1];
+  double min_dist = 1.7976931348623157e308;                                     // project.cpp:125
+  int pick = -1;
+  for (int i = 0; i < paths; ++i) {                                             // :127-136, strict <, first wins
+    if (!valid[(size_t)sc * paths + i]) continue;
+    const double ex = (double)end_world[2 * ((size_t)sc * paths + i)], ey = (double)end_world[2 * ((size_t)sc * paths + i) + 1];
+    const double d = sqrt((ex - gx) * (ex - gx) + (ey - gy) * (ey - gy));
+    if (d < min_dist) { min_dist = d; pick = i; }
+  }
+  chosen[sc] = pick;
+  // parameter record (include/f110_mpc_b200.h): x0 | (v, steer) | l1 | l2 | ref[0..N-1]
+  const float yaw = (float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);         // Transforms::GetCarOrientation (float)
+  rec[0] = p[0]; rec[1] = p[1]; rec[2] = (double)yaw;                           // project.cpp:163-164
+  rec[3] = v_lin;                                                               // project.cpp:170
+  rec[4] = prev_steer ? prev_steer[sc] : 0.0;
+  for (int j = 0; j < 6; ++j) rec[5 + j] = l1l2 ? l1l2[6 * (size_t)sc + j] : 0.0;
+  const double r00 = rot[4 * sc], r01 = rot[4 * sc + 1], r10 = rot[4 * sc + 2], r11 = rot[4 * sc + 3];
+  const float posex = (float)p[0], posey = (float)p[1];
+  const double* tp = table_xy + (size_t)pick * samples * 2;
+  for (int k = 0; k < N; ++k) {                                                 // project.cpp:145-149, clamped to the path length
+    const int kk = k < samples ? k : samples - 1;
+    const double cx = (double)(float)tp[2 * kk], cy = (double)(float)tp[2 * kk + 1];
+    const float fx = (float)(((r00 * cx + r01 * cy) + 0.0 * 0.0) + (double)posex);
+    const float fy = (float)(((r10 * cx + r11 * cy) + 0.0 * 0.0) + (double)posey);
+    rec[11 + 3 * k] = (double)fx; rec[12 + 3 * k] = (double)fy; rec[13 + 3 * k] = 0.0;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fill_grid(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
+                             float angle_inc, const double* pose7, const float* ranges, float* grid, float* offset, cudaStream_t st) {
+  if (scenes == 0) return cudaSuccess;
+  fill_grid_kernel<<<scenes, 256, 0, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, pose7, ranges, grid, offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_half_spaces(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc, float thresh, float divider,
+                               float buffer, const double* state3, const float* ranges, double* l1l2, int32_t* gap, cudaStream_t st) {
+  if (scenes == 0) return cudaSuccess;
+  half_spaces_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, n_beams, num_scans, angle_min, angle_inc, thresh, divider, buffer, state3, ranges, l1l2, gap);
+  return cudaGetLastError();
+}
+cudaError_t launch_state_from_pose(int scenes, const double* pose7, double* state3, cudaStream_t st) {
+  if (scenes == 0) return cudaSuccess;
+  state_from_pose_kernel<<<(scenes + 127) / 128, 128, 0, st>>>(scenes, pose7, state3);
+  return cudaGetLastError();
+}
+cudaError_t launch_rotation(int scenes, const double* pose7, double* rot, double* pose_xy, cudaStream_t st) {
+  if (scenes == 0) return cudaSuccess;
+  rotation_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, pose7, rot, pose_xy);
+  return cudaGetLastError();
+}
+cudaError_t launch_select_build(int scenes, int paths, int samples, int N, int stride, int n_wp, float lookahead, double v_lin,
+                                const double* pose7, const double* rot, const float* wp_xy, const uint8_t* valid, const float* end_world,
+                                const double* table_xy, const double* prev_steer, const double* l1l2, double* recs, int32_t* chosen,
+                                int32_t* best_global, cudaStream_t st) {
+  if (scenes == 0) return cudaSuccess;
+  select_build_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, paths, samples, N, stride, n_wp, lookahead, v_lin, pose7, rot, wp_xy, valid,
+                                                         end_world, table_xy, prev_steer, l1l2, recs, chosen, best_global);
+  return cudaGetLastError();
+}
+
+}  // namespace f110

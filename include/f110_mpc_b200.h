@@ -136,6 +136,36 @@ int f110_collision_check_host(int scenes, int paths, int samples, int blocks, fl
                               const double* table_xy, uint8_t* valid, int32_t* free_count, float* end_world,
                               int device);
 
+/* ---- whole planning + control cycle on the device, no host round trip.
+ * For each of `scenes` independent cars:  FillOccGrid (occupancy_grid.cpp:55-88)  ->  mini-path collision check
+ * (project.cpp:76-113)  ->  look-ahead point + best surviving path (trajectory.cpp:81-108, project.cpp:121-149)
+ * ->  FindHalfSpaces on the scene's scan (constraints.cpp:116-265)  ->  one tracking QP  ->  first control.
+ * The transcendental calls of the fill / gap stages are not bit-identical to glibc's (see pipeline_kernels.cu);
+ * the integer/float paths of the check and the selection are. */
+typedef struct f110_cycle_config {
+  int32_t n_beams;                                 /* ranges per scan */
+  float angle_min, angle_max, angle_increment;     /* sensor_msgs/LaserScan, same for every scene */
+  int32_t occ_size; float occ_discrete, occ_dilation; /* occupancy_grid.cpp:6-8 */
+  float follow_gap_thresh, fov_divider, buffer;    /* constraints.cpp:9-12 */
+  float lookahead;                                 /* trajectory.cpp:10 */
+  int32_t use_half_spaces;                         /* 1: l1, l2 from each scene's scan; 0: zero rows */
+  double v_lin;                                    /* linearisation speed, 4.5 (project.cpp:170) */
+} f110_cycle_config;
+void f110_cycle_default_config(f110_cycle_config* c);
+/*   d_pose7      scenes x 7 doubles (px py pz qx qy qz qw)      d_ranges   scenes x n_beams floats
+ *   d_prev_steer scenes doubles or NULL (previous steering, the linearisation point)
+ *   d_table_xy   paths x samples x 2 doubles                     d_wp_xy    n_wp x 2 floats (raceline, trajectory.cpp:28-32)
+ * outputs (scenes): u0 x2, status (F110_UNSOLVED where no path was valid), iters, chosen path index (-1 = none),
+ *   d_valid scenes x paths or NULL.  Needs scenes <= max_batch of the handle.  Stream-ordered, no sync. */
+int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* d_pose7, const float* d_ranges,
+                      const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy,
+                      int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid,
+                      void* cuda_stream);
+/* Device buffers the last f110_cycle_device call filled (for inspection / tests): grids (scenes x blocks^2 floats),
+ * offsets (x2 floats), l1l2 (x6 doubles), records (x record_doubles), best_global (int32). Any pointer may be NULL. */
+int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs,
+                       int32_t** d_best_global);
+
 /* ---- measurement utility (not on the solve path): FP64 FMA issue rate of `device` in TFLOP/s, the
  * roofline denominator for the ADMM kernel. */
 int f110_bench_fp64_fma(int device, int iters, double* tflops_out);

@@ -1,0 +1,89 @@
+"""GPU tests of the device-resident planning + control cycle (f110_cycle_device):
+grid fill -> collision check -> look-ahead / best path -> half-planes -> QP -> first control, against the oracle
+pipeline.  The fill and gap stages call transcendental functions whose last bit may differ from glibc's, so their
+parity is a mismatch COUNT (expected 0 on these inputs, bounded at 1e-4 of the cells); everything downstream of
+identical inputs is exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_cycle(pkg, workloads, S, sd, seed, use_half_spaces=1, N=30):
+    dev = torch.device("cuda:0")
+    poses, yaws, scans = workloads.scene_batch(S, seed=seed)
+    table = np.ascontiguousarray(workloads.traj_table(steer_discrete=sd)[:, :, :2])
+    xy, _ = workloads.skirk_waypoints()
+    sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(warm_start=0), max_batch=S)
+    cc = pkg.default_cycle_config(use_half_spaces=use_half_spaces)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    prev = np.random.default_rng(seed).uniform(-0.3, 0.3, S)
+    P = table.shape[0]
+    u0 = torch.empty(S, 2, dtype=torch.float64, device=dev); st = torch.empty(S, dtype=torch.int32, device=dev)
+    it = torch.empty(S, dtype=torch.int32, device=dev); ch = torch.empty(S, dtype=torch.int32, device=dev)
+    va = torch.empty(S, P, dtype=torch.uint8, device=dev)
+    sol.cycle_device(cc, t(poses), t(scans), t(prev), t(table), t(xy), u0, st, it, ch, va)
+    torch.cuda.synchronize()
+    bufs = {k: v.cpu().numpy() for k, v in sol.cycle_buffers(S).items()}
+    return dict(poses=poses, yaws=yaws, scans=scans, table=table, xy=xy, prev=prev, u0=u0.cpu().numpy(), status=st.cpu().numpy(),
+                iters=it.cpu().numpy(), chosen=ch.cpu().numpy(), valid=va.cpu().numpy(), launches=sol.last_launches, **bufs)
+
+
+@pytest.mark.parametrize("sd", [19, 30])
+def test_cycle_matches_oracle_pipeline(pkg, oracle, workloads, sd):
+    S, N = 96, 30
+    amin, amax, inc = workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC
+    r = _run_cycle(pkg, workloads, S, sd, seed=31 + sd)
+    assert r["launches"] == 7                           # fill, rotation, check, state, half-planes, select/build, solve
+    cell_mismatch = 0
+    recs_o = []
+    n_none = 0
+    for s in range(S):
+        grid, off, _ = oracle.fill_grid(r["poses"][s], amin, amax, inc, r["scans"][s])
+        cell_mismatch += int((grid != r["grid"][s]).sum())
+        np.testing.assert_allclose(off, r["offset"][s], rtol=0, atol=5e-7)      # cosf/sinf: last float bit may differ from glibc
+        # downstream stages are compared on the DEVICE grid so a (hypothetical) last-bit trig difference cannot cascade
+        R = oracle.car_to_world_R(r["poses"][s])
+        v, f, e = oracle.collision_check(r["grid"][s], 100, 0.1, r["offset"][s], R, r["poses"][s, :2], r["table"])
+        np.testing.assert_array_equal(r["valid"][s], v)
+        if v.sum() == 0:
+            assert r["chosen"][s] == -1 and r["status"][s] == -10 and np.isnan(r["u0"][s]).all()
+            n_none += 1
+            recs_o.append(None)
+            continue
+        bg = oracle.best_global_idx(r["xy"], r["poses"][s], 2.5)
+        assert r["best_global"][s] == bg
+        pick = oracle.select_best(v, e, float(r["xy"][bg, 0]), float(r["xy"][bg, 1]))
+        assert r["chosen"][s] == pick
+        state = np.array([r["poses"][s, 0], r["poses"][s, 1], oracle.car_orientation(r["poses"][s])])
+        ok, l1, l2, _ = oracle.find_half_spaces(state, amin, amax, inc, r["scans"][s])
+        l1l2 = np.concatenate([l1, l2]) if ok else np.zeros(6)
+        np.testing.assert_allclose(r["l1l2"][s], l1l2, rtol=2e-6, atol=2e-5)  # float trig: within a few float ulps of the products
+        # record: reference of the chosen path in the world frame, float-narrowed (project.cpp:145-149)
+        ref = np.zeros((N, 3))
+        for k in range(N):
+            _, _, ew = oracle.collision_check(np.zeros(10000, dtype=np.float32), 100, 0.1, np.array([1e6, 1e6], dtype=np.float32) * 0 + r["offset"][s],
+                                              R, r["poses"][s, :2], r["table"][pick:pick + 1, k:k + 1, :])
+            ref[k, :2] = ew[0]
+        rec = np.concatenate([state, [4.5, r["prev"][s]], r["l1l2"][s], ref.reshape(-1)])
+        np.testing.assert_array_equal(r["recs"][s], rec)
+        recs_o.append(rec)
+    assert cell_mismatch <= 1e-4 * S * 10000
+    assert 0 < n_none < S
+    # the QP solved on the device-built records == oracle solve of the same records
+    idx = [s for s in range(S) if recs_o[s] is not None]
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(warm_start=0), len(idx)).solve(np.array([recs_o[s] for s in idx]))
+    np.testing.assert_array_equal(r["status"][idx], o["status"])
+    np.testing.assert_array_equal(r["iters"][idx], o["iters"])
+    np.testing.assert_allclose(r["u0"][idx], o["x"][:, 3 * (N + 1):3 * (N + 1) + 2], atol=1e-4, rtol=1e-3)
+
+
+def test_cycle_without_half_spaces_and_long_horizon(pkg, oracle, workloads):
+    r = _run_cycle(pkg, workloads, 40, 19, seed=5, use_half_spaces=0, N=50)
+    assert r["launches"] == 5
+    ok = r["chosen"] >= 0
+    assert ok.any() and (r["recs"][ok][:, 5:11] == 0).all()
+    o = oracle.MpcBatch(oracle.default_cfg(50), oracle.default_settings(warm_start=0), int(ok.sum())).solve(r["recs"][ok])
+    np.testing.assert_array_equal(r["status"][ok], o["status"])
+    np.testing.assert_allclose(r["u0"][ok], o["x"][:, 3 * 51:3 * 51 + 2], atol=1e-4, rtol=1e-3)
