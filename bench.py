@@ -512,6 +512,39 @@ def run_configs(args):
                           "algorithmic_tflops": fl / (g["ms"] * 1e-3) / 1e12, "fp64_roofline_frac": fl / (g["ms"] * 1e-3) / 1e12 / peak,
                           "parity": parity(g, o, N)}
     report["config5_horizon_sweep"] = c5
+
+    # ---- device-resident cycle: scan + pose in, control out, one QP per car ----------------------------
+    Sc = 4096 if not args.quick else 256
+    poses, yaws, scans = W.scene_batch(Sc, seed=20240906)
+    table = np.ascontiguousarray(W.traj_table(steer_discrete=19)[:, :, :2])
+    sol = M.MpcSolver(M.default_config(N_HORIZON), M.default_settings(warm_start=0), max_batch=Sc)
+    cc = M.default_cycle_config()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    h_pose, h_scan = torch.from_numpy(poses).pin_memory(), torch.from_numpy(scans).pin_memory()
+    d_pose, d_scan, d_tab, d_wp = t(poses), t(scans), t(table), t(xy)
+    u0 = torch.empty(Sc, 2, dtype=torch.float64, device=dev); stt = torch.empty(Sc, dtype=torch.int32, device=dev)
+    it = torch.empty(Sc, dtype=torch.int32, device=dev); ch = torch.empty(Sc, dtype=torch.int32, device=dev)
+    h_u0 = torch.empty(Sc, 2, dtype=torch.float64).pin_memory()
+    for _ in range(3):
+        sol.cycle_device(cc, d_pose, d_scan, None, d_tab, d_wp, u0, stt, it, ch, stream=stream)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        sol.cycle_device(cc, d_pose, d_scan, None, d_tab, d_wp, u0, stt, it, ch, stream=stream)
+    b.record(); torch.cuda.synchronize()
+    ms_dev = a.elapsed_time(b) / 10
+    t0 = time.perf_counter()
+    for _ in range(10):
+        d_pose.copy_(h_pose, non_blocking=True); d_scan.copy_(h_scan, non_blocking=True)
+        sol.cycle_device(cc, d_pose, d_scan, None, d_tab, d_wp, u0, stt, it, ch, stream=stream)
+        h_u0.copy_(u0, non_blocking=True)
+        torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / 10
+    n_solved = int((stt == 1).sum().item())
+    report["device_cycle"] = {"scenes": Sc, "kernels_per_cycle": sol.last_launches, "solved": n_solved, "device_ms": ms_dev,
+                              "cars_per_s_device": Sc / (ms_dev * 1e-3), "e2e_ms (scan+pose H2D, u0 D2H)": ms_e2e,
+                              "cars_per_s_e2e": Sc / (ms_e2e * 1e-3), "h2d_bytes": int(poses.nbytes + scans.nbytes)}
     out = args.configs_out or os.path.join(ROOT, "gpurun_out", "configs.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     json.dump(report, open(out, "w"), indent=1)

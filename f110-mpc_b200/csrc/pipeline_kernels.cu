@@ -25,15 +25,16 @@ __device__ __forceinline__ int trunc_x86(float v) {  // cvttss2si
   return __float2int_rz(v);
 }
 
-// ---- OccGrid::FillOccGrid --------------------------------------------------------------------------------------
+// ---- OccGrid::FillOccGrid: one CTA per scene, the grid is stamped in shared memory and written out once --------
 __global__ void __launch_bounds__(256) fill_grid_kernel(int scenes, int blocks, float discrete, float dilation, int n_beams,
                                                         int num_scans, float angle_min, float angle_inc,
                                                         const double* __restrict__ pose7, const float* __restrict__ ranges,
                                                         float* __restrict__ grid, float* __restrict__ offset) {
+  extern __shared__ unsigned char cells[];   // blocks * blocks occupancy bytes
   const int sc = blockIdx.x;
   if (sc >= scenes) return;
-  float* g = grid + (size_t)sc * blocks * blocks;
-  for (int i = threadIdx.x; i < blocks * blocks; i += blockDim.x) g[i] = 0.f;  // grid_ = Zero (occupancy_grid.cpp:57)
+  const int ncell = blocks * blocks;
+  for (int i = threadIdx.x; i < ncell; i += blockDim.x) cells[i] = 0;           // grid_ = Zero (occupancy_grid.cpp:57)
   const double* p = pose7 + 7 * (size_t)sc;
   const double qz = p[5], qw = p[6];
   const float yaw = (float)atan2(2 * qw * qz, 1 - 2 * qz * qz);                 // :60
@@ -46,42 +47,75 @@ __global__ void __launch_bounds__(256) fill_grid_kernel(int scenes, int blocks, 
   const int nb = num_scans < n_beams ? num_scans : n_beams;
   for (int ii = threadIdx.x; ii < nb; ii += blockDim.x) {
     const float angle = angle_min + ii * angle_inc + yaw;                       // :71
-    float cx = r[ii] * cosf_cr(angle);                                          // :50
-    float cy = r[ii] * sinf_cr(angle);                                          // :51
+    double sn, cs;
+    sincos((double)angle, &sn, &cs);
+    float cx = r[ii] * (float)cs;                                               // :50
+    float cy = r[ii] * (float)sn;                                               // :51
     cx += offx;                                                                 // :73
     cy += offy;                                                                 // :74
     for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {       // :76
+      const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);       // :80 -> :30
+      if (col < 0 || col >= blocks) continue;
       for (float y_off = -dilation; y_off <= dilation; y_off += discrete) {     // :78
-        const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);     // :80 -> :30
         const int row = trunc_x86(((cy + y_off) - offy) / discrete + half);     // :31
-        if (col >= 0 && col < blocks && row >= 0 && row < blocks) g[(size_t)row + (size_t)col * blocks] = 1.f;  // :83
+        if (row >= 0 && row < blocks) cells[row + col * blocks] = 1;            // :83  grid_(row, col) = 1
       }
     }
   }
+  __syncthreads();
+  float* g = grid + (size_t)sc * ncell;
+  for (int i = threadIdx.x; i < ncell; i += blockDim.x) g[i] = cells[i] ? 1.f : 0.f;
 }
 
-// ---- Constraints::FindHalfSpaces: one thread per scene, the run-length scan kept sequential and literal ------------
-__global__ void __launch_bounds__(64) half_spaces_kernel(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc,
-                                                         float ftg_thresh, float divider, float buffer,
-                                                         const double* __restrict__ state3, const float* __restrict__ ranges,
-                                                         double* __restrict__ l1l2, int32_t* __restrict__ gap) {
-  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- Constraints::FindHalfSpaces: one warp per scene.  The lanes stage the scan in shared memory (coalesced), lane 0
+// runs the run-length scan sequentially and literally (its quirks — SURVEY a13' — depend on the visiting order).
+constexpr int HS_WARPS = 4;
+__global__ void __launch_bounds__(32 * HS_WARPS) half_spaces_kernel(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc,
+                                                                   float ftg_thresh, float divider, float buffer,
+                                                                   const double* __restrict__ state3, const float* __restrict__ ranges,
+                                                                   double* __restrict__ l1l2, int32_t* __restrict__ gap) {
+  extern __shared__ unsigned mask_sm[];  // HS_WARPS x 2 x words: per 32 beams, "inside the field of view" and "far" bit masks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sc = blockIdx.x * HS_WARPS + warp;
   if (sc >= scenes) return;
-  const float* r = ranges + (size_t)sc * n_beams;
   const int nb = num_scans < n_beams ? num_scans : n_beams;
+  const int words = (nb + 31) / 32;
+  unsigned* fov = mask_sm + (size_t)warp * 2 * ((n_beams + 31) / 32);
+  unsigned* far = fov + (n_beams + 31) / 32;
+  const float* rs = ranges + (size_t)sc * n_beams;
   const float half_fov = 1.571f / divider;
+  // the per-beam predicates do not depend on the visiting order: evaluate them 32 at a time (coalesced reads)
+  for (int w = 0; w < words; ++w) {
+    const int i = 32 * w + lane;
+    bool in_fov = false, is_far = false;
+    if (i < nb) {
+      const float bearing = angle_min + i * angle_inc;                          // constraints.cpp:133
+      in_fov = bearing > -half_fov && bearing < half_fov;                       // :135
+      is_far = rs[i] > ftg_thresh;                                              // :138
+    }
+    const unsigned m_fov = __ballot_sync(0xffffffffu, in_fov), m_far = __ballot_sync(0xffffffffu, in_fov && is_far);
+    if (lane == 0) { fov[w] = m_fov; far[w] = m_far; }
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  // the run-length scan itself is order dependent (SURVEY a13'): sequential and literal, over the bit masks
   int widest = -1, lo = -1, hi = -1, best_lo = 0, best_hi = 0;
   bool inside = false;
-  for (int i = 0; i < nb; ++i) {
-    const float bearing = angle_min + i * angle_inc;                            // constraints.cpp:133
-    if (!(bearing > -half_fov && bearing < half_fov)) continue;                 // :135
-    if (r[i] > ftg_thresh) {                                                    // :138
-      if (inside) hi = i; else { lo = i; inside = true; }                       // hi is not reset (SURVEY a13')
-    } else {
-      inside = false;
+  for (int w = 0; w < words; ++w) {
+    unsigned mf = fov[w];
+    const unsigned mr = far[w];
+    while (mf) {
+      const int bit = __ffs(mf) - 1;
+      mf &= mf - 1;
+      const int i = 32 * w + bit;
+      if ((mr >> bit) & 1u) {
+        if (inside) hi = i; else { lo = i; inside = true; }                     // hi is not reset
+      } else {
+        inside = false;
+        if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+      }
       if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
     }
-    if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
   }
   if ((float)(best_hi - best_lo) > 2 * buffer) {                                // :173
     best_hi = (int)((float)best_hi - buffer);
@@ -98,8 +132,8 @@ __global__ void __launch_bounds__(64) half_spaces_kernel(int scenes, int n_beams
   const float heading = (float)state3[3 * sc + 2];                              // :127
   const float a_lo = angle_min + best_lo * angle_inc + heading;                 // :179
   const float a_hi = angle_min + best_hi * angle_inc + heading;                 // :180
-  const float p1x = (float)(r[best_lo] * cosf_cr(a_lo) + px), p1y = (float)(r[best_lo] * sinf_cr(a_lo) + py);  // :182-183
-  const float p2x = (float)(r[best_hi] * cosf_cr(a_hi) + px), p2y = (float)(r[best_hi] * sinf_cr(a_hi) + py);  // :185-186
+  const float p1x = (float)(rs[best_lo] * cosf_cr(a_lo) + px), p1y = (float)(rs[best_lo] * sinf_cr(a_lo) + py);  // :182-183
+  const float p2x = (float)(rs[best_hi] * cosf_cr(a_hi) + px), p2y = (float)(rs[best_hi] * sinf_cr(a_hi) + py);  // :185-186
   const float qx = (float)px, qy = (float)py;                                   // :188-189
   float a1 = qy - p1y, b1 = p1x - qx, c1 = qx * p1y - qy * p1x;                 // :233-235
   if (a1 * p2x + b1 * p2y + c1 < 0) { a1 = -a1; b1 = -b1; c1 = -c1; }           // :237
@@ -161,26 +195,33 @@ __global__ void __launch_bounds__(128) state_from_pose_kernel(int scenes, const 
   state3[3 * sc + 2] = (double)(float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);
 }
 
-// ---- look-ahead point, best surviving path, parameter record: one thread per scene, sequential like the reference ----
-__global__ void __launch_bounds__(64) select_build_kernel(int scenes, int paths, int samples, int N, int stride, int n_wp,
-                                                          float lookahead, double v_lin,
-                                                          const double* __restrict__ pose7, const double* __restrict__ rot,
-                                                          const float* __restrict__ wp_xy, const uint8_t* __restrict__ valid,
-                                                          const float* __restrict__ end_world, const double* __restrict__ table_xy,
-                                                          const double* __restrict__ prev_steer, const double* __restrict__ l1l2,
-                                                          double* __restrict__ recs, int32_t* __restrict__ chosen,
-                                                          int32_t* __restrict__ best_global) {
-  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- look-ahead point, best surviving path, parameter record: one warp per scene.  The lanes evaluate the per-waypoint
+// distances and write the record; the two argmin scans stay sequential on lane 0 because their result depends on the
+// visiting order (strict <, float-narrowed running minimum — trajectory.cpp:103-107, project.cpp:132-135).
+constexpr int SB_WARPS = 4;
+__global__ void __launch_bounds__(32 * SB_WARPS) select_build_kernel(int scenes, int paths, int samples, int N, int stride, int n_wp,
+                                                                    float lookahead, double v_lin,
+                                                                    const double* __restrict__ pose7, const double* __restrict__ rot,
+                                                                    const float* __restrict__ wp_xy, const uint8_t* __restrict__ valid,
+                                                                    const float* __restrict__ end_world, const double* __restrict__ table_xy,
+                                                                    const double* __restrict__ prev_steer, const double* __restrict__ l1l2,
+                                                                    double* __restrict__ recs, int32_t* __restrict__ chosen,
+                                                                    int32_t* __restrict__ best_global) {
+  extern __shared__ double off_sm[];  // SB_WARPS x n_wp look-ahead offsets (negative = waypoint behind the car)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sc = blockIdx.x * SB_WARPS + warp;
   if (sc >= scenes) return;
+  double* offs = off_sm + (size_t)warp * n_wp;
   const double* p = pose7 + 7 * (size_t)sc;
   double* rec = recs + (size_t)sc * stride;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  chosen[sc] = -1; best_global[sc] = -1;
-  rec[3] = qnan;  // "no problem in this slot": the solve kernel reports F110_UNSOLVED for it
   // any valid path? (project.cpp:115-119)
-  bool any_valid = false;
-  for (int i = 0; i < paths; ++i) any_valid |= valid[(size_t)sc * paths + i] != 0;
-  if (!any_valid) return;
+  bool mine = false;
+  for (int i = lane; i < paths; i += 32) mine |= valid[(size_t)sc * paths + i] != 0;
+  if (!__any_sync(0xffffffffu, mine)) {
+    if (lane == 0) { chosen[sc] = -1; best_global[sc] = -1; rec[3] = qnan; }  // empty slot: the solve kernel reports F110_UNSOLVED
+    return;
+  }
   // Transforms::WorldToCarTransform (transforms.cpp:22-31) then TransformPoint per waypoint (:33-44)
   const Basis b = basis_of(p[3], p[4], p[5], p[6]);
   Basis inv;
@@ -191,39 +232,52 @@ __global__ void __launch_bounds__(64) select_build_kernel(int scenes, int paths,
   double q[4];
   quaternion_of(inv, q);
   const Basis w2c = basis_of(q[0], q[1], q[2], q[3]);
-  float best = 3.402823466e+38f;  // numeric_limits<float>::max()
-  int best_idx = -1;
-  for (int i = 0; i < n_wp; ++i) {                                              // trajectory.cpp:93
+  for (int i = lane; i < n_wp; i += 32) {                                       // trajectory.cpp:93, any order: values only
     const double wx = (double)wp_xy[2 * i], wy = (double)wp_xy[2 * i + 1];
     const float fx = (float)((w2c.m[0][0] * wx + w2c.m[0][1] * wy + w2c.m[0][2] * 0.0) + tx);
     const float fy = (float)((w2c.m[1][0] * wx + w2c.m[1][1] * wy + w2c.m[1][2] * 0.0) + ty);
-    if (fx < 0) continue;                                                       // :100
     const double dist = sqrt((double)fx * (double)fx + (double)fy * (double)fy);  // pow(pow(x,2)+pow(y,2), 0.5)
-    const double off = fabs(dist - (double)lookahead);                          // :102
-    if (off < (double)best) { best = (float)off; best_idx = i; }                // :103-107 (float minDistance)
+    offs[i] = (fx < 0) ? -1.0 : fabs(dist - (double)lookahead);                 // :100, :102
   }
-  best_global[sc] = best_idx;
-  if (best_idx < 0) return;
-  const double gx = (double)wp_xy[2 * best_idx], gy = (double)wp_xy[2 * best_idx + 1];
-  double min_dist = 1.7976931348623157e308;                                     // project.cpp:125
-  int pick = -1;
-  for (int i = 0; i < paths; ++i) {                                             // :127-136, strict <, first wins
-    if (!valid[(size_t)sc * paths + i]) continue;
-    const double ex = (double)end_world[2 * ((size_t)sc * paths + i)], ey = (double)end_world[2 * ((size_t)sc * paths + i) + 1];
-    const double d = sqrt((ex - gx) * (ex - gx) + (ey - gy) * (ey - gy));
-    if (d < min_dist) { min_dist = d; pick = i; }
+  __syncwarp();
+  int best_idx = -1, pick = -1;
+  if (lane == 0) {
+    float best = 3.402823466e+38f;  // numeric_limits<float>::max()
+    for (int i = 0; i < n_wp; ++i) {
+      const double off = offs[i];
+      if (off < 0.0) continue;                                                  // behind the car
+      if (off < (double)best) { best = (float)off; best_idx = i; }              // :103-107 (float minDistance)
+    }
+    if (best_idx >= 0) {
+      const double gx = (double)wp_xy[2 * best_idx], gy = (double)wp_xy[2 * best_idx + 1];
+      double min_dist = 1.7976931348623157e308;                                 // project.cpp:125
+      for (int i = 0; i < paths; ++i) {                                         // :127-136, strict <, first wins
+        if (!valid[(size_t)sc * paths + i]) continue;
+        const double ex = (double)end_world[2 * ((size_t)sc * paths + i)], ey = (double)end_world[2 * ((size_t)sc * paths + i) + 1];
+        const double d = sqrt((ex - gx) * (ex - gx) + (ey - gy) * (ey - gy));
+        if (d < min_dist) { min_dist = d; pick = i; }
+      }
+    }
+    best_global[sc] = best_idx;
+    chosen[sc] = pick;
   }
-  chosen[sc] = pick;
+  pick = __shfl_sync(0xffffffffu, pick, 0);
+  if (pick < 0) {
+    if (lane == 0) rec[3] = qnan;
+    return;
+  }
   // parameter record (include/f110_mpc_b200.h): x0 | (v, steer) | l1 | l2 | ref[0..N-1]
-  const float yaw = (float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);         // Transforms::GetCarOrientation (float)
-  rec[0] = p[0]; rec[1] = p[1]; rec[2] = (double)yaw;                           // project.cpp:163-164
-  rec[3] = v_lin;                                                               // project.cpp:170
-  rec[4] = prev_steer ? prev_steer[sc] : 0.0;
-  for (int j = 0; j < 6; ++j) rec[5 + j] = l1l2 ? l1l2[6 * (size_t)sc + j] : 0.0;
+  if (lane == 0) {
+    const float yaw = (float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);       // Transforms::GetCarOrientation (float)
+    rec[0] = p[0]; rec[1] = p[1]; rec[2] = (double)yaw;                         // project.cpp:163-164
+    rec[3] = v_lin;                                                             // project.cpp:170
+    rec[4] = prev_steer ? prev_steer[sc] : 0.0;
+  }
+  if (lane < 6) rec[5 + lane] = l1l2 ? l1l2[6 * (size_t)sc + lane] : 0.0;
   const double r00 = rot[4 * sc], r01 = rot[4 * sc + 1], r10 = rot[4 * sc + 2], r11 = rot[4 * sc + 3];
   const float posex = (float)p[0], posey = (float)p[1];
   const double* tp = table_xy + (size_t)pick * samples * 2;
-  for (int k = 0; k < N; ++k) {                                                 // project.cpp:145-149, clamped to the path length
+  for (int k = lane; k < N; k += 32) {                                          // project.cpp:145-149, clamped to the path length
     const int kk = k < samples ? k : samples - 1;
     const double cx = (double)(float)tp[2 * kk], cy = (double)(float)tp[2 * kk + 1];
     const float fx = (float)(((r00 * cx + r01 * cy) + 0.0 * 0.0) + (double)posex);
@@ -237,13 +291,13 @@ __global__ void __launch_bounds__(64) select_build_kernel(int scenes, int paths,
 cudaError_t launch_fill_grid(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
                              float angle_inc, const double* pose7, const float* ranges, float* grid, float* offset, cudaStream_t st) {
   if (scenes == 0) return cudaSuccess;
-  fill_grid_kernel<<<scenes, 256, 0, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, pose7, ranges, grid, offset);
+  fill_grid_kernel<<<scenes, 256, (size_t)blocks * blocks, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, pose7, ranges, grid, offset);
   return cudaGetLastError();
 }
 cudaError_t launch_half_spaces(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc, float thresh, float divider,
                                float buffer, const double* state3, const float* ranges, double* l1l2, int32_t* gap, cudaStream_t st) {
   if (scenes == 0) return cudaSuccess;
-  half_spaces_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, n_beams, num_scans, angle_min, angle_inc, thresh, divider, buffer, state3, ranges, l1l2, gap);
+  half_spaces_kernel<<<(scenes + HS_WARPS - 1) / HS_WARPS, 32 * HS_WARPS, (size_t)HS_WARPS * 2 * ((n_beams + 31) / 32) * sizeof(unsigned), st>>>(scenes, n_beams, num_scans, angle_min, angle_inc, thresh, divider, buffer, state3, ranges, l1l2, gap);
   return cudaGetLastError();
 }
 cudaError_t launch_state_from_pose(int scenes, const double* pose7, double* state3, cudaStream_t st) {
@@ -261,7 +315,7 @@ cudaError_t launch_select_build(int scenes, int paths, int samples, int N, int s
                                 const double* table_xy, const double* prev_steer, const double* l1l2, double* recs, int32_t* chosen,
                                 int32_t* best_global, cudaStream_t st) {
   if (scenes == 0) return cudaSuccess;
-  select_build_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, paths, samples, N, stride, n_wp, lookahead, v_lin, pose7, rot, wp_xy, valid,
+  select_build_kernel<<<(scenes + SB_WARPS - 1) / SB_WARPS, 32 * SB_WARPS, (size_t)SB_WARPS * n_wp * sizeof(double), st>>>(scenes, paths, samples, N, stride, n_wp, lookahead, v_lin, pose7, rot, wp_xy, valid,
                                                          end_world, table_xy, prev_steer, l1l2, recs, chosen, best_global);
   return cudaGetLastError();
 }
