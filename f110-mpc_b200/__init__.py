@@ -299,6 +299,8 @@ def host():
         H.f110h_mpc_update.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp]
         H.f110h_plan.argtypes = [C.c_int, C.c_int, dp, C.c_float, C.c_float, C.c_float, fp, C.c_int, fp, C.c_int, C.c_int, dp,
                                  C.POINTER(C.c_uint8), ip]
+        H.f110h_closed_loop.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, fp, C.c_int, dp, C.c_float, C.c_float, C.c_float,
+                                        fp, C.c_int, C.c_int, dp, ip]
         _host = H
     return _host
 
@@ -399,3 +401,19 @@ def host_plan(pose7, angle_min, angle_max, angle_inc, ranges, wp_xy, steer_discr
     idx = host().f110h_plan(steer_discrete, traj_discrete, _dp(pose7), angle_min, angle_max, angle_inc, _fp(ranges), len(ranges),
                             _fp(wp_xy), len(wp_xy), device, _dp(path), valid.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(bg))
     return idx, path, valid, bg.value
+
+
+def host_closed_loop(ticks, wp_xy, start_xyyaw, angle_min, angle_max, angle_inc, ranges, dt_tick=0.01, drive_every=2,
+                     scan_every=4, device=0):
+    """The C++ `project` orchestrator (host/project.h) driving a simulated car.  Returns (traj (ticks,5) = x, y, yaw,
+    v, steer per tick; MPC cycles solved; planning cycles)."""
+    wp_xy = np.ascontiguousarray(wp_xy, dtype=np.float32)
+    start = np.ascontiguousarray(start_xyyaw, dtype=np.float64)
+    ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+    traj = np.zeros((ticks, 5))
+    plans = C.c_int(0)
+    solved = host().f110h_closed_loop(ticks, dt_tick, drive_every, scan_every, _fp(wp_xy), len(wp_xy), _dp(start), angle_min,
+                                      angle_max, angle_inc, _fp(ranges), len(ranges), device, _dp(traj), C.byref(plans))
+    if solved < 0:
+        raise RuntimeError("closed loop failed: " + lib().f110_last_error().decode())
+    return traj, solved, plans.value

@@ -1,6 +1,7 @@
 // C shims over the C++ host classes so the Python harness (tests/, bench.py) can drive them through ctypes.
 // Poses travel as 7 doubles (px, py, pz, qx, qy, qz, qw); scans as (angle_min, angle_max, angle_increment,
 // ranges, n).  Not part of the drop-in boundary (that is include/f110_mpc_b200.h); these are conveniences.
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include "constraints.h"
@@ -8,6 +9,7 @@
 #include "mpc.h"
 #include "occupancy_grid.h"
 #include "planner.h"
+#include "project.h"
 #include "trajectory.h"
 #include "trajectory_planner.h"
 #include "transforms.h"
@@ -142,6 +144,45 @@ int f110h_plan(int steer_discrete, int traj_discrete, const double* pose7, float
   if (!ok) return -1;
   for (std::size_t k = 0; k < path.size(); ++k) { mini_path_out[3 * k] = path[k].x(); mini_path_out[3 * k + 1] = path[k].y(); mini_path_out[3 * k + 2] = path[k].ori(); }
   return planner.best_trajectory_idx();
+}
+
+// ---- closed loop: the `project` orchestrator driving a simulated car (Model::simulate_dynamics) ------------------------
+// ticks of `dt_tick` seconds; OdomCallback every tick, DriveStep every `drive_every` ticks, ScanCallback with a
+// constant scan every `scan_every` ticks.  Outputs per tick: pose (x, y, yaw) and the applied input (v, steer).
+// Returns the number of MPC cycles solved.
+int f110h_closed_loop(int ticks, double dt_tick, int drive_every, int scan_every, const float* wp_xy, int W, const double* start_xyyaw,
+                      float amin, float amax, float inc, const float* ranges, int n, int device, double* traj_out, int* plans_out) {
+  try {
+    f110::Params prm;
+    project node(prm, device);
+    std::vector<std::pair<float, float>> xy(W);
+    for (int i = 0; i < W; ++i) xy[i] = {wp_xy[2 * i], wp_xy[2 * i + 1]};
+    node.SetRaceline(xy);
+    const sensor_msgs::LaserScan scan = scan_of(amin, amax, inc, ranges, n);
+    Model plant;
+    State car(start_xyyaw[0], start_xyyaw[1], start_xyyaw[2]);
+    Input applied(0.5, 0.0);
+    for (int t = 0; t < ticks; ++t) {
+      geometry_msgs::Pose pose;
+      pose.position.x = car.x(); pose.position.y = car.y();
+      pose.orientation.z = std::sin(car.ori() / 2.0); pose.orientation.w = std::cos(car.ori() / 2.0);
+      node.OdomCallback(pose);
+      if (t % scan_every == 0) node.ScanCallback(scan);
+      if (t % drive_every == 0) {
+        Input in;
+        if (node.DriveStep(&in)) applied = in;
+      }
+      traj_out[5 * t] = car.x(); traj_out[5 * t + 1] = car.y(); traj_out[5 * t + 2] = car.ori();
+      traj_out[5 * t + 3] = applied.v(); traj_out[5 * t + 4] = applied.steer_ang();
+      State next;
+      plant.simulate_dynamics(car, applied, dt_tick, next);
+      car = next;
+    }
+    if (plans_out) *plans_out = node.cycles_planned();
+    return node.cycles_solved();
+  } catch (const std::exception&) {
+    return -1;
+  }
 }
 
 }  // extern "C"

@@ -85,3 +85,20 @@ def test_planning_cycle_matches_oracle(pkg, oracle, workloads, sd):
         assert (path[:, 2] == 0).all()
         n_planned += 1
     assert n_planned > 5
+
+
+def test_closed_loop_follows_raceline(pkg, workloads):
+    # the project orchestrator (plan -> track -> re-plan near the path end) against
+    # Model::simulate_dynamics, free scan, start on the raceline.  The car must make progress along skirk and stay near it.
+    xy, ori = workloads.skirk_waypoints()
+    scan = np.full(1080, 10.0, dtype=np.float32)
+    ticks = 600
+    traj, solved, plans = pkg.host_closed_loop(ticks, xy, [float(xy[5, 0]), float(xy[5, 1]), float(ori[5])], workloads.SCAN_ANGLE_MIN,
+                                               workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC, scan)
+    assert plans >= 3 and solved > 400                       # re-planned several times, an MPC solve on most ticks
+    d = np.sqrt(((traj[:, None, :2] - xy[None, :, :].astype(np.float64)) ** 2).sum(-1))
+    nearest = d.argmin(axis=1)
+    assert d.min(axis=1)[50:].max() < 0.8                    # stays within 0.8 m of the raceline
+    progress = (nearest[-1] - nearest[0]) % len(xy)
+    assert 150 < progress < 450                              # ~6 s at ~4.4 m/s on a 31.9 m lap of 500 points
+    assert (traj[100:, 3] >= 3.0 - 1e-3).all() and (traj[100:, 3] <= 4.5 + 1e-3).all() and (np.abs(traj[:, 4]) <= 0.43 + 1e-3).all()
