@@ -43,14 +43,14 @@ class CycleConfig(C.Structure):
     _fields_ = [("n_beams", C.c_int32), ("angle_min", C.c_float), ("angle_max", C.c_float), ("angle_increment", C.c_float),
                 ("occ_size", C.c_int32), ("occ_discrete", C.c_float), ("occ_dilation", C.c_float),
                 ("follow_gap_thresh", C.c_float), ("fov_divider", C.c_float), ("buffer", C.c_float), ("lookahead", C.c_float),
-                ("use_half_spaces", C.c_int32), ("v_lin", C.c_double)]
+                ("use_half_spaces", C.c_int32), ("qp_mode", C.c_int32), ("reserved", C.c_int32), ("v_lin", C.c_double)]
 
 
 EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
            "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
            "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma", "f110_cycle_default_config",
-           "f110_cycle_device", "f110_cycle_buffers"]
+           "f110_cycle_device", "f110_cycle_host", "f110_cycle_buffers"]
 
 
 def build(force=False, verbose=False):
@@ -96,6 +96,7 @@ def lib():
         L.f110_cycle_default_config.argtypes = [C.POINTER(CycleConfig)]
         L.f110_cycle_device.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int,
                                         vp, vp, vp, vp, vp, vp]
+        L.f110_cycle_host.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
         L.f110_cycle_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
         _lib = L
     return _lib
@@ -199,7 +200,24 @@ class MpcSolver:
                                        table_xy.shape[0], table_xy.shape[1], _tp(wp_xy), wp_xy.shape[0], _tp(u0), _tp(status),
                                        _tp(iters), _tp(chosen), _tp(valid), sp), "f110_cycle_device")
 
-    def cycle_buffers(self, scenes):
+    def cycle_host(self, cc, pose7, ranges, prev_steer, table_xy, wp_xy, out=None):
+        """f110_cycle_host: numpy in / numpy out.  Returns dict(u0, status, iters, chosen, valid)."""
+        pose7 = np.ascontiguousarray(pose7, dtype=np.float64); ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        table_xy = np.ascontiguousarray(table_xy, dtype=np.float64); wp_xy = np.ascontiguousarray(wp_xy, dtype=np.float32)
+        S, P = pose7.shape[0], table_xy.shape[0]
+        nqp = S if cc.qp_mode == 0 else S * P
+        out = out or {}
+        u0 = out.get("u0", np.empty((nqp, 2))); status = out.get("status", np.empty(nqp, dtype=np.int32))
+        iters = out.get("iters", np.empty(nqp, dtype=np.int32)); chosen = out.get("chosen", np.empty(S, dtype=np.int32))
+        valid = out.get("valid", np.empty((S, P), dtype=np.uint8))
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        if prev_steer is not None:
+            prev_steer = np.ascontiguousarray(prev_steer, dtype=np.float64)
+        _check(lib().f110_cycle_host(self._h, C.byref(cc), S, vp(pose7), vp(ranges), vp(prev_steer), vp(table_xy), P, table_xy.shape[1],
+                                     vp(wp_xy), wp_xy.shape[0], vp(u0), vp(status), vp(iters), vp(chosen), vp(valid)), "f110_cycle_host")
+        return dict(u0=u0, status=status, iters=iters, chosen=chosen, valid=valid)
+
+    def cycle_buffers(self, scenes, nrec=None):
         """Torch views (no copy) of the device buffers the last cycle filled:
         dict(grid (S, blocks^2) f32, offset (S,2) f32, l1l2 (S,6) f64, recs (S, 11+3N) f64, best_global (S,) i32)."""
         import torch
@@ -214,7 +232,7 @@ class MpcSolver:
             return torch.as_tensor(_Dev(ptr.value, shape, typestr), device="cuda:%d" % self.device)
         blocks2 = 100 * 100
         return dict(grid=view(ptrs[0], (scenes, blocks2), "<f4"), offset=view(ptrs[1], (scenes, 2), "<f4"),
-                    l1l2=view(ptrs[2], (scenes, 6), "<f8"), recs=view(ptrs[3], (scenes, record_doubles(self.N)), "<f8"),
+                    l1l2=view(ptrs[2], (scenes, 6), "<f8"), recs=view(ptrs[3], (nrec or scenes, record_doubles(self.N)), "<f8"),
                     best_global=view(ptrs[4], (scenes,), "<i4"))
 
     def reset(self):

@@ -52,9 +52,10 @@ cudaError_t launch_half_spaces(int scenes, int n_beams, int num_scans, float ang
                                float buffer, const double* state3, const float* ranges, double* l1l2, int32_t* gap, cudaStream_t st);
 cudaError_t launch_state_from_pose(int scenes, const double* pose7, double* state3, cudaStream_t st);
 cudaError_t launch_rotation(int scenes, const double* pose7, double* rot, double* pose_xy, cudaStream_t st);
-cudaError_t launch_select_build(int scenes, int paths, int samples, int N, int stride, int n_wp, float lookahead, double v_lin,
-                                const double* pose7, const double* rot, const float* wp_xy, const uint8_t* valid, const float* end_world,
-                                const double* table_xy, const double* prev_steer, const double* l1l2, double* recs, int32_t* chosen,
-                                int32_t* best_global, cudaStream_t st);
+cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,
+                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st);
+cudaError_t launch_build_records(int scenes, int paths, int samples, int N, int stride, int qp_mode, double v_lin, const double* pose7,
+                                 const double* rot, const uint8_t* valid, const int32_t* chosen, const double* table_xy,
+                                 const double* prev_steer, const double* l1l2, double* recs, cudaStream_t st);
 
 }  // namespace f110

@@ -38,6 +38,8 @@ struct f110_mpc_solver {
   unsigned char* h_pin = nullptr;   // pinned: records of <= kSmallBatch QPs, then their outputs
   size_t out_bytes = 0;
   double* d_packed_next = nullptr;
+  unsigned char* cyc_stage = nullptr;  // device staging of f110_cycle_host
+  size_t cyc_stage_bytes = 0;
   // f110_cycle_device scratch (allocated on first use, sized for max_batch scenes)
   struct Cycle {
     int blocks = 0, paths = 0;
@@ -129,6 +131,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaFree(s->d_scratch);
   cudaFree(s->d_recs); cudaFree(s->d_out);
   s->cyc.release();
+  cudaFree(s->cyc_stage);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -244,6 +247,8 @@ void f110_cycle_default_config(f110_cycle_config* c) {
   c->follow_gap_thresh = 3.0f; c->fov_divider = 1.5f; c->buffer = 3.0f;
   c->lookahead = 2.5f;
   c->use_half_spaces = 1;
+  c->qp_mode = 0;
+  c->reserved = 0;
   c->v_lin = 4.5;
 }
 
@@ -251,7 +256,9 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                       const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy, int n_wp,
                       double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid, void* cuda_stream) {
   if (!s || !cc || !d_pose7 || !d_ranges || !d_table_xy || !d_wp_xy || !d_chosen) return fail(F110_ERR_ARG, "f110_cycle_device: null argument");
-  if (scenes < 0 || scenes > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: scenes exceed max_batch");
+  if (cc->qp_mode < 0 || cc->qp_mode > 2) return fail(F110_ERR_ARG, "f110_cycle_device: bad qp_mode");
+  const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
+  if (scenes < 0 || nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: QP count exceeds max_batch");
   if (paths <= 0 || samples <= 0 || n_wp <= 0 || cc->n_beams <= 0) return fail(F110_ERR_ARG, "f110_cycle_device: bad sizes");
   s->last_launches = 0;
   if (scenes == 0) return F110_OK;
@@ -292,14 +299,63 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                                                        cc->fov_divider, cc->buffer, c.state3, d_ranges, c.l1l2, c.gap, st);
     launches += 2;
   }
-  if (e == cudaSuccess) e = f110::launch_select_build(scenes, paths, samples, N, rd, n_wp, cc->lookahead, cc->v_lin, d_pose7, c.rot, d_wp_xy,
-                                                      valid, c.endw, d_table_xy, d_prev_steer, cc->use_half_spaces ? c.l1l2 : nullptr, c.recs,
-                                                      d_chosen, c.best_global, st);
-  ++launches;
+  if (e == cudaSuccess) e = f110::launch_select(scenes, paths, n_wp, cc->lookahead, d_pose7, d_wp_xy, valid, c.endw, d_chosen, c.best_global, st);
+  if (e == cudaSuccess) e = f110::launch_build_records(scenes, paths, samples, N, rd, cc->qp_mode, cc->v_lin, d_pose7, c.rot, valid, d_chosen,
+                                                       d_table_xy, d_prev_steer, cc->use_half_spaces ? c.l1l2 : nullptr, c.recs, st);
+  launches += 2;
   if (e != cudaSuccess) return cuda_fail(e, "f110_cycle_device: kernel launch");
-  const int rc = f110_mpc_solve_device(s, scenes, c.recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
+  const int rc = f110_mpc_solve_device(s, (int)nqp, c.recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
   s->last_launches += launches;
   return rc;
+}
+
+int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
+                    const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp, double* u0,
+                    int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid) {
+  if (!s || !cc || !pose7 || !ranges || !table_xy || !wp_xy) return fail(F110_ERR_ARG, "f110_cycle_host: null argument");
+  if (scenes <= 0) return scenes == 0 ? F110_OK : fail(F110_ERR_ARG, "f110_cycle_host: negative scene count");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
+  if (nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_host: QP count exceeds max_batch");
+  // one staging block on the device, grown on demand: inputs then outputs
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t b_pose = up((size_t)scenes * 7 * sizeof(double)), b_rng = up((size_t)scenes * cc->n_beams * sizeof(float));
+  const size_t b_prev = up((size_t)scenes * sizeof(double)), b_tab = up((size_t)paths * samples * 2 * sizeof(double));
+  const size_t b_wp = up((size_t)n_wp * 2 * sizeof(float)), b_u0 = up((size_t)nqp * 2 * sizeof(double)), b_i = up((size_t)nqp * sizeof(int32_t));
+  const size_t b_ch = up((size_t)scenes * sizeof(int32_t)), b_val = up((size_t)scenes * paths);
+  const size_t total = b_pose + b_rng + b_prev + b_tab + b_wp + b_u0 + 2 * b_i + b_ch + b_val;
+  if (total > s->cyc_stage_bytes) {
+    cudaFree(s->cyc_stage); s->cyc_stage = nullptr; s->cyc_stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s->cyc_stage, total));
+    s->cyc_stage_bytes = total;
+  }
+  unsigned char* q = s->cyc_stage;
+  double* d_pose = (double*)q; q += b_pose;
+  float* d_rng = (float*)q; q += b_rng;
+  double* d_prev = (double*)q; q += b_prev;
+  double* d_tab = (double*)q; q += b_tab;
+  float* d_wp = (float*)q; q += b_wp;
+  double* d_u0 = (double*)q; q += b_u0;
+  int32_t* d_st = (int32_t*)q; q += b_i;
+  int32_t* d_it = (int32_t*)q; q += b_i;
+  int32_t* d_ch = (int32_t*)q; q += b_ch;
+  uint8_t* d_val = (uint8_t*)q;
+  cudaStream_t st = s->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_pose, pose7, (size_t)scenes * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_rng, ranges, (size_t)scenes * cc->n_beams * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (prev_steer) CUDA_TRY(cudaMemcpyAsync(d_prev, prev_steer, (size_t)scenes * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_tab, table_xy, (size_t)paths * samples * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_wp, wp_xy, (size_t)n_wp * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int rc = f110_cycle_device(s, cc, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp, d_u0, d_st,
+                                   d_it, d_ch, d_val, st);
+  if (rc != F110_OK) return rc;
+  if (u0) CUDA_TRY(cudaMemcpyAsync(u0, d_u0, (size_t)nqp * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, (size_t)nqp * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (iters) CUDA_TRY(cudaMemcpyAsync(iters, d_it, (size_t)nqp * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (chosen) CUDA_TRY(cudaMemcpyAsync(chosen, d_ch, (size_t)scenes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (valid) CUDA_TRY(cudaMemcpyAsync(valid, d_val, (size_t)scenes * paths, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return F110_OK;
 }
 
 int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs, int32_t** d_best_global) {

@@ -195,31 +195,25 @@ __global__ void __launch_bounds__(128) state_from_pose_kernel(int scenes, const 
   state3[3 * sc + 2] = (double)(float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);
 }
 
-// ---- look-ahead point, best surviving path, parameter record: one warp per scene.  The lanes evaluate the per-waypoint
-// distances and write the record; the two argmin scans stay sequential on lane 0 because their result depends on the
+// ---- look-ahead point and best surviving path: one warp per scene.  The lanes evaluate the per-waypoint
+// distances; the two argmin scans stay sequential on lane 0 because their result depends on the
 // visiting order (strict <, float-narrowed running minimum — trajectory.cpp:103-107, project.cpp:132-135).
 constexpr int SB_WARPS = 4;
-__global__ void __launch_bounds__(32 * SB_WARPS) select_build_kernel(int scenes, int paths, int samples, int N, int stride, int n_wp,
-                                                                    float lookahead, double v_lin,
-                                                                    const double* __restrict__ pose7, const double* __restrict__ rot,
-                                                                    const float* __restrict__ wp_xy, const uint8_t* __restrict__ valid,
-                                                                    const float* __restrict__ end_world, const double* __restrict__ table_xy,
-                                                                    const double* __restrict__ prev_steer, const double* __restrict__ l1l2,
-                                                                    double* __restrict__ recs, int32_t* __restrict__ chosen,
-                                                                    int32_t* __restrict__ best_global) {
+__global__ void __launch_bounds__(32 * SB_WARPS) select_kernel(int scenes, int paths, int n_wp, float lookahead,
+                                                              const double* __restrict__ pose7, const float* __restrict__ wp_xy,
+                                                              const uint8_t* __restrict__ valid, const float* __restrict__ end_world,
+                                                              int32_t* __restrict__ chosen, int32_t* __restrict__ best_global) {
   extern __shared__ double off_sm[];  // SB_WARPS x n_wp look-ahead offsets (negative = waypoint behind the car)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sc = blockIdx.x * SB_WARPS + warp;
   if (sc >= scenes) return;
   double* offs = off_sm + (size_t)warp * n_wp;
   const double* p = pose7 + 7 * (size_t)sc;
-  double* rec = recs + (size_t)sc * stride;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   // any valid path? (project.cpp:115-119)
   bool mine = false;
   for (int i = lane; i < paths; i += 32) mine |= valid[(size_t)sc * paths + i] != 0;
   if (!__any_sync(0xffffffffu, mine)) {
-    if (lane == 0) { chosen[sc] = -1; best_global[sc] = -1; rec[3] = qnan; }  // empty slot: the solve kernel reports F110_UNSOLVED
+    if (lane == 0) { chosen[sc] = -1; best_global[sc] = -1; }
     return;
   }
   // Transforms::WorldToCarTransform (transforms.cpp:22-31) then TransformPoint per waypoint (:33-44)
@@ -261,12 +255,31 @@ __global__ void __launch_bounds__(32 * SB_WARPS) select_build_kernel(int scenes,
     best_global[sc] = best_idx;
     chosen[sc] = pick;
   }
-  pick = __shfl_sync(0xffffffffu, pick, 0);
+}
+
+// ---- parameter records (include/f110_mpc_b200.h: x0 | (v, steer) | l1 | l2 | ref[0..N-1]), one warp per record ------------
+// qp_mode 0: one record per scene, for the selected path (the reference's behaviour, project.cpp:141-149 + mpc.cpp:69-80)
+// qp_mode 1: one record per (scene, path), empty where the path collides  (BASELINE config 2: a QP per surviving path)
+// qp_mode 2: one record per (scene, path), colliding paths included
+__global__ void __launch_bounds__(32 * SB_WARPS) build_records_kernel(int scenes, int paths, int samples, int N, int stride, int qp_mode,
+                                                                     double v_lin, const double* __restrict__ pose7,
+                                                                     const double* __restrict__ rot, const uint8_t* __restrict__ valid,
+                                                                     const int32_t* __restrict__ chosen, const double* __restrict__ table_xy,
+                                                                     const double* __restrict__ prev_steer, const double* __restrict__ l1l2,
+                                                                     double* __restrict__ recs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long slot = (long long)blockIdx.x * SB_WARPS + warp;
+  const long long nslots = qp_mode == 0 ? scenes : (long long)scenes * paths;
+  if (slot >= nslots) return;
+  const int sc = qp_mode == 0 ? (int)slot : (int)(slot / paths);
+  int pick = qp_mode == 0 ? chosen[sc] : (int)(slot % paths);
+  if (qp_mode == 1 && !valid[(size_t)sc * paths + pick]) pick = -1;
+  double* rec = recs + (size_t)slot * stride;
   if (pick < 0) {
-    if (lane == 0) rec[3] = qnan;
+    if (lane == 0) rec[3] = __longlong_as_double(0x7ff8000000000000LL);  // empty slot: the solve kernel reports F110_UNSOLVED
     return;
   }
-  // parameter record (include/f110_mpc_b200.h): x0 | (v, steer) | l1 | l2 | ref[0..N-1]
+  const double* p = pose7 + 7 * (size_t)sc;
   if (lane == 0) {
     const float yaw = (float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);       // Transforms::GetCarOrientation (float)
     rec[0] = p[0]; rec[1] = p[1]; rec[2] = (double)yaw;                         // project.cpp:163-164
@@ -310,13 +323,20 @@ cudaError_t launch_rotation(int scenes, const double* pose7, double* rot, double
   rotation_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, pose7, rot, pose_xy);
   return cudaGetLastError();
 }
-cudaError_t launch_select_build(int scenes, int paths, int samples, int N, int stride, int n_wp, float lookahead, double v_lin,
-                                const double* pose7, const double* rot, const float* wp_xy, const uint8_t* valid, const float* end_world,
-                                const double* table_xy, const double* prev_steer, const double* l1l2, double* recs, int32_t* chosen,
-                                int32_t* best_global, cudaStream_t st) {
+cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,
+                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st) {
   if (scenes == 0) return cudaSuccess;
-  select_build_kernel<<<(scenes + SB_WARPS - 1) / SB_WARPS, 32 * SB_WARPS, (size_t)SB_WARPS * n_wp * sizeof(double), st>>>(scenes, paths, samples, N, stride, n_wp, lookahead, v_lin, pose7, rot, wp_xy, valid,
-                                                         end_world, table_xy, prev_steer, l1l2, recs, chosen, best_global);
+  select_kernel<<<(scenes + SB_WARPS - 1) / SB_WARPS, 32 * SB_WARPS, (size_t)SB_WARPS * n_wp * sizeof(double), st>>>(
+      scenes, paths, n_wp, lookahead, pose7, wp_xy, valid, end_world, chosen, best_global);
+  return cudaGetLastError();
+}
+cudaError_t launch_build_records(int scenes, int paths, int samples, int N, int stride, int qp_mode, double v_lin, const double* pose7,
+                                 const double* rot, const uint8_t* valid, const int32_t* chosen, const double* table_xy,
+                                 const double* prev_steer, const double* l1l2, double* recs, cudaStream_t st) {
+  const long long nslots = qp_mode == 0 ? scenes : (long long)scenes * paths;
+  if (nslots == 0) return cudaSuccess;
+  build_records_kernel<<<(unsigned)((nslots + SB_WARPS - 1) / SB_WARPS), 32 * SB_WARPS, 0, st>>>(
+      scenes, paths, samples, N, stride, qp_mode, v_lin, pose7, rot, valid, chosen, table_xy, prev_steer, l1l2, recs);
   return cudaGetLastError();
 }
 

@@ -149,6 +149,13 @@ typedef struct f110_cycle_config {
   float follow_gap_thresh, fov_divider, buffer;    /* constraints.cpp:9-12 */
   float lookahead;                                 /* trajectory.cpp:10 */
   int32_t use_half_spaces;                         /* 1: l1, l2 from each scene's scan; 0: zero rows */
+  int32_t qp_mode;                                 /* 0: one QP per scene, for the selected path (the reference's behaviour);
+                                                      1: one QP per (scene, path), skipped (F110_UNSOLVED) where the path collides
+                                                         — BASELINE config 2, "a QP per surviving path";
+                                                      2: one QP per (scene, path), colliding paths included.
+                                                      Modes 1, 2: outputs u0/status/iters have scenes*paths rows (slot = scene*paths + path)
+                                                      and scenes*paths must not exceed max_batch. */
+  int32_t reserved;
   double v_lin;                                    /* linearisation speed, 4.5 (project.cpp:170) */
 } f110_cycle_config;
 void f110_cycle_default_config(f110_cycle_config* c);
@@ -161,6 +168,11 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                       const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy,
                       int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid,
                       void* cuda_stream);
+/* Same cycle, HOST buffers (copies in, runs, copies back, synchronises): the reference-facing call for a whole
+ * planning + control cycle — laser scans and poses in, controls out.  valid may be NULL. */
+int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
+                    const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp,
+                    double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid);
 /* Device buffers the last f110_cycle_device call filled (for inspection / tests): grids (scenes x blocks^2 floats),
  * offsets (x2 floats), l1l2 (x6 doubles), records (x record_doubles), best_global (int32). Any pointer may be NULL. */
 int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs,

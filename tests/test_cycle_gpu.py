@@ -35,7 +35,7 @@ def test_cycle_matches_oracle_pipeline(pkg, oracle, workloads, sd):
     S, N = 96, 30
     amin, amax, inc = workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC
     r = _run_cycle(pkg, workloads, S, sd, seed=31 + sd)
-    assert r["launches"] == 7                           # fill, rotation, check, state, half-planes, select/build, solve
+    assert r["launches"] == 8                           # fill, rotation, check, state, half-planes, select, build, solve
     cell_mismatch = 0
     recs_o = []
     n_none = 0
@@ -81,9 +81,47 @@ def test_cycle_matches_oracle_pipeline(pkg, oracle, workloads, sd):
 
 def test_cycle_without_half_spaces_and_long_horizon(pkg, oracle, workloads):
     r = _run_cycle(pkg, workloads, 40, 19, seed=5, use_half_spaces=0, N=50)
-    assert r["launches"] == 5
+    assert r["launches"] == 6
     ok = r["chosen"] >= 0
     assert ok.any() and (r["recs"][ok][:, 5:11] == 0).all()
     o = oracle.MpcBatch(oracle.default_cfg(50), oracle.default_settings(warm_start=0), int(ok.sum())).solve(r["recs"][ok])
     np.testing.assert_array_equal(r["status"][ok], o["status"])
     np.testing.assert_allclose(r["u0"][ok], o["x"][:, 3 * 51:3 * 51 + 2], atol=1e-4, rtol=1e-3)
+
+
+@pytest.mark.parametrize("qp_mode", [1, 2])
+def test_cycle_qp_per_path_modes(pkg, oracle, workloads, qp_mode):
+    # BASELINE config 2: a tracking QP per surviving mini-path (mode 1), or per candidate path (mode 2), built on the device
+    S, sd, N = 48, 19, 30
+    P = sd + 1
+    poses, yaws, scans = workloads.scene_batch(S, seed=77)
+    table = np.ascontiguousarray(workloads.traj_table(steer_discrete=sd)[:, :, :2])
+    xy, _ = workloads.skirk_waypoints()
+    sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(warm_start=0), max_batch=S * P)
+    cc = pkg.default_cycle_config(qp_mode=qp_mode)
+    prev = np.linspace(-0.2, 0.2, S)
+    g = sol.cycle_host(cc, poses, scans, prev, table, xy)
+    assert g["u0"].shape == (S * P, 2)
+    recs = sol.cycle_buffers(S, S * P)["recs"].cpu().numpy()
+    valid = g["valid"].reshape(-1).astype(bool)
+    assert 0 < valid.sum() < S * P
+    solve = valid if qp_mode == 1 else np.ones(S * P, dtype=bool)
+    assert (g["status"][~solve] == -10).all() and np.isnan(g["u0"][~solve]).all() and np.isnan(recs[~solve][:, 3]).all()
+    # every built record carries its scene's state / steering and its own path
+    for slot in np.nonzero(solve)[0][::7]:
+        s_, p_ = divmod(int(slot), P)
+        assert recs[slot, 0] == poses[s_, 0] and recs[slot, 4] == prev[s_] and recs[slot, 3] == 4.5
+        R = oracle.car_to_world_R(poses[s_])
+        _, _, ew = oracle.collision_check(np.zeros(10000, dtype=np.float32), 100, 0.1, np.array([poses[s_, 0], poses[s_, 1]], dtype=np.float32),
+                                          R, poses[s_, :2], table[p_:p_ + 1, N - 1:N, :])
+        np.testing.assert_array_equal(recs[slot, 11 + 3 * (N - 1): 13 + 3 * (N - 1)].astype(np.float32), ew[0])
+    o = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(warm_start=0), int(solve.sum())).solve(recs[solve])
+    np.testing.assert_array_equal(g["status"][solve], o["status"])
+    np.testing.assert_array_equal(g["iters"][solve], o["iters"])
+    np.testing.assert_allclose(g["u0"][solve], o["x"][:, 3 * (N + 1):3 * (N + 1) + 2], atol=1e-4, rtol=1e-3)
+    # the selected path of each scene is one of its valid ones
+    v2 = g["valid"].astype(bool)
+    for s_ in range(S):
+        assert (g["chosen"][s_] == -1) == (not v2[s_].any())
+        if g["chosen"][s_] >= 0:
+            assert v2[s_, g["chosen"][s_]]
