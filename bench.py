@@ -82,44 +82,60 @@ def build_workload(M, W, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled through NVML from a thread (the region lasts a few
+    milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query when NVML is unavailable."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self._nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        if self._nvml is None:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "how": "nvidia-smi after the region"}
             except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self._stop.set()
+        self._thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": "NVML polled from a thread during the timed region"}
 
 
 def cpu_reference_run(recs, steps, warmup, nthreads=0):
@@ -307,8 +323,16 @@ def main_product(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = B * hbm_bytes_per_qp(N_HORIZON) / admm_s_per_launch / 1e9
+    traffic = None
+    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload size)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "admm_traffic.json")))
+        if tj.get("qps_per_launch") == B:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64_issue", "kernel": "admm_kernel", "achieved": achieved_tf, "peak": peak_fp64, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_fp64, "traffic": None,
+                "frac": achieved_tf / peak_fp64, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "algorithmic_bytes_per_launch": B * hbm_bytes_per_qp(N_HORIZON),
                 "peak_source": "DFMA micro-benchmark in this run (f110_bench_fp64_fma); MEASURED_PEAKS.json has no FP64 figure",
                 "algorithmic_flops_per_launch": flops_launch, "launch_ms": admm_s_per_launch * 1e3,
                 "mean_iters": float(iters.mean()), "rho_updates_mean": float(rhoup.mean()),
