@@ -260,6 +260,8 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (scenes < 0 || nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: QP count exceeds max_batch");
   if (paths <= 0 || samples <= 0 || n_wp <= 0 || cc->n_beams <= 0) return fail(F110_ERR_ARG, "f110_cycle_device: bad sizes");
+  if (n_wp > 1500) return fail(F110_ERR_UNSUPPORTED, "f110_cycle_device: more than 1500 raceline waypoints (shared-memory staging)");
+  if (reinterpret_cast<uintptr_t>(d_table_xy) % 16) return fail(F110_ERR_ARG, "f110_cycle_device: table_xy must be 16-byte aligned");
   s->last_launches = 0;
   if (scenes == 0) return F110_OK;
   CUDA_TRY(cudaSetDevice(s->device));
@@ -374,6 +376,7 @@ int f110_collision_check_device(int scenes, int paths, int samples, int blocks, 
   if (scenes < 0 || paths <= 0 || samples <= 0 || blocks <= 0) return fail(F110_ERR_ARG, "f110_collision_check: bad sizes");
   if (!d_grid || !d_offset || !d_rot || !d_pose_xy || !d_table_xy || !d_valid || !d_free_count || !d_end_world)
     return fail(F110_ERR_ARG, "f110_collision_check: null buffer");
+  if (reinterpret_cast<uintptr_t>(d_table_xy) % 16) return fail(F110_ERR_ARG, "f110_collision_check: table_xy must be 16-byte aligned");
   cudaError_t e = f110::launch_collision(scenes, paths, samples, blocks, discrete, d_grid, d_offset, d_rot, d_pose_xy, d_table_xy,
                                          d_valid, d_free_count, d_end_world, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "collision kernel launch");
