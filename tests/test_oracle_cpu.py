@@ -203,3 +203,22 @@ def test_oracle_reproduces_golden(oracle, name):
     np.testing.assert_array_equal(r["iters"], g["iters"])
     np.testing.assert_allclose(r["x"], g["x"], atol=1e-9, rtol=1e-9, equal_nan=True)
     np.testing.assert_allclose(r["y"], g["y"], atol=1e-7, rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("N,eps", [(5, 1e-3), (12, 1e-4), (30, 1e-3), (30, 1e-6)])
+def test_cpp_restatement_vs_independent_numpy_osqp(oracle, workloads, N, eps):
+    # iterate-level cross-check of the C++ sparse restatement against an independent dense numpy statement of OSQP:
+    # same iteration counts, same rho updates, same solution
+    from osqp_numpy import solve
+    B = 5
+    recs = workloads.tracking_batch(B, N, seed=900 + N)
+    cfg = oracle.default_cfg(N)
+    r = oracle.MpcBatch(cfg, oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B, 1).solve(recs)
+    for b in range(B):
+        P, q, A, l, u = oracle.mpc_assemble_dense(cfg, recs[b])
+        o = solve(P, q, A, l, u, eps_abs=eps, eps_rel=eps)
+        assert o["status"] == r["status"][b] == 1
+        assert o["iters"] == r["iters"][b] and o["rho_updates"] == r["rho_updates"][b]
+        np.testing.assert_allclose(r["x"][b], o["x"], atol=1e-7, rtol=1e-7)
+        np.testing.assert_allclose(r["y"][b], o["y"], atol=1e-5, rtol=1e-6)
+        assert abs(r["rho"][b] - o["rho"]) <= 1e-6 * o["rho"]
