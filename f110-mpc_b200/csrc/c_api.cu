@@ -40,6 +40,9 @@ struct f110_mpc_solver {
   double* d_packed_next = nullptr;
   unsigned char* cyc_stage = nullptr;  // device staging of f110_cycle_host
   size_t cyc_stage_bytes = 0;
+  unsigned char* cyc_pin = nullptr;    // pinned mirror of the output block
+  size_t cyc_pin_bytes = 0;
+  unsigned long long cyc_tab_hash = 0; // content hash of the uploaded mini-path table + raceline
   // f110_cycle_device scratch (allocated on first use, sized for max_batch scenes)
   struct Cycle {
     int blocks = 0, paths = 0;
@@ -132,6 +135,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaFree(s->d_recs); cudaFree(s->d_out);
   s->cyc.release();
   cudaFree(s->cyc_stage);
+  if (s->cyc_pin) cudaFreeHost(s->cyc_pin);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -289,18 +293,12 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   // beam count from the float expression of occupancy_grid.cpp:66 / constraints.cpp:118
   const int num_scans = (int)((cc->angle_max - cc->angle_min) / cc->angle_increment + 1);
   uint8_t* valid = d_valid ? d_valid : c.valid;
-  cudaError_t e = f110::launch_fill_grid(scenes, blocks, cc->occ_discrete, cc->occ_dilation, cc->n_beams, num_scans, cc->angle_min,
-                                         cc->angle_increment, d_pose7, d_ranges, c.grid, c.offset, st);
-  if (e == cudaSuccess) e = f110::launch_rotation(scenes, d_pose7, c.rot, c.pose_xy, st);
+  cudaError_t e = f110::launch_scene_prep(scenes, blocks, cc->occ_discrete, cc->occ_dilation, cc->n_beams, num_scans, cc->angle_min,
+                                          cc->angle_increment, cc->follow_gap_thresh, cc->fov_divider, cc->buffer, d_pose7, d_ranges, c.grid,
+                                          c.offset, c.rot, c.pose_xy, cc->use_half_spaces ? c.l1l2 : nullptr, c.gap, st);
   if (e == cudaSuccess) e = f110::launch_collision(scenes, paths, samples, blocks, cc->occ_discrete, c.grid, c.offset, c.rot, c.pose_xy,
                                                    d_table_xy, valid, c.free_cnt, c.endw, st);
-  int launches = 3;
-  if (e == cudaSuccess && cc->use_half_spaces) {
-    e = f110::launch_state_from_pose(scenes, d_pose7, c.state3, st);
-    if (e == cudaSuccess) e = f110::launch_half_spaces(scenes, cc->n_beams, num_scans, cc->angle_min, cc->angle_increment, cc->follow_gap_thresh,
-                                                       cc->fov_divider, cc->buffer, c.state3, d_ranges, c.l1l2, c.gap, st);
-    launches += 2;
-  }
+  int launches = 2;
   if (e == cudaSuccess) e = f110::launch_select(scenes, paths, n_wp, cc->lookahead, d_pose7, d_wp_xy, valid, c.endw, d_chosen, c.best_global, st);
   if (e == cudaSuccess) e = f110::launch_build_records(scenes, paths, samples, N, rd, cc->qp_mode, cc->v_lin, d_pose7, c.rot, valid, d_chosen,
                                                        d_table_xy, d_prev_steer, cc->use_half_spaces ? c.l1l2 : nullptr, c.recs, st);
@@ -319,17 +317,26 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
   CUDA_TRY(cudaSetDevice(s->device));
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_host: QP count exceeds max_batch");
-  // one staging block on the device, grown on demand: inputs then outputs
+  // One staging block on the device (grown on demand): [inputs | table | waypoints | outputs].  The outputs are contiguous so
+  // they come back in ONE copy (into a pinned mirror, then scattered to the caller's arrays).  The mini-path table and the
+  // raceline are start-up constants in the reference (project.cpp:34-37): they are uploaded only when their bytes change.
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t n_tab = (size_t)paths * samples * 2 * sizeof(double), n_wpb = (size_t)n_wp * 2 * sizeof(float);
   const size_t b_pose = up((size_t)scenes * 7 * sizeof(double)), b_rng = up((size_t)scenes * cc->n_beams * sizeof(float));
-  const size_t b_prev = up((size_t)scenes * sizeof(double)), b_tab = up((size_t)paths * samples * 2 * sizeof(double));
-  const size_t b_wp = up((size_t)n_wp * 2 * sizeof(float)), b_u0 = up((size_t)nqp * 2 * sizeof(double)), b_i = up((size_t)nqp * sizeof(int32_t));
-  const size_t b_ch = up((size_t)scenes * sizeof(int32_t)), b_val = up((size_t)scenes * paths);
-  const size_t total = b_pose + b_rng + b_prev + b_tab + b_wp + b_u0 + 2 * b_i + b_ch + b_val;
-  if (total > s->cyc_stage_bytes) {
+  const size_t b_prev = up((size_t)scenes * sizeof(double)), b_tab = up(n_tab), b_wp = up(n_wpb);
+  const size_t o_u0 = 0, o_st = o_u0 + up((size_t)nqp * 2 * sizeof(double)), o_it = o_st + up((size_t)nqp * sizeof(int32_t));
+  const size_t o_ch = o_it + up((size_t)nqp * sizeof(int32_t)), o_val = o_ch + up((size_t)scenes * sizeof(int32_t));
+  const size_t b_out = o_val + up((size_t)scenes * paths);
+  const size_t total = b_pose + b_rng + b_prev + b_tab + b_wp + b_out;
+  if (total > s->cyc_stage_bytes || b_out > s->cyc_pin_bytes) {
     cudaFree(s->cyc_stage); s->cyc_stage = nullptr; s->cyc_stage_bytes = 0;
+    if (s->cyc_pin) cudaFreeHost(s->cyc_pin);
+    s->cyc_pin = nullptr; s->cyc_pin_bytes = 0;
+    s->cyc_tab_hash = 0;
     CUDA_TRY(cudaMalloc(&s->cyc_stage, total));
     s->cyc_stage_bytes = total;
+    CUDA_TRY(cudaHostAlloc(&s->cyc_pin, b_out, cudaHostAllocDefault));
+    s->cyc_pin_bytes = b_out;
   }
   unsigned char* q = s->cyc_stage;
   double* d_pose = (double*)q; q += b_pose;
@@ -337,26 +344,36 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
   double* d_prev = (double*)q; q += b_prev;
   double* d_tab = (double*)q; q += b_tab;
   float* d_wp = (float*)q; q += b_wp;
-  double* d_u0 = (double*)q; q += b_u0;
-  int32_t* d_st = (int32_t*)q; q += b_i;
-  int32_t* d_it = (int32_t*)q; q += b_i;
-  int32_t* d_ch = (int32_t*)q; q += b_ch;
-  uint8_t* d_val = (uint8_t*)q;
+  unsigned char* d_out = q;
   cudaStream_t st = s->stream;
   CUDA_TRY(cudaMemcpyAsync(d_pose, pose7, (size_t)scenes * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_rng, ranges, (size_t)scenes * cc->n_beams * sizeof(float), cudaMemcpyHostToDevice, st));
   if (prev_steer) CUDA_TRY(cudaMemcpyAsync(d_prev, prev_steer, (size_t)scenes * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_tab, table_xy, (size_t)paths * samples * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_wp, wp_xy, (size_t)n_wp * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-  const int rc = f110_cycle_device(s, cc, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp, d_u0, d_st,
-                                   d_it, d_ch, d_val, st);
+  // FNV-1a over the constant tables (20 KB): cheaper than two more copies per cycle
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&h](const void* ptr, size_t n) {
+    const unsigned long long* w = static_cast<const unsigned long long*>(ptr);
+    for (size_t i = 0; i < n / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+  };
+  mix(table_xy, n_tab); mix(wp_xy, n_wpb);
+  h ^= (unsigned long long)paths * 1315423911ull + (unsigned long long)samples * 2654435761ull + (unsigned long long)n_wp;
+  if (h != s->cyc_tab_hash) {
+    CUDA_TRY(cudaMemcpyAsync(d_tab, table_xy, n_tab, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_wp, wp_xy, n_wpb, cudaMemcpyHostToDevice, st));
+    s->cyc_tab_hash = h;
+  }
+  const int rc = f110_cycle_device(s, cc, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp,
+                                   (double*)(d_out + o_u0), (int32_t*)(d_out + o_st), (int32_t*)(d_out + o_it), (int32_t*)(d_out + o_ch),
+                                   d_out + o_val, st);
   if (rc != F110_OK) return rc;
-  if (u0) CUDA_TRY(cudaMemcpyAsync(u0, d_u0, (size_t)nqp * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, (size_t)nqp * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (iters) CUDA_TRY(cudaMemcpyAsync(iters, d_it, (size_t)nqp * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (chosen) CUDA_TRY(cudaMemcpyAsync(chosen, d_ch, (size_t)scenes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (valid) CUDA_TRY(cudaMemcpyAsync(valid, d_val, (size_t)scenes * paths, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(s->cyc_pin, d_out, b_out, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned char* ho = s->cyc_pin;
+  if (u0) std::memcpy(u0, ho + o_u0, (size_t)nqp * 2 * sizeof(double));
+  if (status) std::memcpy(status, ho + o_st, (size_t)nqp * sizeof(int32_t));
+  if (iters) std::memcpy(iters, ho + o_it, (size_t)nqp * sizeof(int32_t));
+  if (chosen) std::memcpy(chosen, ho + o_ch, (size_t)scenes * sizeof(int32_t));
+  if (valid) std::memcpy(valid, ho + o_val, (size_t)scenes * paths);
   return F110_OK;
 }
 

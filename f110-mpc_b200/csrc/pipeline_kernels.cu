@@ -25,124 +25,6 @@ __device__ __forceinline__ int trunc_x86(float v) {  // cvttss2si
   return __float2int_rz(v);
 }
 
-// ---- OccGrid::FillOccGrid: one CTA per scene, the grid is stamped in shared memory and written out once --------
-__global__ void __launch_bounds__(256) fill_grid_kernel(int scenes, int blocks, float discrete, float dilation, int n_beams,
-                                                        int num_scans, float angle_min, float angle_inc,
-                                                        const double* __restrict__ pose7, const float* __restrict__ ranges,
-                                                        float* __restrict__ grid, float* __restrict__ offset) {
-  extern __shared__ unsigned char cells[];   // blocks * blocks occupancy bytes
-  const int sc = blockIdx.x;
-  if (sc >= scenes) return;
-  const int ncell = blocks * blocks;
-  for (int i = threadIdx.x; i < ncell; i += blockDim.x) cells[i] = 0;           // grid_ = Zero (occupancy_grid.cpp:57)
-  const double* p = pose7 + 7 * (size_t)sc;
-  const double qz = p[5], qw = p[6];
-  const float yaw = (float)atan2(2 * qw * qz, 1 - 2 * qz * qz);                 // :60
-  const float offx = (float)(p[0] + 0.275 * cosf_cr(yaw));                      // :63
-  const float offy = (float)(p[1] + 0.275 * sinf_cr(yaw));                      // :64
-  if (threadIdx.x == 0) { offset[2 * sc] = offx; offset[2 * sc + 1] = offy; }
-  __syncthreads();
-  const float* r = ranges + (size_t)sc * n_beams;
-  const float half = (float)(blocks / 2);
-  const int nb = num_scans < n_beams ? num_scans : n_beams;
-  for (int ii = threadIdx.x; ii < nb; ii += blockDim.x) {
-    const float angle = angle_min + ii * angle_inc + yaw;                       // :71
-    double sn, cs;
-    sincos((double)angle, &sn, &cs);
-    float cx = r[ii] * (float)cs;                                               // :50
-    float cy = r[ii] * (float)sn;                                               // :51
-    cx += offx;                                                                 // :73
-    cy += offy;                                                                 // :74
-    for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {       // :76
-      const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);       // :80 -> :30
-      if (col < 0 || col >= blocks) continue;
-      for (float y_off = -dilation; y_off <= dilation; y_off += discrete) {     // :78
-        const int row = trunc_x86(((cy + y_off) - offy) / discrete + half);     // :31
-        if (row >= 0 && row < blocks) cells[row + col * blocks] = 1;            // :83  grid_(row, col) = 1
-      }
-    }
-  }
-  __syncthreads();
-  float* g = grid + (size_t)sc * ncell;
-  for (int i = threadIdx.x; i < ncell; i += blockDim.x) g[i] = cells[i] ? 1.f : 0.f;
-}
-
-// ---- Constraints::FindHalfSpaces: one warp per scene.  The lanes stage the scan in shared memory (coalesced), lane 0
-// runs the run-length scan sequentially and literally (its quirks — SURVEY a13' — depend on the visiting order).
-constexpr int HS_WARPS = 4;
-__global__ void __launch_bounds__(32 * HS_WARPS) half_spaces_kernel(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc,
-                                                                   float ftg_thresh, float divider, float buffer,
-                                                                   const double* __restrict__ state3, const float* __restrict__ ranges,
-                                                                   double* __restrict__ l1l2, int32_t* __restrict__ gap) {
-  extern __shared__ unsigned mask_sm[];  // HS_WARPS x 2 x words: per 32 beams, "inside the field of view" and "far" bit masks
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sc = blockIdx.x * HS_WARPS + warp;
-  if (sc >= scenes) return;
-  const int nb = num_scans < n_beams ? num_scans : n_beams;
-  const int words = (nb + 31) / 32;
-  unsigned* fov = mask_sm + (size_t)warp * 2 * ((n_beams + 31) / 32);
-  unsigned* far = fov + (n_beams + 31) / 32;
-  const float* rs = ranges + (size_t)sc * n_beams;
-  const float half_fov = 1.571f / divider;
-  // the per-beam predicates do not depend on the visiting order: evaluate them 32 at a time (coalesced reads)
-  for (int w = 0; w < words; ++w) {
-    const int i = 32 * w + lane;
-    bool in_fov = false, is_far = false;
-    if (i < nb) {
-      const float bearing = angle_min + i * angle_inc;                          // constraints.cpp:133
-      in_fov = bearing > -half_fov && bearing < half_fov;                       // :135
-      is_far = rs[i] > ftg_thresh;                                              // :138
-    }
-    const unsigned m_fov = __ballot_sync(0xffffffffu, in_fov), m_far = __ballot_sync(0xffffffffu, in_fov && is_far);
-    if (lane == 0) { fov[w] = m_fov; far[w] = m_far; }
-  }
-  __syncwarp();
-  if (lane != 0) return;
-  // the run-length scan itself is order dependent (SURVEY a13'): sequential and literal, over the bit masks
-  int widest = -1, lo = -1, hi = -1, best_lo = 0, best_hi = 0;
-  bool inside = false;
-  for (int w = 0; w < words; ++w) {
-    unsigned mf = fov[w];
-    const unsigned mr = far[w];
-    while (mf) {
-      const int bit = __ffs(mf) - 1;
-      mf &= mf - 1;
-      const int i = 32 * w + bit;
-      if ((mr >> bit) & 1u) {
-        if (inside) hi = i; else { lo = i; inside = true; }                     // hi is not reset
-      } else {
-        inside = false;
-        if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
-      }
-      if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
-    }
-  }
-  if ((float)(best_hi - best_lo) > 2 * buffer) {                                // :173
-    best_hi = (int)((float)best_hi - buffer);
-    best_lo = (int)((float)best_lo + buffer);
-  }
-  gap[2 * sc] = best_lo; gap[2 * sc + 1] = best_hi;
-  double* out = l1l2 + 6 * (size_t)sc;
-  if (best_lo < 0 || best_hi < 0 || best_lo >= n_beams || best_hi >= n_beams) {  // the reference reads ranges[-1] here
-    for (int j = 0; j < 6; ++j) out[j] = 0.0;
-    gap[2 * sc] = -1; gap[2 * sc + 1] = -1;
-    return;
-  }
-  const double px = state3[3 * sc], py = state3[3 * sc + 1];
-  const float heading = (float)state3[3 * sc + 2];                              // :127
-  const float a_lo = angle_min + best_lo * angle_inc + heading;                 // :179
-  const float a_hi = angle_min + best_hi * angle_inc + heading;                 // :180
-  const float p1x = (float)(rs[best_lo] * cosf_cr(a_lo) + px), p1y = (float)(rs[best_lo] * sinf_cr(a_lo) + py);  // :182-183
-  const float p2x = (float)(rs[best_hi] * cosf_cr(a_hi) + px), p2y = (float)(rs[best_hi] * sinf_cr(a_hi) + py);  // :185-186
-  const float qx = (float)px, qy = (float)py;                                   // :188-189
-  float a1 = qy - p1y, b1 = p1x - qx, c1 = qx * p1y - qy * p1x;                 // :233-235
-  if (a1 * p2x + b1 * p2y + c1 < 0) { a1 = -a1; b1 = -b1; c1 = -c1; }           // :237
-  float a2 = qy - p2y, b2 = p2x - qx, c2 = qx * p2y - qy * p2x;                 // :244-246
-  if (a2 * p1x + b2 * p1y + c2 < 0) { a2 = -a2; b2 = -b2; c2 = -c2; }           // :248
-  out[0] = a1; out[1] = b1; out[2] = c1 + 0.5;                                  // :258-260
-  out[3] = a2; out[4] = b2; out[5] = c2 + 0.5;                                  // :262-264
-}
-
 // ---- tf2 restated (see host/transforms.cpp) ---------------------------------------------------------------------------
 struct Basis { double m[3][3]; };
 __device__ Basis basis_of(double x, double y, double z, double w) {
@@ -173,26 +55,133 @@ __device__ void quaternion_of(const Basis& b, double* q) {
   }
 }
 
-// Car -> world rotation rows (what CarPointToWorldPoint applies after its tf2 round trip), one thread per scene.
-__global__ void __launch_bounds__(64) rotation_kernel(int scenes, const double* __restrict__ pose7, double* __restrict__ rot,
-                                                      double* __restrict__ pose_xy) {
-  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sc >= scenes) return;
-  const double* p = pose7 + 7 * (size_t)sc;
-  double q[4];
-  quaternion_of(basis_of(p[3], p[4], p[5], p[6]), q);
-  const Basis b = basis_of(q[0], q[1], q[2], q[3]);
-  rot[4 * sc] = b.m[0][0]; rot[4 * sc + 1] = b.m[0][1]; rot[4 * sc + 2] = b.m[1][0]; rot[4 * sc + 3] = b.m[1][1];
-  pose_xy[2 * sc] = p[0]; pose_xy[2 * sc + 1] = p[1];
+// ---- Constraints::FindHalfSpaces for one scene, executed by one warp.  The per-beam predicates do not depend on the
+// visiting order: they are evaluated 32 at a time into ballot masks (coalesced reads); the run-length scan itself IS order
+// dependent (SURVEY a13'), so lane 0 runs it sequentially and literally over the masks.
+__device__ void find_half_spaces_warp(int lane, unsigned* fov, unsigned* far, int n_beams, int num_scans, float angle_min, float angle_inc,
+                                      float ftg_thresh, float divider, float buffer, double px, double py, float heading,
+                                      const float* __restrict__ rs, double* __restrict__ out, int32_t* __restrict__ gap) {
+  const int nb = num_scans < n_beams ? num_scans : n_beams;
+  const int words = (nb + 31) / 32;
+  const float half_fov = 1.571f / divider;
+  for (int w = 0; w < words; ++w) {
+    const int i = 32 * w + lane;
+    bool in_fov = false, is_far = false;
+    if (i < nb) {
+      const float bearing = angle_min + i * angle_inc;                          // constraints.cpp:133
+      in_fov = bearing > -half_fov && bearing < half_fov;                       // :135
+      is_far = rs[i] > ftg_thresh;                                              // :138
+    }
+    const unsigned m_fov = __ballot_sync(0xffffffffu, in_fov), m_far = __ballot_sync(0xffffffffu, in_fov && is_far);
+    if (lane == 0) { fov[w] = m_fov; far[w] = m_far; }
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  int widest = -1, lo = -1, hi = -1, best_lo = 0, best_hi = 0;
+  bool inside = false;
+  for (int w = 0; w < words; ++w) {
+    unsigned mf = fov[w];
+    const unsigned mr = far[w];
+    while (mf) {
+      const int bit = __ffs(mf) - 1;
+      mf &= mf - 1;
+      const int i = 32 * w + bit;
+      if ((mr >> bit) & 1u) {
+        if (inside) hi = i; else { lo = i; inside = true; }                     // hi is not reset
+      } else {
+        inside = false;
+        if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+      }
+      if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+    }
+  }
+  if ((float)(best_hi - best_lo) > 2 * buffer) {                                // :173
+    best_hi = (int)((float)best_hi - buffer);
+    best_lo = (int)((float)best_lo + buffer);
+  }
+  gap[0] = best_lo; gap[1] = best_hi;
+  if (best_lo < 0 || best_hi < 0 || best_lo >= n_beams || best_hi >= n_beams) {  // the reference reads ranges[-1] here
+    for (int j = 0; j < 6; ++j) out[j] = 0.0;
+    gap[0] = -1; gap[1] = -1;
+    return;
+  }
+  const float a_lo = angle_min + best_lo * angle_inc + heading;                 // :179
+  const float a_hi = angle_min + best_hi * angle_inc + heading;                 // :180
+  const float p1x = (float)(rs[best_lo] * cosf_cr(a_lo) + px), p1y = (float)(rs[best_lo] * sinf_cr(a_lo) + py);  // :182-183
+  const float p2x = (float)(rs[best_hi] * cosf_cr(a_hi) + px), p2y = (float)(rs[best_hi] * sinf_cr(a_hi) + py);  // :185-186
+  const float qx = (float)px, qy = (float)py;                                   // :188-189
+  float a1 = qy - p1y, b1 = p1x - qx, c1 = qx * p1y - qy * p1x;                 // :233-235
+  if (a1 * p2x + b1 * p2y + c1 < 0) { a1 = -a1; b1 = -b1; c1 = -c1; }           // :237
+  float a2 = qy - p2y, b2 = p2x - qx, c2 = qx * p2y - qy * p2x;                 // :244-246
+  if (a2 * p1x + b2 * p1y + c2 < 0) { a2 = -a2; b2 = -b2; c2 = -c2; }           // :248
+  out[0] = a1; out[1] = b1; out[2] = c1 + 0.5;                                  // :258-260
+  out[3] = a2; out[4] = b2; out[5] = c2 + 0.5;                                  // :262-264
 }
 
-// state3 = (px, py, float yaw) per scene: the State project.cpp:163-164 builds from the pose
-__global__ void __launch_bounds__(128) state_from_pose_kernel(int scenes, const double* __restrict__ pose7, double* __restrict__ state3) {
-  const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- per-scene preparation, one CTA (8 warps) per scene, everything that only needs the pose and the scan:
+//   warps 0..6  OccGrid::FillOccGrid: the grid is stamped as bytes in shared memory and written out once, coalesced
+//   warp  7     Constraints::FindHalfSpaces on the scene's scan (skipped when l1l2 == nullptr; then it stamps too)
+//   thread 0    the car->world rotation CarPointToWorldPoint applies after its tf2 round trip, pose xy
+constexpr int PREP_THREADS = 256;
+__global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, int blocks, float discrete, float dilation, int n_beams,
+                                                                  int num_scans, float angle_min, float angle_inc, float ftg_thresh,
+                                                                  float divider, float buffer, const double* __restrict__ pose7,
+                                                                  const float* __restrict__ ranges, float* __restrict__ grid,
+                                                                  float* __restrict__ offset, double* __restrict__ rot,
+                                                                  double* __restrict__ pose_xy, double* __restrict__ l1l2,
+                                                                  int32_t* __restrict__ gap) {
+  extern __shared__ unsigned char prep_sm[];   // blocks * blocks occupancy bytes, then 2 x words mask words
+  const int sc = blockIdx.x;
   if (sc >= scenes) return;
+  const int ncell = blocks * blocks;
+  unsigned char* cells = prep_sm;
+  unsigned* masks = reinterpret_cast<unsigned*>(prep_sm + (ncell + 15) / 16 * 16);
+  for (int i = threadIdx.x; i < ncell; i += PREP_THREADS) cells[i] = 0;         // grid_ = Zero (occupancy_grid.cpp:57)
   const double* p = pose7 + 7 * (size_t)sc;
-  state3[3 * sc] = p[0]; state3[3 * sc + 1] = p[1];
-  state3[3 * sc + 2] = (double)(float)atan2(2 * p[6] * p[5], 1 - 2 * p[5] * p[5]);
+  const double qz = p[5], qw = p[6];
+  const float yaw = (float)atan2(2 * qw * qz, 1 - 2 * qz * qz);                 // :60, also Transforms::GetCarOrientation
+  const float offx = (float)(p[0] + 0.275 * cosf_cr(yaw));                      // :63
+  const float offy = (float)(p[1] + 0.275 * sinf_cr(yaw));                      // :64
+  const float* r = ranges + (size_t)sc * n_beams;
+  if (threadIdx.x == 0) {
+    offset[2 * sc] = offx; offset[2 * sc + 1] = offy;
+    double q[4];
+    quaternion_of(basis_of(p[3], p[4], p[5], p[6]), q);
+    const Basis b = basis_of(q[0], q[1], q[2], q[3]);
+    rot[4 * sc] = b.m[0][0]; rot[4 * sc + 1] = b.m[0][1]; rot[4 * sc + 2] = b.m[1][0]; rot[4 * sc + 3] = b.m[1][1];
+    pose_xy[2 * sc] = p[0]; pose_xy[2 * sc + 1] = p[1];
+  }
+  __syncthreads();
+  const bool gap_warp = (l1l2 != nullptr) && (threadIdx.x >= PREP_THREADS - 32);
+  if (gap_warp) {
+    // State(pose.x, pose.y, float yaw) of project.cpp:163-164
+    find_half_spaces_warp(threadIdx.x & 31, masks, masks + (n_beams + 31) / 32, n_beams, num_scans, angle_min, angle_inc, ftg_thresh,
+                          divider, buffer, p[0], p[1], yaw, r, l1l2 + 6 * (size_t)sc, gap + 2 * (size_t)sc);
+  } else {
+    const int stampers = (l1l2 != nullptr) ? PREP_THREADS - 32 : PREP_THREADS;
+    const float half = (float)(blocks / 2);
+    const int nb = num_scans < n_beams ? num_scans : n_beams;
+    for (int ii = threadIdx.x; ii < nb; ii += stampers) {
+      const float angle = angle_min + ii * angle_inc + yaw;                     // :71
+      double sn, cs;
+      sincos((double)angle, &sn, &cs);
+      float cx = r[ii] * (float)cs;                                             // :50
+      float cy = r[ii] * (float)sn;                                             // :51
+      cx += offx;                                                               // :73
+      cy += offy;                                                               // :74
+      for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {     // :76
+        const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);     // :80 -> :30
+        if (col < 0 || col >= blocks) continue;
+        for (float y_off = -dilation; y_off <= dilation; y_off += discrete) {   // :78
+          const int row = trunc_x86(((cy + y_off) - offy) / discrete + half);   // :31
+          if (row >= 0 && row < blocks) cells[row + col * blocks] = 1;          // :83  grid_(row, col) = 1
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* g = grid + (size_t)sc * ncell;
+  for (int i = threadIdx.x; i < ncell; i += PREP_THREADS) g[i] = cells[i] ? 1.f : 0.f;
 }
 
 // ---- look-ahead point and best surviving path: one warp per scene.  The lanes evaluate the per-waypoint
@@ -301,26 +290,13 @@ __global__ void __launch_bounds__(32 * SB_WARPS) build_records_kernel(int scenes
 
 }  // namespace
 
-cudaError_t launch_fill_grid(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
-                             float angle_inc, const double* pose7, const float* ranges, float* grid, float* offset, cudaStream_t st) {
+cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
+                              float angle_inc, float thresh, float divider, float buffer, const double* pose7, const float* ranges,
+                              float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st) {
   if (scenes == 0) return cudaSuccess;
-  fill_grid_kernel<<<scenes, 256, (size_t)blocks * blocks, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, pose7, ranges, grid, offset);
-  return cudaGetLastError();
-}
-cudaError_t launch_half_spaces(int scenes, int n_beams, int num_scans, float angle_min, float angle_inc, float thresh, float divider,
-                               float buffer, const double* state3, const float* ranges, double* l1l2, int32_t* gap, cudaStream_t st) {
-  if (scenes == 0) return cudaSuccess;
-  half_spaces_kernel<<<(scenes + HS_WARPS - 1) / HS_WARPS, 32 * HS_WARPS, (size_t)HS_WARPS * 2 * ((n_beams + 31) / 32) * sizeof(unsigned), st>>>(scenes, n_beams, num_scans, angle_min, angle_inc, thresh, divider, buffer, state3, ranges, l1l2, gap);
-  return cudaGetLastError();
-}
-cudaError_t launch_state_from_pose(int scenes, const double* pose7, double* state3, cudaStream_t st) {
-  if (scenes == 0) return cudaSuccess;
-  state_from_pose_kernel<<<(scenes + 127) / 128, 128, 0, st>>>(scenes, pose7, state3);
-  return cudaGetLastError();
-}
-cudaError_t launch_rotation(int scenes, const double* pose7, double* rot, double* pose_xy, cudaStream_t st) {
-  if (scenes == 0) return cudaSuccess;
-  rotation_kernel<<<(scenes + 63) / 64, 64, 0, st>>>(scenes, pose7, rot, pose_xy);
+  const size_t smem = (size_t)(blocks * blocks + 15) / 16 * 16 + 2 * (size_t)((n_beams + 31) / 32) * sizeof(unsigned);
+  scene_prep_kernel<<<scenes, PREP_THREADS, smem, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, thresh,
+                                                        divider, buffer, pose7, ranges, grid, offset, rot, pose_xy, l1l2, gap);
   return cudaGetLastError();
 }
 cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,

@@ -35,7 +35,7 @@ def test_cycle_matches_oracle_pipeline(pkg, oracle, workloads, sd):
     S, N = 96, 30
     amin, amax, inc = workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC
     r = _run_cycle(pkg, workloads, S, sd, seed=31 + sd)
-    assert r["launches"] == 8                           # fill, rotation, check, state, half-planes, select, build, solve
+    assert r["launches"] == 5                           # scene prep (fill + gap finder + rotation), check, select, build, solve
     cell_mismatch = 0
     recs_o = []
     n_none = 0
@@ -81,7 +81,7 @@ def test_cycle_matches_oracle_pipeline(pkg, oracle, workloads, sd):
 
 def test_cycle_without_half_spaces_and_long_horizon(pkg, oracle, workloads):
     r = _run_cycle(pkg, workloads, 40, 19, seed=5, use_half_spaces=0, N=50)
-    assert r["launches"] == 6
+    assert r["launches"] == 5
     ok = r["chosen"] >= 0
     assert ok.any() and (r["recs"][ok][:, 5:11] == 0).all()
     o = oracle.MpcBatch(oracle.default_cfg(50), oracle.default_settings(warm_start=0), int(ok.sum())).solve(r["recs"][ok])
