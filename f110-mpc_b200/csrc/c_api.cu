@@ -264,6 +264,8 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (scenes < 0 || nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: QP count exceeds max_batch");
   if (paths <= 0 || samples <= 0 || n_wp <= 0 || cc->n_beams <= 0) return fail(F110_ERR_ARG, "f110_cycle_device: bad sizes");
+  if (!(cc->occ_discrete > 0.f) || 2.f * cc->occ_dilation / cc->occ_discrete + 1.f > 8.f)
+    return fail(F110_ERR_UNSUPPORTED, "f110_cycle_device: more than 8 dilation stamps per axis");
   if (n_wp > 1500) return fail(F110_ERR_UNSUPPORTED, "f110_cycle_device: more than 1500 raceline waypoints (shared-memory staging)");
   if (reinterpret_cast<uintptr_t>(d_table_xy) % 16) return fail(F110_ERR_ARG, "f110_cycle_device: table_xy must be 16-byte aligned");
   s->last_launches = 0;

@@ -77,22 +77,65 @@ __device__ void find_half_spaces_warp(int lane, unsigned* fov, unsigned* far, in
   }
   __syncwarp();
   if (lane != 0) return;
+  // The reference visits the in-view beams one by one (constraints.cpp:130-168).  Its state only changes where the "far"
+  // predicate changes, and inside a run of far beams hi - lo grows by one per beam while the update test is a strict >,
+  // so visiting the maximal stretches of equal predicate gives the same (widest, best_lo, best_hi): per stretch, the test
+  // at its first beam (with the stale hi for a far stretch — `hi` is never reset, SURVEY a13') and the test at its last.
+  auto next_bit = [words](const unsigned* m, int pos, bool want) -> int {   // first index >= pos whose bit == want
+    int w = pos >> 5;
+    if (w >= words) return words * 32;
+    unsigned x = (want ? m[w] : ~m[w]) & (0xffffffffu << (pos & 31));
+    while (!x) {
+      if (++w >= words) return words * 32;
+      x = want ? m[w] : ~m[w];
+    }
+    return w * 32 + __ffs(x) - 1;
+  };
   int widest = -1, lo = -1, hi = -1, best_lo = 0, best_hi = 0;
-  bool inside = false;
-  for (int w = 0; w < words; ++w) {
-    unsigned mf = fov[w];
-    const unsigned mr = far[w];
-    while (mf) {
-      const int bit = __ffs(mf) - 1;
-      mf &= mf - 1;
-      const int i = 32 * w + bit;
-      if ((mr >> bit) & 1u) {
-        if (inside) hi = i; else { lo = i; inside = true; }                     // hi is not reset
-      } else {
-        inside = false;
-        if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+  const int f0 = next_bit(fov, 0, true);
+  if (f0 < nb) {
+    int f1 = next_bit(fov, f0, false) - 1;
+    if (f1 >= nb) f1 = nb - 1;
+    const bool contiguous = next_bit(fov, f1 + 1, true) >= nb;
+    if (contiguous) {
+      int pos = f0;
+      while (pos <= f1) {
+        if ((far[pos >> 5] >> (pos & 31)) & 1u) {
+          int e = next_bit(far, pos, false) - 1;
+          if (e > f1) e = f1;
+          lo = pos;                                                             // :147 (a stretch starts outside a gap)
+          if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }   // first beam of the run, stale hi
+          if (e > pos) {
+            hi = e;                                                             // :143 at the last beam of the run
+            if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+          }
+          pos = e + 1;
+        } else {
+          int e = next_bit(far, pos, true) - 1;
+          if (e > f1) e = f1;
+          if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }   // :154-160
+          pos = e + 1;
+        }
       }
-      if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+    } else {
+      // non-monotone bearings: literal beam-by-beam visit
+      bool inside = false;
+      for (int w = 0; w < words; ++w) {
+        unsigned mf = fov[w];
+        const unsigned mr = far[w];
+        while (mf) {
+          const int bit = __ffs(mf) - 1;
+          mf &= mf - 1;
+          const int i = 32 * w + bit;
+          if ((mr >> bit) & 1u) {
+            if (inside) hi = i; else { lo = i; inside = true; }
+          } else {
+            inside = false;
+            if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+          }
+          if (hi - lo > widest) { widest = hi - lo; best_hi = hi; best_lo = lo; }
+        }
+      }
     }
   }
   if ((float)(best_hi - best_lo) > 2 * buffer) {                                // :173
@@ -169,13 +212,21 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
       float cy = r[ii] * (float)sn;                                             // :51
       cx += offx;                                                               // :73
       cy += offy;                                                               // :74
+      // the row index does not depend on x_off: evaluate the (identical) y_off sequence once per beam, not once per x_off
+      // (at most 8 stamps per axis: the launcher rejects 2*dilation/discrete + 1 > 8)
+      int rows[8];
+      float y_off = -dilation;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {                                             // :78
+        rows[t] = (y_off <= dilation) ? trunc_x86(((cy + y_off) - offy) / discrete + half) : -1;   // :31
+        y_off += discrete;
+      }
       for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {     // :76
         const int col = trunc_x86(((cx + x_off) - offx) / discrete + half);     // :80 -> :30
         if (col < 0 || col >= blocks) continue;
-        for (float y_off = -dilation; y_off <= dilation; y_off += discrete) {   // :78
-          const int row = trunc_x86(((cy + y_off) - offy) / discrete + half);   // :31
-          if (row >= 0 && row < blocks) cells[row + col * blocks] = 1;          // :83  grid_(row, col) = 1
-        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (rows[t] >= 0 && rows[t] < blocks) cells[rows[t] + col * blocks] = 1;   // :83  grid_(row, col) = 1
       }
     }
   }

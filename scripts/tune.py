@@ -8,7 +8,10 @@ W = importlib.import_module("f110-mpc_b200.workloads")
 N = int(os.environ.get("TUNE_N", "30")); B = int(os.environ.get("TUNE_B", "4096"))
 recs = W.tracking_batch(B, N, seed=4096)
 dev = torch.device("cuda:0")
-sol = M.MpcSolver(M.default_config(N), M.default_settings(warm_start=0), max_batch=B)
+kw = dict(warm_start=0)
+if os.environ.get("TUNE_FIXED"):      # fixed work per QP: exactly 50 iterations, one final check (for what-if experiments)
+    kw.update(max_iter=50, check_termination=0, adaptive_rho=0)
+sol = M.MpcSolver(M.default_config(N), M.default_settings(**kw), max_batch=B)
 r = torch.from_numpy(recs).to(dev)
 u0 = torch.empty(B, 2, dtype=torch.float64, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
 s = torch.cuda.current_stream().cuda_stream

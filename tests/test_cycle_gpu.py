@@ -125,3 +125,43 @@ def test_cycle_qp_per_path_modes(pkg, oracle, workloads, qp_mode):
         assert (g["chosen"][s_] == -1) == (not v2[s_].any())
         if g["chosen"][s_] >= 0:
             assert v2[s_, g["chosen"][s_]]
+
+
+def test_device_gap_finder_random_scans(pkg, oracle, workloads):
+    # the device gap finder visits stretches of equal predicate instead of single beams: hammer it with random scans
+    # (many gaps, one-beam gaps, no gap at all, gaps touching the edge of the field of view) against the literal oracle
+    S, N = 512, 30
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(123)
+    amin, amax, inc = workloads.SCAN_ANGLE_MIN, workloads.SCAN_ANGLE_MAX, workloads.SCAN_ANGLE_INC
+    poses = np.zeros((S, 7)); scans = np.zeros((S, 1080), dtype=np.float32)
+    for s_ in range(S):
+        poses[s_] = workloads.yaw_pose(rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3.1, 3.1))
+        kind = s_ % 8
+        r = rng.uniform(0.5, 2.8, 1080).astype(np.float32)
+        if kind == 0:
+            pass                                              # no gap
+        elif kind == 1:
+            r[rng.integers(200, 880, 30)] = 9.0               # isolated one-beam gaps
+        elif kind == 2:
+            r[:] = 9.0                                        # everything far
+        elif kind == 3:
+            r = np.where(rng.random(1080) < 0.5, 9.0, 1.0).astype(np.float32)   # salt and pepper
+        else:
+            for _ in range(rng.integers(1, 6)):
+                a = rng.integers(0, 1075); w = rng.integers(2, 300)
+                r[a:a + w] = rng.uniform(3.01, 10.0)
+        scans[s_] = r
+    table = np.ascontiguousarray(workloads.traj_table(steer_discrete=19)[:, :, :2])
+    xy, _ = workloads.skirk_waypoints()
+    sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(warm_start=0, max_iter=25), max_batch=S)
+    sol.cycle_host(pkg.default_cycle_config(), poses, scans, None, table, xy)
+    l1l2 = sol.cycle_buffers(S)["l1l2"].cpu().numpy()
+    n_ok = 0
+    for s_ in range(S):
+        state = np.array([poses[s_, 0], poses[s_, 1], oracle.car_orientation(poses[s_])])
+        ok, l1, l2, lohi = oracle.find_half_spaces(state, amin, amax, inc, scans[s_])
+        want = np.concatenate([l1, l2]) if ok else np.zeros(6)
+        np.testing.assert_allclose(l1l2[s_], want, rtol=2e-6, atol=2e-5, err_msg="scene %d kind %d lohi %s" % (s_, s_ % 8, lohi))
+        n_ok += int(ok)
+    assert 100 < n_ok < S
