@@ -502,7 +502,8 @@ def run_configs(args):
         if ok:
             recs3[b_, 5:8] = l1; recs3[b_, 8:11] = l2; n_gap += 1
     c3 = {"B": B3, "scans_with_gap": n_gap}
-    for mode, label in ((0, "as_shipped (gap bounds +-1e30)"), (1, "gap_enabled (lower = -l(2))")):
+    for mode, label in ((0, "as_shipped (gap bounds +-1e30)"), (1, "gap_enabled (lower = -l(2), every stage incl. the all-ones stage-0 pair)"),
+                        (2, "gap_enabled_k>=1 (stage-0 pair loose)")):
         g = gpu_batch_time(N_HORIZON, recs3, gap_mode=mode)
         o, thr = cpu_batch(N_HORIZON, recs3, gap_mode=mode)
         c3[label] = {"gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B3 / o["seconds"], "cpu_threads": thr,

@@ -317,8 +317,11 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       s.gm[0] = l1a; s.gm[1] = l1b; s.gm[2] = 0.0;
       s.gm[3] = l2a; s.gm[4] = l2b; s.gm[5] = 0.0;
     }
-    s.gl[0] = (p.gap_mode && act) ? -l1c : -OSQP_INFTY;  // mpc.cpp:297 (commented alternative when gap_mode = 1)
-    s.gl[1] = (p.gap_mode && act) ? -l2c : -OSQP_INFTY;  // mpc.cpp:298; upper bound +INFTY (mpc.cpp:288-290)
+    // gap_mode 1: the commented alternative of mpc.cpp:297-298 on every stage (incl. the all-ones stage-0 pair);
+    // gap_mode 2: the same on stages k >= 1 only (the stage-0 pair, whose rows are not half-planes, stays loose)
+    const bool gap_on = act && (p.gap_mode == 1 || (p.gap_mode == 2 && k > 0));
+    s.gl[0] = gap_on ? -l1c : -OSQP_INFTY;  // mpc.cpp:297
+    s.gl[1] = gap_on ? -l2c : -OSQP_INFTY;  // mpc.cpp:298; upper bound +INFTY (mpc.cpp:288-290)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       s.bl[j] = actu ? p.u_min[j] : -HUGE_BOUND;

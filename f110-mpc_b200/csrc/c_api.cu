@@ -100,6 +100,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
                     f110_mpc_solver** out) {
   if (!cfg || !st || !out || max_batch <= 0) return fail(F110_ERR_ARG, "f110_mpc_create: null argument or max_batch <= 0");
   if (cfg->horizon < 1 || cfg->horizon > F110_MAX_HORIZON) return fail(F110_ERR_ARG, "f110_mpc_create: horizon out of range");
+  if (cfg->gap_mode < 0 || cfg->gap_mode > 2) return fail(F110_ERR_ARG, "f110_mpc_create: gap_mode must be 0, 1 or 2");
   if (st->scaled_termination) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: scaled_termination = 1 is not supported");
   if (st->max_iter < 1 || st->check_termination < 0 || st->scaling < 0) return fail(F110_ERR_ARG, "f110_mpc_create: bad settings");
   int ndev = 0;

@@ -55,7 +55,9 @@ extern "C" {
 typedef struct f110_mpc_config {
   int32_t horizon;   /* params.yaml:12 */
   int32_t gap_mode;  /* 0 = as shipped: gap rows bounded by (-INFTY, +INFTY) (mpc.cpp:297-298);
-                        1 = lower bound -l(2) restored (the commented code on those lines) */
+                        1 = lower bound -l(2) restored (the commented code on those lines), every stage;
+                        2 = same, but the stage-0 pair — all-ones rows that are never overwritten
+                            (mpc.cpp:237-241, 267) and are not half-planes — stays loose */
   double dt;         /* (double)0.01f — MPC::dt_ is a float (mpc.h:48) */
   double wheelbase;  /* (double)0.3302f (model.cpp:32) */
   double q[3];       /* state weights  q0 q1 q2 (params.yaml:1-3) */

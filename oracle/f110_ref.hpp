@@ -399,7 +399,8 @@ struct MpcConfig {
   double u_des[2] = {4.5, 0.0};     // mpc.cpp:18-19
   double u_min[2] = {(double)3.0f, (double)-0.43f};  // constraints.cpp:18-21 (floats into VectorXd)
   double u_max[2] = {(double)4.5f, (double)0.43f};
-  int gap_mode = 0;  // 0: as shipped, gap bounds (-INFTY, +INFTY) (mpc.cpp:297-298); 1: lower = -l(2) (the commented code)
+  int gap_mode = 0;  // 0: as shipped, gap bounds (-INFTY, +INFTY) (mpc.cpp:297-298); 1: lower = -l(2) (the commented code);
+                     // 2: like 1 but the stage-0 pair (all-ones rows, not half-planes — SURVEY fact 3) stays loose
 };
 
 struct QpData {
@@ -503,8 +504,9 @@ inline void qp_fill_values(const MpcConfig& cfg, const double* rec, QpData* d) {
   for (int r = 0; r < 3; ++r) d->l[r] = d->u[r] = -x0[r];           // :299, :305
   for (int k = 1; k <= N; ++k) for (int r = 0; r < 3; ++r) d->l[3 * k + r] = d->u[3 * k + r] = -C[r];
   for (int k = 0; k <= N; ++k) {
-    d->l[ns + 2 * k + 0] = cfg.gap_mode ? -l1[2] : -osqp_restated::OSQP_INFTY;  // :297
-    d->l[ns + 2 * k + 1] = cfg.gap_mode ? -l2[2] : -osqp_restated::OSQP_INFTY;  // :298
+    const bool on = cfg.gap_mode == 1 || (cfg.gap_mode == 2 && k > 0);
+    d->l[ns + 2 * k + 0] = on ? -l1[2] : -osqp_restated::OSQP_INFTY;  // :297
+    d->l[ns + 2 * k + 1] = on ? -l2[2] : -osqp_restated::OSQP_INFTY;  // :298
   }
 }
 

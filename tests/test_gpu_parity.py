@@ -71,6 +71,25 @@ def test_gap_enabled_mode_including_infeasible(pkg, oracle, workloads):
     np.testing.assert_array_equal(g["iters"], o["iters"])
 
 
+def test_gap_mode_2_half_planes_active(pkg, oracle, workloads):
+    # gap rows on for stages k >= 1 only: feasible laser-gap constrained MPC ("approach 2" of the reference README)
+    N, B, eps = 30, 256, 1e-4
+    recs = workloads.tracking_batch(B, N, seed=8, gaps=True)
+    g = pkg.MpcSolver(pkg.default_config(N, 2), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N, 2), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    assert (o["status"] == oracle.SOLVED).mean() > 0.9
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])
+    # the half-plane rows hold on the solution and some are active (non-zero multipliers)
+    ok = o["status"] == 1
+    xs = g["x"][ok][:, 3:3 * (N + 1)].reshape(-1, N, 3)
+    for r in range(2):
+        a, b, c = recs[ok][:, 5 + 3 * r], recs[ok][:, 6 + 3 * r], recs[ok][:, 7 + 3 * r]
+        assert (a[:, None] * xs[:, :, 0] + b[:, None] * xs[:, :, 1] >= -c[:, None] - 1e-3).all()
+    yg = g["y"][ok][:, 3 * (N + 1) + 2:5 * (N + 1)]
+    assert (np.abs(yg) > 1e-6).any()
+
+
 def test_tight_tolerance_solutions_agree(pkg, oracle, workloads):
     # at eps 1e-6 both sides sit on the (unique) solution; iteration counts may differ by one check period
     N, B, eps = 30, 128, 1e-6
