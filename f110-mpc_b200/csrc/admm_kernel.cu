@@ -233,6 +233,10 @@ struct Stage {
 // per-QP scratch line in global memory (L2): [24][32] doubles, element-major
 constexpr int SCR_DX = 0, SCR_DU = 3, SCR_ED = 5, SCR_EG = 8, SCR_EB = 10;       // scaling vectors D, E
 constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22;  // iterate before the last step
+constexpr int SCR_WD = 24, SCR_WG = 27, SCR_WB = 29;    // e_i^2 / c per row: rho_i = rho_bar_i * w_i (factor step only)
+constexpr int SCR_CG = 31, SCR_CB = 33;                 // row class codes of the gap / box rows (factor step only)
+constexpr int SCR_NQ = 35, SCR_SNQ = 36;                // ||q||_inf unscaled / scaled (termination checks only)
+constexpr int SCR_ROWS = 37;
 
 }  // namespace
 
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   constexpr int SM_PAIRS = NLEV * 9 - 1;
   double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;
   Comm<WPQ> cm(smem_all + 2 * SM_PAIRS * T, k);
-  double* scr = p.scratch + (size_t)qp * (24 * T) + k;
+  double* scr = p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) + k;
 
   const int N = p.N;
   const bool act = k <= N;         // lane owns a stage
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     Cv[1] = -1.0 * vlin * x0[2] * co * dt;
     Cv[2] = -1.0 * slin * vlin * pw * dt / L;
   }
-  const double qu[2] = {-1.0 * p.R[0] * p.u_des[0], -1.0 * p.R[1] * p.u_des[1]};  // mpc.cpp:226
+  const double* qu = p.qu;  // -R u_des (mpc.cpp:226), precomputed on the host: lives in the constant bank
 
   Stage s;
   {
@@ -331,9 +335,8 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 
   // ---------------- Ruiz equilibration (OSQP scale_data) -------------------------------------------------
   double c = 1.0, cinv = 1.0;
-  double wd[3], wg[2], wb[2];  // e_i^2 / c : rho_i = rho_bar_i * w_i
-  int cls_g[2], cls_b[2];      // row class: 1 equality (1e3 rho), 0 inequality (rho), -1 loose (RHO_MIN)
-  double nq, snq;              // ||q||_inf unscaled / scaled
+  // Everything only the factor step or the termination checks need (w_i = e_i^2 / c, row classes, ||q||) is parked in the
+  // scratch line instead of registers: the iteration loop runs at the 255-register ceiling.
   {
     double dx[3] = {1, 1, 1}, du[2] = {1, 1}, ed[3] = {1, 1, 1}, eg[2] = {1, 1}, eb[2] = {1, 1};
     const double aA02 = fabs(md.a02), aA12 = fabs(md.a12);
@@ -437,14 +440,14 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const double lb = eg[r] * s.gl[r], ub = eg[r] * OSQP_INFTY;
-      cls_g[r] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1 : ((ub - lb < RHO_TOL) ? 1 : 0);
+      scr[(SCR_CG + r) * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
       const double lbb = eb[r] * s.bl[r], ubb = eb[r] * s.bu[r];
-      cls_b[r] = (lbb < -INF_THRESH && ubb > INF_THRESH) ? -1 : ((ubb - lbb < RHO_TOL) ? 1 : 0);
+      scr[(SCR_CB + r) * T] = (lbb < -INF_THRESH && ubb > INF_THRESH) ? -1.0 : ((ubb - lbb < RHO_TOL) ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) wd[i] = ed[i] * ed[i] * cinv;
+    for (int i = 0; i < 3; ++i) scr[(SCR_WD + i) * T] = ed[i] * ed[i] * cinv;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) { wg[r] = eg[r] * eg[r] * cinv; wb[r] = eb[r] * eb[r] * cinv; }
+    for (int r = 0; r < 2; ++r) { scr[(SCR_WG + r) * T] = eg[r] * eg[r] * cinv; scr[(SCR_WB + r) * T] = eb[r] * eb[r] * cinv; }
 #pragma unroll
     for (int j = 0; j < 3; ++j) s.sx[j] = p.sigma * cinv / (dx[j] * dx[j]);
 #pragma unroll
@@ -458,8 +461,8 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 #pragma unroll
       for (int j = 0; j < 2; ++j) { a = dmax(a, fabs(qu[j])); b = dmax(b, fabs(du[j] * qu[j])); }
     }
-    nq = cm.rmax(a);
-    snq = c * cm.rmax(b);
+    scr[SCR_NQ * T] = cm.rmax(a);
+    scr[SCR_SNQ * T] = c * cm.rmax(b);
   }
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
@@ -510,20 +513,21 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   int ar_left = ari > 0 ? ari : -1;
   bool need_factor = true;
   double pri_res = 0, dua_res = 0, obj = 0;
-  const double al = p.alpha, oma = 1.0 - p.alpha;
+  const double al = p.alpha, oma = p.one_minus_alpha;
 
   for (;;) {
     if (need_factor) {
       // ---------- factor step: metric from rho_bar, input elimination, PCR multipliers -------------------------
       need_factor = false;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.rd[i] = RHO_EQ_OVER_RHO_INEQ * rho_bar * wd[i];
+      for (int i = 0; i < 3; ++i) s.rd[i] = RHO_EQ_OVER_RHO_INEQ * rho_bar * scr[(SCR_WD + i) * T];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const double rg = cls_g[r] < 0 ? RHO_MIN : (cls_g[r] > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
-        const double rb = cls_b[r] < 0 ? RHO_MIN : (cls_b[r] > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
-        s.rg[r] = rg * wg[r]; s.ig[r] = 1.0 / s.rg[r];
-        s.rb[r] = rb * wb[r]; s.ib[r] = 1.0 / s.rb[r];
+        const double cg = scr[(SCR_CG + r) * T], cb = scr[(SCR_CB + r) * T];
+        const double rg = cg < 0 ? RHO_MIN : (cg > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+        const double rb = cb < 0 ? RHO_MIN : (cb > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+        s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = 1.0 / s.rg[r];
+        s.rb[r] = rb * scr[(SCR_WB + r) * T]; s.ib[r] = 1.0 / s.rb[r];
       }
       cm.template dn<3>(s.rd, s.rdn, 1);
 #pragma unroll
@@ -858,7 +862,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) { status = ST_NON_CVX; finished = true; exact_hit = !approximate; break; }
         if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
         const bool prim_ok = pri_res < eps_abs + eps_rel * dmax(n_z, n_Ax);
-        const bool dual_ok = dua_res < eps_abs + eps_rel * dmax(nq, dmax(n_Aty, n_Px));
+        const bool dual_ok = dua_res < eps_abs + eps_rel * dmax(scr[SCR_NQ * T], dmax(n_Aty, n_Px));
         bool pinf = false, dinf = false;
         if (!prim_ok) {
           // is_primal_infeasible: delta_y projected on the polar of the recession cone of [l, u]
@@ -955,7 +959,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     if (adp) {
       // compute_rho_estimate on the scaled residuals, adapt_rho
       const double pr = s_pri / (dmax(s_z, s_Ax) + 1e-10);
-      const double dr = s_dua / (dmax(snq, dmax(s_Aty, s_Px)) + 1e-10);
+      const double dr = s_dua / (dmax(scr[SCR_SNQ * T], dmax(s_Aty, s_Px)) + 1e-10);
       double rho_new = rho_bar * sqrt(pr / (dr + 1e-10));
       rho_new = dmin(dmax(rho_new, RHO_MIN), RHO_MAX);
       if (rho_new > rho_bar * p.adaptive_rho_tolerance || rho_new < rho_bar / p.adaptive_rho_tolerance) {

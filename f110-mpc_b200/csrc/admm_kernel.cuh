@@ -10,13 +10,16 @@
 namespace f110 {
 
 // per-QP scratch line in global memory: D, E (12) + previous iterate (12), one column per lane
-constexpr int SCRATCH_DOUBLES = 24 * 128;  // sized for 4 warps per QP (horizon <= 127)
+constexpr int SCR_ROWS_ALLOC = 40;                       // rows of the per-QP scratch line (37 used)
+constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // sized for 4 warps per QP (horizon <= 127)
 
 struct KParams {
   // problem family (f110_mpc_config)
   int N, B, stride, gap_mode;
   double dt, wheelbase;
   double Q[3], R[2], u_des[2], u_min[2], u_max[2];
+  double qu[2];            // -R u_des
+  double one_minus_alpha;
   // OSQP settings (f110_solver_settings)
   double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval, warm_start;

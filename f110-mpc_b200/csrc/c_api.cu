@@ -118,7 +118,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   const size_t ssz = (size_t)max_batch * f110::state_doubles(N) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * 24 * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);
@@ -170,6 +170,8 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
   p.dt = s->cfg.dt; p.wheelbase = s->cfg.wheelbase;
   for (int i = 0; i < 3; ++i) p.Q[i] = s->cfg.q[i];
   for (int i = 0; i < 2; ++i) { p.R[i] = s->cfg.r[i]; p.u_des[i] = s->cfg.u_des[i]; p.u_min[i] = s->cfg.u_min[i]; p.u_max[i] = s->cfg.u_max[i]; }
+  for (int i = 0; i < 2; ++i) p.qu[i] = -1.0 * s->cfg.r[i] * s->cfg.u_des[i];
+  p.one_minus_alpha = 1.0 - s->st.alpha;
   p.rho0 = s->st.rho; p.sigma = s->st.sigma; p.alpha = s->st.alpha; p.eps_abs = s->st.eps_abs; p.eps_rel = s->st.eps_rel;
   p.eps_prim_inf = s->st.eps_prim_inf; p.eps_dual_inf = s->st.eps_dual_inf; p.adaptive_rho_tolerance = s->st.adaptive_rho_tolerance;
   p.max_iter = s->st.max_iter; p.check_termination = s->st.check_termination; p.scaling = s->st.scaling;
