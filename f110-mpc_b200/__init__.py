@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
     stale = force or any(not os.path.exists(o) for o in outs) or any(
         os.path.getmtime(s) > min(os.path.getmtime(o) for o in outs) for s in srcs)
     if stale:
-        out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+        out = subprocess.run(["make", "-j8", "-C", _HERE], capture_output=True, text=True)
         if verbose or out.returncode:
             print(out.stdout + out.stderr)
         if out.returncode:

@@ -1,0 +1,1063 @@
+// Batched OSQP-ADMM solve of the f110-mpc tracking QP — one warp per QP, one horizon stage per lane.
+//
+// What it replaces: the OsqpEigen/OSQP call sequence of MPC::Update (reference src/mpc.cpp:81-142) for
+// the QP that MPC::MPC / Create*/Update* build (mpc.cpp:26-35, 208-306) from Model::Linearize
+// (model.cpp:30-59).  The algorithm is OSQP's (Ruiz equilibration, rho vector by row class, relaxed
+// ADMM, residual test every `check_termination` iterations, adaptive rho) — the same iterates as the
+// CPU oracle in exact arithmetic — but the linear algebra is re-derived for the horizon structure:
+//
+//  * The scaled problem (D, E, c from Ruiz) is iterated in UNSCALED coordinates with diagonal metrics
+//        sigma_j = sigma / (c d_j^2),   rho_i = rho_bar_i e_i^2 / c,
+//    which is algebraically the same iteration, and keeps the dynamics LTI (A, B are 6 numbers).
+//  * The quasi-definite KKT solve  [P+Sigma, A'; A, -1/rho] is condensed: z~ = A x~ exactly, so each
+//    iteration solves (P + Sigma + A' R A) w = Sigma w_prev - q + A'(R z_prev - y).  Inputs u_k are
+//    eliminated per stage (2x2), leaving a symmetric block-tridiagonal system in x_0..x_N with 3x3 blocks.
+//  * That system is solved by parallel cyclic reduction across the lanes of the warp: log2(N+1) levels,
+//    every lane busy at every level.  The PCR multipliers are computed once per rho (factor step) and kept
+//    in shared memory; each iteration only applies them to the right-hand side.
+//  * x/z/y update, projection onto [l,u], residual norms and the termination test are fused in the same
+//    kernel; all reductions are warp shuffles.  Nothing but the parameter record is read from HBM and
+//    nothing but the solution is written (a per-QP scratch line in L2 holds the scaling vectors and the
+//    previous iterate, touched once per termination check).
+//
+// Lane k owns stage k: x_k(3), u_k(2) (k<N), dynamics rows k (3), gap rows k (2), input-box rows k (2).
+// Lanes above N hold all-zero state and never feed an active lane (every cross-lane read is masked or
+// multiplied by a zero multiplier), so no branch in the iteration depends on the lane.
+#pragma once
+#include "admm_kernel.cuh"
+
+namespace f110 {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double OSQP_INFTY = 1e30;
+constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_EQ_OVER_RHO_INEQ = 1e3, RHO_TOL = 1e-4;
+constexpr double MIN_SCALING = 1e-4, MAX_SCALING = 1e4;
+constexpr double INF_THRESH = OSQP_INFTY * MIN_SCALING;  // 1e26
+constexpr double HUGE_BOUND = 1e300;
+
+enum : int {
+  ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4,
+  ST_MAX_ITER = -2, ST_PINF = -3, ST_DINF = -4, ST_NON_CVX = -7, ST_UNSOLVED = -10
+};
+
+// plain compare-select min/max: every operand here is finite, so fmax/fmin's NaN handling is dead weight
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = dmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double limit_scaling(double v) {
+  v = v < MIN_SCALING ? 1.0 : v;
+  return v > MAX_SCALING ? MAX_SCALING : v;
+}
+// 1/sqrt(x) for x in [1e-4, 1e4] (the range limit_scaling leaves): float seed + two Newton steps, no special cases.
+// Within ~2 ulp of 1.0 / sqrt(x), which is all the Ruiz scaling vectors need.
+__device__ __forceinline__ double rsqrt_scaling(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return dmin(dmax(v, lo), hi); }
+
+// ---- cross-stage communication ------------------------------------------------------------------------------
+// One stage per thread.  WPQ = warps per QP: 1 -> everything is a warp shuffle; 2 or 4 (horizons 32..127) -> the
+// CTA is the QP, values travel through a double-buffered shared-memory exchange with one barrier per exchange
+// (a thread can only overwrite buffer b after passing the barrier of the exchange on buffer b^1, which every
+// thread reaches only after it has finished reading b).
+template <int WPQ>
+struct Comm;
+
+template <>
+struct Comm<1> {
+  __device__ __forceinline__ Comm(double*, int) {}
+  template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_up_sync(FULL, v[i], h);
+  }
+  template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_down_sync(FULL, v[i], h);
+  }
+  template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lo[i] = __shfl_up_sync(FULL, v[i], h); hi[i] = __shfl_down_sync(FULL, v[i], h); }
+  }
+  template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {  // partner k ^ h
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = __shfl_xor_sync(FULL, v[i], h);
+  }
+  __device__ __forceinline__ double rmax(double v) { return wmax(v); }
+  __device__ __forceinline__ double rsum(double v) { return wsum(v); }
+  __device__ __forceinline__ bool any(bool b) { return __any_sync(FULL, b); }
+  __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+template <int WPQ>
+struct Comm {
+  static constexpr int T = 32 * WPQ;
+  static constexpr int KMAX = 9;
+  double* xb;   // [2][KMAX][T] exchange buffers
+  double* rb;   // [2][WPQ] reduction slots
+  int tid, xph = 0, rph = 0;
+  __device__ __forceinline__ Comm(double* smem, int t) : xb(smem), rb(smem + 2 * KMAX * T), tid(t) {}
+  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ; }
+  template <int K> __device__ __forceinline__ double* put(const double* v) {
+    double* b = xb + xph * KMAX * T;
+    xph ^= 1;
+#pragma unroll
+    for (int i = 0; i < K; ++i) b[i * T + tid] = v[i];
+    __syncthreads();
+    return b;
+  }
+  // out-of-range sources return the caller's own value, like a shuffle; callers mask them
+  template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid - h >= 0 ? tid - h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+  }
+  template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid + h < T ? tid + h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+  }
+  template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
+    const double* b = put<K>(v);
+    const int sl = tid - h >= 0 ? tid - h : tid, sh = tid + h < T ? tid + h : tid;
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lo[i] = b[i * T + sl]; hi[i] = b[i * T + sh]; }
+  }
+  template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {
+    const double* b = put<K>(v);
+    const int src = tid ^ h;
+#pragma unroll
+    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+  }
+  __device__ __forceinline__ double* rslot(double v) {
+    double* r = rb + rph * WPQ;
+    rph ^= 1;
+    if ((tid & 31) == 0) r[tid >> 5] = v;
+    __syncthreads();
+    return r;
+  }
+  __device__ __forceinline__ double rmax(double v) {
+    const double* r = rslot(wmax(v));
+    double m = r[0];
+#pragma unroll
+    for (int w = 1; w < WPQ; ++w) m = dmax(m, r[w]);
+    return m;
+  }
+  __device__ __forceinline__ double rsum(double v) {
+    const double* r = rslot(wsum(v));
+    double m = r[0];
+#pragma unroll
+    for (int w = 1; w < WPQ; ++w) m += r[w];
+    return m;
+  }
+  __device__ __forceinline__ bool any(bool b) { return __syncthreads_or(b) != 0; }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+// ---- 3x3 helpers (row-major double[9]) ------------------------------------------------------------
+__device__ __forceinline__ void mm3(const double* a, const double* b, double* c) {  // c = a b
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+// inverse of a symmetric positive definite 3x3 via LDL^T (reads the lower triangle)
+__device__ __forceinline__ void inv_spd3(const double* a, double* inv) {
+  const double d0 = a[0], i0 = 1.0 / d0;
+  const double l10 = a[3] * i0, l20 = a[6] * i0;
+  const double d1 = a[4] - l10 * a[3], i1 = 1.0 / d1;
+  const double l21 = (a[7] - l20 * a[3]) * i1;
+  const double d2 = a[8] - l20 * a[6] - l21 * (a[7] - l20 * a[3]), i2 = 1.0 / d2;
+  const double m10 = -l10, m20 = l10 * l21 - l20, m21 = -l21;  // L^-1 = [[1,0,0],[m10,1,0],[m20,m21,1]]
+  inv[0] = i0 + m10 * m10 * i1 + m20 * m20 * i2;
+  inv[1] = inv[3] = m10 * i1 + m20 * m21 * i2;
+  inv[2] = inv[6] = m20 * i2;
+  inv[4] = i1 + m21 * m21 * i2;
+  inv[5] = inv[7] = m21 * i2;
+  inv[8] = i2;
+}
+
+struct Model {  // Model::Linearize output (model.cpp:30-59): A = I + [0 0 a02; 0 0 a12; 0 0 0], B = [b00 0; b10 0; b20 b21]
+  double a02, a12, b00, b10, b20, b21;
+};
+__device__ __forceinline__ void A_mul(const Model& m, const double* v, double* o) {   // o = A v
+  o[0] = v[0] + m.a02 * v[2]; o[1] = v[1] + m.a12 * v[2]; o[2] = v[2];
+}
+__device__ __forceinline__ void At_mul(const Model& m, const double* v, double* o) {  // o = A' v
+  o[0] = v[0]; o[1] = v[1]; o[2] = m.a02 * v[0] + m.a12 * v[1] + v[2];
+}
+__device__ __forceinline__ void B_mul(const Model& m, const double* h, double* o) {   // o = B h
+  o[0] = m.b00 * h[0]; o[1] = m.b10 * h[0]; o[2] = m.b20 * h[0] + m.b21 * h[1];
+}
+__device__ __forceinline__ void Bt_mul(const Model& m, const double* v, double* o) {  // o = B' v
+  o[0] = m.b00 * v[0] + m.b10 * v[1] + m.b20 * v[2]; o[1] = m.b21 * v[2];
+}
+
+// Everything one lane keeps in registers for its stage.
+struct Stage {
+  // problem data
+  double bd[3];            // dynamics rhs (l = u): -x_cur at k = 0, -C at k >= 1      (mpc.cpp:299,305)
+  double gm[6];            // gap rows 2x3: ones at k = 0, [l1a l1b 0; l2a l2b 0] after (mpc.cpp:237-241, 260-272)
+  double gl[2];            // gap lower bounds (upper is +INFTY)                       (mpc.cpp:279-300)
+  double bl[2], bu[2];     // input box                                               (mpc.cpp:281,290)
+  double qx[3];            // -Q ref_k                                                 (mpc.cpp:225,228)
+  // iterates (unscaled)
+  double x[3], u[2];
+  double zd[3], zg[2], zb[2];
+  double yd[3], yg[2], yb[2];
+  // metric
+  double sx[3], su[2];                 // sigma_j
+  double rd[3], rg[2], rb[2];          // rho_i
+  double ig[2], ib[2];                 // 1 / rho_i (inequality rows only; equality rows project to l = u)
+  // input elimination
+  double wi[3];            // inverse of W_k = R + Sigma_u + rho_box + B' R_{k+1} B   (00, 01, 11)
+  double rdn[3];           // rho of the NEXT stage's dynamics rows
+};
+
+// per-QP scratch line in global memory (L2): [24][32] doubles, element-major
+constexpr int SCR_DX = 0, SCR_DU = 3, SCR_ED = 5, SCR_EG = 8, SCR_EB = 10;       // scaling vectors D, E
+constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22;  // iterate before the last step
+constexpr int SCR_WD = 24, SCR_WG = 27, SCR_WB = 29;    // e_i^2 / c per row: rho_i = rho_bar_i * w_i (factor step only)
+constexpr int SCR_CG = 31, SCR_CB = 33;                 // row class codes of the gap / box rows (factor step only)
+constexpr int SCR_NQ = 35, SCR_SNQ = 36;                // ||q||_inf unscaled / scaled (termination checks only)
+constexpr int SCR_ROWS = 37;
+
+}  // namespace
+
+// One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
+// NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == 32 WPQ): the last thread is an active
+// stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
+template <int NLEV, int WPQ, bool LASTFULL>
+__global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+  extern __shared__ __align__(16) double smem_all[];
+  constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
+  const int qp = blockIdx.x;
+  const int k = threadIdx.x;
+  // PCR multipliers as double2 pairs, pair-major, stage fastest: 9 pairs (-alpha, -gamma) for each of the first
+  // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
+  constexpr int SM_PAIRS = NLEV * 9 - 1;
+  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;
+  Comm<WPQ> cm(smem_all + 2 * SM_PAIRS * T, k);
+  double* scr = p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) + k;
+
+  const int N = p.N;
+  const bool act = k <= N;         // lane owns a stage
+  const bool actu = k < N;         // stage has an input (and box rows, and a successor)
+  const bool hasp = act && k > 0;  // stage has a predecessor
+  const int nvar = 5 * N + 3;
+  const int mcon = 7 * N + 5;
+
+  // ---------------- load the parameter record, linearise, stack -----------------------------------------
+  const double* rec = p.recs + (size_t)qp * p.stride;
+  const double x0[3] = {rec[0], rec[1], rec[2]};
+  const double vlin = rec[3], slin = rec[4];
+  if (!(vlin == vlin)) {
+    // NaN linearisation speed marks an empty slot (the planning stage found no valid mini-path for this scene,
+    // project.cpp:115-119): nothing to solve, status stays UNSOLVED
+    if (k == 0) {
+      const double qn = __longlong_as_double(0x7ff8000000000000LL);
+      if (p.u0_out) { p.u0_out[2 * (size_t)qp] = qn; p.u0_out[2 * (size_t)qp + 1] = qn; }
+      if (p.status) p.status[qp] = ST_UNSOLVED;
+      if (p.iters) p.iters[qp] = 0;
+      if (p.rho_updates) p.rho_updates[qp] = 0;
+      if (p.packed) { double* po = p.packed + 4 * (size_t)qp; po[0] = qn; po[1] = qn; po[2] = (double)ST_UNSOLVED; po[3] = 0.0; }
+    }
+    return;
+  }
+  Model md;
+  double Cv[3];
+  {
+    // Model::Linearize, model.cpp:42-55 (operation order kept)
+    const double L = p.wheelbase, dt = p.dt;
+    double so, co, ss, cs;
+    sincos(x0[2], &so, &co);
+    sincos(slin, &ss, &cs);
+    const double pw = 1.0 / (cs * cs);   // pow(cos, -2) of model.cpp:51,55 to within 1 ulp
+    md.a02 = -1.0 * vlin * so * dt;
+    md.a12 = vlin * co * dt;
+    md.b00 = co * dt;
+    md.b10 = so * dt;
+    md.b20 = (ss / cs) * dt / L;         // tan(steer), model.cpp:50, to within 1 ulp
+    md.b21 = vlin * pw * dt / L;
+    Cv[0] = vlin * x0[2] * so * dt;
+    Cv[1] = -1.0 * vlin * x0[2] * co * dt;
+    Cv[2] = -1.0 * slin * vlin * pw * dt / L;
+  }
+  const double* qu = p.qu;  // -R u_des (mpc.cpp:226), precomputed on the host: lives in the constant bank
+
+  Stage s;
+  {
+    const int kr = (k < N) ? k : (N - 1);  // terminal stage re-uses ref[N-1] (mpc.cpp:228)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double r = act ? rec[11 + 3 * kr + j] : 0.0;
+      s.qx[j] = act ? (-1.0 * p.Q[j] * r) : 0.0;
+      s.bd[j] = act ? (k == 0 ? -x0[j] : -Cv[j]) : 0.0;
+    }
+    const double l1a = rec[5], l1b = rec[6], l1c = rec[7], l2a = rec[8], l2b = rec[9], l2c = rec[10];
+    if (!act) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) s.gm[e] = 0.0;
+    } else if (k == 0) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) s.gm[e] = 1.0;
+    } else {
+      s.gm[0] = l1a; s.gm[1] = l1b; s.gm[2] = 0.0;
+      s.gm[3] = l2a; s.gm[4] = l2b; s.gm[5] = 0.0;
+    }
+    // gap_mode 1: the commented alternative of mpc.cpp:297-298 on every stage (incl. the all-ones stage-0 pair);
+    // gap_mode 2: the same on stages k >= 1 only (the stage-0 pair, whose rows are not half-planes, stays loose)
+    const bool gap_on = act && (p.gap_mode == 1 || (p.gap_mode == 2 && k > 0));
+    s.gl[0] = gap_on ? -l1c : -OSQP_INFTY;  // mpc.cpp:297
+    s.gl[1] = gap_on ? -l2c : -OSQP_INFTY;  // mpc.cpp:298; upper bound +INFTY (mpc.cpp:288-290)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      s.bl[j] = actu ? p.u_min[j] : -HUGE_BOUND;
+      s.bu[j] = actu ? p.u_max[j] : HUGE_BOUND;
+    }
+  }
+
+  // ---------------- Ruiz equilibration (OSQP scale_data) -------------------------------------------------
+  double c = 1.0, cinv = 1.0;
+  // Everything only the factor step or the termination checks need (w_i = e_i^2 / c, row classes, ||q||) is parked in the
+  // scratch line instead of registers: the iteration loop runs at the 255-register ceiling.
+  {
+    double dx[3] = {1, 1, 1}, du[2] = {1, 1}, ed[3] = {1, 1, 1}, eg[2] = {1, 1}, eb[2] = {1, 1};
+    const double aA02 = fabs(md.a02), aA12 = fabs(md.a12);
+    const double aB[6] = {fabs(md.b00), 0.0, fabs(md.b10), 0.0, fabs(md.b20), fabs(md.b21)};
+    double ag[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) ag[e] = fabs(s.gm[e]);
+    for (int it = 0; it < p.scaling; ++it) {
+      double edn[3], dxp[3], dup[2];
+      {
+        const double snd[5] = {dx[0], dx[1], dx[2], du[0], du[1]};
+        double rcv[5];
+        cm.template dn<3>(ed, edn, 1);
+        cm.template up<5>(snd, rcv, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { edn[i] = actu ? edn[i] : 0.0; dxp[i] = hasp ? rcv[i] : 0.0; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dup[j] = hasp ? rcv[3 + j] : 0.0;
+      }
+      double tx[3], tu[2], td[3], tg[2], tb[2];
+      // KKT column of x_k[j]: P, the -1 of dyn row k, column j of A in dyn rows k+1 (A = I + a02/a12 in col 2), gap rows k
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double v = c * dx[j] * dx[j] * p.Q[j];
+        v = dmax(v, ed[j] * dx[j]);
+        v = dmax(v, edn[j] * dx[j]);
+        v = dmax(v, dmax(eg[0] * ag[j], eg[1] * ag[3 + j]) * dx[j]);
+        tx[j] = v;
+      }
+      tx[2] = dmax(tx[2], dmax(edn[0] * aA02, edn[1] * aA12) * dx[2]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {  // KKT column of u_k[j]
+        double v = c * du[j] * du[j] * p.R[j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v = dmax(v, edn[i] * aB[2 * i + j] * du[j]);
+        v = dmax(v, eb[j] * du[j]);
+        tu[j] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {  // KKT column (= A row) of dyn row (k, i)
+        double v = dmax(dx[i], dxp[i]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) v = dmax(v, aB[2 * i + j] * dup[j]);
+        td[i] = v;
+      }
+      td[0] = dmax(td[0], aA02 * dxp[2]);
+      td[1] = dmax(td[1], aA12 * dxp[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) td[i] *= ed[i];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v = dmax(v, ag[3 * r + j] * dx[j]);
+        tg[r] = eg[r] * v;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tb[j] = eb[j] * du[j];
+      if (!act) {  // lanes above N: keep D = E = 1
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { tx[j] = 1.0; td[j] = 1.0; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tg[j] = 1.0;
+      }
+      if (!actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { tu[j] = 1.0; tb[j] = 1.0; }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dx[j] *= rsqrt_scaling(limit_scaling(tx[j]));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) du[j] *= rsqrt_scaling(limit_scaling(tu[j]));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ed[i] *= rsqrt_scaling(limit_scaling(td[i]));
+#pragma unroll
+      for (int r = 0; r < 2; ++r) eg[r] *= rsqrt_scaling(limit_scaling(tg[r]));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) eb[j] *= rsqrt_scaling(limit_scaling(tb[j]));
+      // cost normalisation: c_temp = 1 / max(mean column norm of P, ||q||_inf)
+      double psum = 0.0, qn = 0.0;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { psum += c * dx[j] * dx[j] * p.Q[j]; qn = dmax(qn, fabs(dx[j] * s.qx[j])); }
+      }
+      if (actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { psum += c * du[j] * du[j] * p.R[j]; qn = dmax(qn, fabs(du[j] * qu[j])); }
+      }
+      const double mean = cm.rsum(psum) / (double)nvar;
+      const double qinf = limit_scaling(c * cm.rmax(qn));
+      const double ct = limit_scaling(dmax(mean, qinf));
+      c *= 1.0 / ct;
+    }
+    cinv = 1.0 / c;
+    // park D, E in the scratch line: only the rho estimate, infeasibility tests and the state store read them again
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { scr[(SCR_DX + j) * T] = dx[j]; scr[(SCR_ED + j) * T] = ed[j]; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { scr[(SCR_DU + j) * T] = du[j]; scr[(SCR_EG + j) * T] = eg[j]; scr[(SCR_EB + j) * T] = eb[j]; }
+    // row classes (OSQP set_rho_vec, on the SCALED bounds); dynamics rows have l = u -> equality
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double lb = eg[r] * s.gl[r], ub = eg[r] * OSQP_INFTY;
+      scr[(SCR_CG + r) * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
+      const double lbb = eb[r] * s.bl[r], ubb = eb[r] * s.bu[r];
+      scr[(SCR_CB + r) * T] = (lbb < -INF_THRESH && ubb > INF_THRESH) ? -1.0 : ((ubb - lbb < RHO_TOL) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) scr[(SCR_WD + i) * T] = ed[i] * ed[i] * cinv;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { scr[(SCR_WG + r) * T] = eg[r] * eg[r] * cinv; scr[(SCR_WB + r) * T] = eb[r] * eb[r] * cinv; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s.sx[j] = p.sigma * cinv / (dx[j] * dx[j]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s.su[j] = p.sigma * cinv / (du[j] * du[j]);
+    double a = 0.0, b = 0.0;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { a = dmax(a, fabs(s.qx[j])); b = dmax(b, fabs(dx[j] * s.qx[j])); }
+    }
+    if (actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { a = dmax(a, fabs(qu[j])); b = dmax(b, fabs(du[j] * qu[j])); }
+    }
+    scr[SCR_NQ * T] = cm.rmax(a);
+    scr[SCR_SNQ * T] = c * cm.rmax(b);
+  }
+
+  // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { s.x[j] = 0; s.zd[j] = 0; s.yd[j] = 0; }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { s.u[j] = 0; s.zg[j] = 0; s.zb[j] = 0; s.yg[j] = 0; s.yb[j] = 0; }
+  double rho_bar = dmin(dmax(p.rho0, RHO_MIN), RHO_MAX);
+  double* slot = p.state ? p.state + (size_t)qp * state_doubles(N) : nullptr;
+  if (slot && p.warm_start && slot[nvar + 2 * mcon + 1] != 0.0) {
+    // OSQP keeps x, z, y in SCALED coordinates across re-scalings (osqp_update_A rescales the data only):
+    // x = D xbar, z = zbar / E, y = E ybar / c with the NEW D, E, c.
+    rho_bar = slot[nvar + 2 * mcon];
+    const double* sx_ = slot;
+    const double* sz_ = slot + nvar;
+    const double* sy_ = slot + nvar + mcon;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double e = scr[(SCR_ED + j) * T];
+        s.x[j] = scr[(SCR_DX + j) * T] * sx_[3 * k + j];
+        s.zd[j] = sz_[3 * k + j] / e;
+        s.yd[j] = e * sy_[3 * k + j] * cinv;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double e = scr[(SCR_EG + r) * T];
+        s.zg[r] = sz_[3 * (N + 1) + 2 * k + r] / e;
+        s.yg[r] = e * sy_[3 * (N + 1) + 2 * k + r] * cinv;
+      }
+    }
+    if (actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double e = scr[(SCR_EB + j) * T];
+        s.u[j] = scr[(SCR_DU + j) * T] * sx_[3 * (N + 1) + 2 * k + j];
+        s.zb[j] = sz_[5 * (N + 1) + 2 * k + j] / e;
+        s.yb[j] = e * sy_[5 * (N + 1) + 2 * k + j] * cinv;
+      }
+    }
+  }
+
+  // ---------------- main loop (OSQP osqp_solve); factor / update_info / check each have ONE call site ----------
+  int status = ST_UNSOLVED;
+  int iter = 1, n_rho_updates = 0;
+  int ct_left = p.check_termination > 0 ? p.check_termination : -1;  // countdown to the next termination check
+  const int ari = p.adaptive_rho ? p.adaptive_rho_interval : 0;
+  int ar_left = ari > 0 ? ari : -1;
+  bool need_factor = true;
+  double pri_res = 0, dua_res = 0, obj = 0;
+  const double al = p.alpha, oma = p.one_minus_alpha;
+
+  for (;;) {
+    if (need_factor) {
+      // ---------- factor step: metric from rho_bar, input elimination, PCR multipliers -------------------------
+      need_factor = false;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.rd[i] = RHO_EQ_OVER_RHO_INEQ * rho_bar * scr[(SCR_WD + i) * T];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double cg = scr[(SCR_CG + r) * T], cb = scr[(SCR_CB + r) * T];
+        const double rg = cg < 0 ? RHO_MIN : (cg > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+        const double rb = cb < 0 ? RHO_MIN : (cb > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+        s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = 1.0 / s.rg[r];
+        s.rb[r] = rb * scr[(SCR_WB + r) * T]; s.ib[r] = 1.0 / s.rb[r];
+      }
+      cm.template dn<3>(s.rd, s.rdn, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.rdn[i] = actu ? s.rdn[i] : 0.0;
+      double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.B) W^-1 (rdn.B)'
+      {
+        const double w00 = p.R[0] + s.su[0] + s.rb[0] + md.b00 * md.b00 * s.rdn[0] + md.b10 * md.b10 * s.rdn[1] + md.b20 * md.b20 * s.rdn[2];
+        const double w01 = md.b20 * md.b21 * s.rdn[2];
+        const double w11 = p.R[1] + s.su[1] + s.rb[1] + md.b21 * md.b21 * s.rdn[2];
+        const double idet = 1.0 / (w00 * w11 - w01 * w01);
+        s.wi[0] = actu ? w11 * idet : 0.0;
+        s.wi[1] = actu ? -w01 * idet : 0.0;
+        s.wi[2] = actu ? w00 * idet : 0.0;
+        const double M[6] = {s.rdn[0] * md.b00, 0.0, s.rdn[1] * md.b10, 0.0, s.rdn[2] * md.b20, s.rdn[2] * md.b21};
+        double MW[6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          MW[2 * i] = M[2 * i] * s.wi[0] + M[2 * i + 1] * s.wi[1];
+          MW[2 * i + 1] = M[2 * i] * s.wi[1] + M[2 * i + 1] * s.wi[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - (MW[2 * i] * M[2 * l] + MW[2 * i + 1] * M[2 * l + 1]);
+      }
+      double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
+      cm.template up<9>(Rn, Rt, 1);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? Rt[e] : 0.0);
+      double Bm[9], Lm[9], Um[9];
+      {
+        // Hx = diag(Q + sigma_x) + G' diag(rho_g) G  (+ R~_k)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int l = 0; l < 3; ++l)
+            Bm[3 * i + l] = (i == l ? p.Q[i] + s.sx[i] : 0.0) + s.rg[0] * s.gm[i] * s.gm[l] + s.rg[1] * s.gm[3 + i] * s.gm[3 + l] + Rt[3 * i + l];
+        double ARn[9];  // A' Rn
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          ARn[0 + l] = Rn[0 + l];
+          ARn[3 + l] = Rn[3 + l];
+          ARn[6 + l] = md.a02 * Rn[0 + l] + md.a12 * Rn[3 + l] + Rn[6 + l];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {  // + A' Rn A ; U_k = -A' Rn
+          const double r0 = ARn[3 * i], r1 = ARn[3 * i + 1], r2 = ARn[3 * i + 2];
+          Bm[3 * i + 0] += r0;
+          Bm[3 * i + 1] += r1;
+          Bm[3 * i + 2] += r0 * md.a02 + r1 * md.a12 + r2;
+          Um[3 * i + 0] = -r0; Um[3 * i + 1] = -r1; Um[3 * i + 2] = -r2;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {  // L_k = -R~_k A
+          const double r0 = Rt[3 * i], r1 = Rt[3 * i + 1], r2 = Rt[3 * i + 2];
+          Lm[3 * i + 0] = hasp ? -r0 : 0.0;
+          Lm[3 * i + 1] = hasp ? -r1 : 0.0;
+          Lm[3 * i + 2] = hasp ? -(r0 * md.a02 + r1 * md.a12 + r2) : 0.0;
+        }
+        if (!act) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) { Bm[e] = (e % 4 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
+        }
+      }
+      // parallel cyclic reduction; multipliers alpha, gamma go to shared memory
+#pragma unroll 1
+      for (int lev = 0; lev < NLEV; ++lev) {
+        const int h = 1 << lev;
+        const bool vlo = act && (k - h >= 0);
+        const bool vhi = act && (k + h <= N);
+        double Bi[9], XU[9], XL[9];
+        inv_spd3(Bm, Bi);
+        mm3(Bi, Um, XU);
+        mm3(Bi, Lm, XL);
+        double nlo[9], nhi[9], t1[9], t2[9];
+        double alp[9], gam[9], Ln[9], Un[9];
+        cm.template both<9>(Bi, nlo, nhi, h);
+        mm3(Lm, nlo, alp);
+        mm3(Um, nhi, gam);
+        cm.template both<9>(XU, nlo, nhi, h);
+        mm3(Lm, nlo, t1);
+        mm3(Um, nhi, Un);
+        cm.template both<9>(XL, nlo, nhi, h);
+        mm3(Lm, nlo, Ln);
+        mm3(Um, nhi, t2);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+          Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
+          Lm[e] = vlo ? -Ln[e] : 0.0;
+          Um[e] = vhi ? -Un[e] : 0.0;
+          alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
+          gam[e] = vhi ? -gam[e] : 0.0;
+        }
+        if (lev < NLEV - 1) {
+          // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+            sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+            sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+          }
+        } else {
+          // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
+          // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
+          double one[10];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
+          one[9] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) sm_pair[(lev * 9 + q) * T] = make_double2(one[2 * q], one[2 * q + 1]);
+        }
+      }
+      {
+        double Bi[9];
+        inv_spd3(Bm, Bi);
+        sm_pair[(NLEV * 9 - 4 + 0) * T] = make_double2(Bi[0], Bi[1]);
+        sm_pair[(NLEV * 9 - 4 + 1) * T] = make_double2(Bi[2], Bi[4]);
+        sm_pair[(NLEV * 9 - 4 + 2) * T] = make_double2(Bi[5], Bi[8]);
+      }
+      cm.sync();
+    }
+
+    const bool last = (iter == p.max_iter);
+    const bool chk = (--ct_left == 0);
+    const bool adp = (--ar_left == 0);
+    if (chk) ct_left = p.check_termination;
+    if (adp) ar_left = ari;
+    const bool info_iter = chk || adp || last;
+    if (info_iter) {  // the infeasibility tests need delta x, delta y of this iteration
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
+    }
+
+    // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
+    {
+      // s = rho (z - y/rho) = rho z - y per row; right-hand side of the condensed system
+      double sd[3], sg[2], sb[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sd[i] = s.rd[i] * s.zd[i] - s.yd[i];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
+      double sdn[3];
+      cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
+      if (LASTFULL) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
+      }
+      double gx[3], gu[2], t3[3], t2[2];
+      At_mul(md, sdn, t3);
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        gx[j] = s.sx[j] * s.x[j] - s.qx[j] - sd[j] + t3[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1];
+      Bt_mul(md, sdn, t2);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) gu[j] = s.su[j] * s.u[j] - qu[j] + t2[j] + sb[j];
+      // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
+      const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
+      double f[3];
+      B_mul(md, hh, f);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) f[i] *= s.rdn[i];
+      double r[3], fp[3];
+      At_mul(md, f, t3);
+      cm.template up<3>(f, fp, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
+      // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
+#pragma unroll
+      for (int lev = 0; lev < NLEV - 1; ++lev) {
+        const int h = 1 << lev;
+        double lo[3], hi[3];
+        cm.template both<3>(r, lo, hi, h);
+        const double2* cf = sm_pair + (lev * 9) * T;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
+          double a = fma(c0.x, lo[0], r[i]);
+          double b = c1.y * hi[0];
+          a = fma(c0.y, lo[1], a);
+          b = fma(c2.x, hi[1], b);
+          a = fma(c1.x, lo[2], a);
+          b = fma(c2.y, hi[2], b);
+          r[i] = a + b;
+        }
+      }
+      {  // top level: single neighbour k ^ h
+        constexpr int h = 1 << (NLEV - 1);
+        double nb[3];
+        cm.template xr<3>(r, nb, h);
+        const double2* cf = sm_pair + ((NLEV - 1) * 9) * T;
+        const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
+        r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
+        r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
+        r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
+      }
+      double xt[3];
+      {
+        const double2 q0 = sm_pair[(NLEV * 9 - 4 + 0) * T], q1 = sm_pair[(NLEV * 9 - 4 + 1) * T], q2 = sm_pair[(NLEV * 9 - 4 + 2) * T];
+        const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
+        xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
+        xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
+        xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+      }
+      // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
+      double axt[3], v[3], xn[3];
+      A_mul(md, xt, axt);
+      cm.template dn<3>(xt, xn, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = s.rdn[i] * (axt[i] - xn[i]);
+      Bt_mul(md, v, t2);
+      const double ut[2] = {hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]), hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1])};
+      // z~ = A w~ : dynamics rows need the predecessor's prediction
+      double pred[3], ztd[3], pp[3];
+      B_mul(md, ut, pred);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pred[i] += axt[i];
+      cm.template up<3>(pred, pp, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? pp[i] : 0.0) - xt[i];
+      const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s.u[j] = al * ut[j] + oma * s.u[j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {  // equality rows: the projection onto [l, u] = {b} is b itself
+        const double zr = al * ztd[i] + oma * s.zd[i];
+        s.yd[i] += s.rd[i] * (zr - s.bd[i]);
+        s.zd[i] = s.bd[i];
+      }
+#pragma unroll
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const double zr = al * ztg[r2] + oma * s.zg[r2];
+        const double zn = clampd(zr + s.ig[r2] * s.yg[r2], s.gl[r2], OSQP_INFTY);
+        s.yg[r2] += s.rg[r2] * (zr - zn);
+        s.zg[r2] = zn;
+        const double zrb = al * ut[r2] + oma * s.zb[r2];
+        const double znb = clampd(zrb + s.ib[r2] * s.yb[r2], s.bl[r2], s.bu[r2]);
+        s.yb[r2] += s.rb[r2] * (zrb - znb);
+        s.zb[r2] = znb;
+      }
+    }
+    if (!info_iter) { ++iter; continue; }
+
+    // ---------- residuals & norms (OSQP update_info + the norms of compute_rho_estimate) -----------------------
+    double n_z, n_Ax, n_Aty, n_Px;                      // unscaled (termination)
+    double s_pri, s_dua, s_z, s_Ax, s_Aty, s_Px;        // scaled (rho estimate)
+    const double edv[3] = {scr[(SCR_ED + 0) * T], scr[(SCR_ED + 1) * T], scr[(SCR_ED + 2) * T]};
+    const double egv[2] = {scr[(SCR_EG + 0) * T], scr[(SCR_EG + 1) * T]};
+    const double ebv[2] = {scr[(SCR_EB + 0) * T], scr[(SCR_EB + 1) * T]};
+    {
+      double ax[3], pred[3], t3[3], t2[2];
+      A_mul(md, s.x, ax);
+      B_mul(md, s.u, pred);
+      double Axd[3], pp[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pred[i] += ax[i];
+      cm.template up<3>(pred, pp, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Axd[i] = (hasp ? pp[i] : 0.0) - s.x[i];
+      const double Axg[2] = {s.gm[0] * s.x[0] + s.gm[1] * s.x[1] + s.gm[2] * s.x[2], s.gm[3] * s.x[0] + s.gm[4] * s.x[1] + s.gm[5] * s.x[2]};
+      double ydn[3];
+      cm.template dn<3>(s.yd, ydn, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ydn[i] = actu ? ydn[i] : 0.0;
+      At_mul(md, ydn, t3);
+      Bt_mul(md, ydn, t2);
+      const double dxv[3] = {scr[(SCR_DX + 0) * T], scr[(SCR_DX + 1) * T], scr[(SCR_DX + 2) * T]};
+      const double duv[2] = {scr[(SCR_DU + 0) * T], scr[(SCR_DU + 1) * T]};
+      double m_pri = 0, m_z = 0, m_Ax = 0, m_dua = 0, m_Aty = 0, m_Px = 0;
+      double q_pri = 0, q_z = 0, q_Ax = 0, q_dua = 0, q_Aty = 0, q_Px = 0, o = 0;
+      bool poisoned = false;  // NaN must not hide inside a compare-select max
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double rr = fabs(Axd[i] - s.zd[i]), zz = fabs(s.zd[i]), aa = fabs(Axd[i]);
+          poisoned |= !(rr == rr);
+          m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
+          q_pri = dmax(q_pri, edv[i] * rr); q_z = dmax(q_z, edv[i] * zz); q_Ax = dmax(q_Ax, edv[i] * aa);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double rr = fabs(Axg[r] - s.zg[r]), zz = fabs(s.zg[r]), aa = fabs(Axg[r]);
+          poisoned |= !(rr == rr);
+          m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
+          q_pri = dmax(q_pri, egv[r] * rr); q_z = dmax(q_z, egv[r] * zz); q_Ax = dmax(q_Ax, egv[r] * aa);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double Atx = -s.yd[j] + t3[j] + s.gm[j] * s.yg[0] + s.gm[3 + j] * s.yg[1];
+          const double Pxx = p.Q[j] * s.x[j];
+          const double dr = fabs(Pxx + s.qx[j] + Atx), ay = fabs(Atx), px = fabs(Pxx);
+          poisoned |= !(dr == dr);
+          m_dua = dmax(m_dua, dr); m_Aty = dmax(m_Aty, ay); m_Px = dmax(m_Px, px);
+          q_dua = dmax(q_dua, dxv[j] * dr); q_Aty = dmax(q_Aty, dxv[j] * ay); q_Px = dmax(q_Px, dxv[j] * px);
+          o += 0.5 * s.x[j] * Pxx + s.qx[j] * s.x[j];
+        }
+      }
+      if (actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double rr = fabs(s.u[j] - s.zb[j]), zz = fabs(s.zb[j]), aa = fabs(s.u[j]);
+          m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
+          q_pri = dmax(q_pri, ebv[j] * rr); q_z = dmax(q_z, ebv[j] * zz); q_Ax = dmax(q_Ax, ebv[j] * aa);
+          const double Atu = t2[j] + s.yb[j];
+          const double Pxu = p.R[j] * s.u[j];
+          const double dr = fabs(Pxu + qu[j] + Atu), ay = fabs(Atu), px = fabs(Pxu);
+          poisoned |= !(dr == dr) || !(rr == rr);
+          m_dua = dmax(m_dua, dr); m_Aty = dmax(m_Aty, ay); m_Px = dmax(m_Px, px);
+          q_dua = dmax(q_dua, duv[j] * dr); q_Aty = dmax(q_Aty, duv[j] * ay); q_Px = dmax(q_Px, duv[j] * px);
+          o += 0.5 * s.u[j] * Pxu + qu[j] * s.u[j];
+        }
+      }
+      poisoned = cm.any(poisoned);
+      pri_res = cm.rmax(m_pri); n_z = cm.rmax(m_z); n_Ax = cm.rmax(m_Ax);
+      if (poisoned) pri_res = 2.0 * OSQP_INFTY;
+      dua_res = cm.rmax(m_dua); n_Aty = cm.rmax(m_Aty); n_Px = cm.rmax(m_Px);
+      s_pri = cm.rmax(q_pri); s_z = cm.rmax(q_z); s_Ax = cm.rmax(q_Ax);
+      s_dua = c * cm.rmax(q_dua); s_Aty = c * cm.rmax(q_Aty); s_Px = c * cm.rmax(q_Px);
+      obj = cm.rsum(o);
+    }
+
+    // ---------- termination (OSQP check_termination, exact then — on the last iteration — approximate) ---------
+    bool finished = false, exact_hit = false;
+    if (chk || last) {
+      const int passes = last ? 2 : 1;
+      for (int pass = 0; pass < passes && !finished; ++pass) {
+        const bool approximate = pass == 1;
+        double eps_abs = p.eps_abs, eps_rel = p.eps_rel, epi = p.eps_prim_inf, edi = p.eps_dual_inf;
+        if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) { status = ST_NON_CVX; finished = true; exact_hit = !approximate; break; }
+        if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
+        const bool prim_ok = pri_res < eps_abs + eps_rel * dmax(n_z, n_Ax);
+        const bool dual_ok = dua_res < eps_abs + eps_rel * dmax(scr[SCR_NQ * T], dmax(n_Aty, n_Px));
+        bool pinf = false, dinf = false;
+        if (!prim_ok) {
+          // is_primal_infeasible: delta_y projected on the polar of the recession cone of [l, u]
+          double dyd[3], dyg[2], dyb[2];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) dyd[i] = s.yd[i] - scr[(SCR_PYD + i) * T];   // finite l = u: no projection
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            dyg[r] = s.yg[r] - scr[(SCR_PYG + r) * T];
+            dyb[r] = s.yb[r] - scr[(SCR_PYB + r) * T];
+            // upper bound infinite (scaled test): keep the non-positive part, or nothing if the lower is infinite too
+            dyg[r] = (egv[r] * s.gl[r] < -INF_THRESH) ? 0.0 : dmin(dyg[r], 0.0);
+            const double lbb = ebv[r] * s.bl[r], ubb = ebv[r] * s.bu[r];
+            if (ubb > INF_THRESH) dyb[r] = (lbb < -INF_THRESH) ? 0.0 : dmin(dyb[r], 0.0);
+            else if (lbb < -INF_THRESH) dyb[r] = dmax(dyb[r], 0.0);
+          }
+          double mx = 0.0, lhs = 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { dyd[i] = act ? dyd[i] : 0.0; mx = dmax(mx, fabs(dyd[i])); lhs += s.bd[i] * dyd[i]; }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            dyg[r] = act ? dyg[r] : 0.0; dyb[r] = actu ? dyb[r] : 0.0;
+            mx = dmax(mx, dmax(fabs(dyg[r]), fabs(dyb[r])));
+            lhs += s.gl[r] * dmin(dyg[r], 0.0) + s.bu[r] * dmax(dyb[r], 0.0) + s.bl[r] * dmin(dyb[r], 0.0);
+          }
+          const double ndy = cm.rmax(mx);  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
+          const double lhs_all = cm.rsum(lhs);
+          if (c * ndy > epi && lhs_all < -epi * ndy) {
+            double dn[3], t3[3], t2[2];
+            cm.template dn<3>(dyd, dn, 1);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dn[i] = actu ? dn[i] : 0.0;
+            At_mul(md, dn, t3);
+            Bt_mul(md, dn, t2);
+            double m2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m2 = dmax(m2, fabs(-dyd[j] + t3[j] + s.gm[j] * dyg[0] + s.gm[3 + j] * dyg[1]));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) m2 = dmax(m2, fabs(t2[j] + dyb[j]));
+            pinf = cm.rmax(m2) < epi * ndy;
+          }
+        }
+        if (!dual_ok) {
+          // is_dual_infeasible
+          double ddx[3], ddu[2];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) ddx[j] = s.x[j] - scr[(SCR_PX + j) * T];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) ddu[j] = s.u[j] - scr[(SCR_PU + j) * T];
+          double mx = 0.0, qd = 0.0, mp = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { mx = dmax(mx, fabs(ddx[j])); qd += s.qx[j] * ddx[j]; mp = dmax(mp, fabs(p.Q[j] * ddx[j])); }
+          if (actu) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { mx = dmax(mx, fabs(ddu[j])); qd += qu[j] * ddu[j]; mp = dmax(mp, fabs(p.R[j] * ddu[j])); }
+          }
+          const double ndx = cm.rmax(mx);
+          const double qd_all = cm.rsum(qd), mp_all = cm.rmax(mp);
+          if (ndx > edi && qd_all < -edi * ndx && mp_all < edi * ndx) {
+            double ax[3], pred[3];
+            A_mul(md, ddx, ax);
+            B_mul(md, ddu, pred);
+            bool bad = false;
+            const double th = edi * ndx;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pred[i] += ax[i];
+            double pp[3];
+            cm.template up<3>(pred, pp, 1);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {  // equality rows: both sides finite
+              const double a = (hasp ? pp[i] : 0.0) - ddx[i];
+              if (act && (a > th || a < -th)) bad = true;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const double a = s.gm[3 * r] * ddx[0] + s.gm[3 * r + 1] * ddx[1] + s.gm[3 * r + 2] * ddx[2];
+              if (act && (egv[r] * s.gl[r] > -INF_THRESH && a < -th)) bad = true;   // upper side is infinite
+              const double b = ddu[r];
+              if (actu && ((ebv[r] * s.bu[r] < INF_THRESH && b > th) || (ebv[r] * s.bl[r] > -INF_THRESH && b < -th))) bad = true;
+            }
+            dinf = !cm.any(bad);
+          }
+        }
+        if (prim_ok && dual_ok) { status = approximate ? ST_SOLVED_INACC : ST_SOLVED; finished = true; }
+        else if (pinf) { status = approximate ? ST_PINF_INACC : ST_PINF; obj = OSQP_INFTY; finished = true; }
+        else if (dinf) { status = approximate ? ST_DINF_INACC : ST_DINF; obj = -OSQP_INFTY; finished = true; }
+        exact_hit = finished && !approximate;
+      }
+      if (!finished && last) { status = ST_MAX_ITER; finished = true; }
+      // OSQP leaves the loop BEFORE adapt_rho only when the in-loop exact check fires; the after-loop checks
+      // (iteration max_iter) come after that iteration's adapt_rho
+      if (chk && exact_hit) break;
+    }
+    if (adp) {
+      // compute_rho_estimate on the scaled residuals, adapt_rho
+      const double pr = s_pri / (dmax(s_z, s_Ax) + 1e-10);
+      const double dr = s_dua / (dmax(scr[SCR_SNQ * T], dmax(s_Aty, s_Px)) + 1e-10);
+      double rho_new = rho_bar * sqrt(pr / (dr + 1e-10));
+      rho_new = dmin(dmax(rho_new, RHO_MIN), RHO_MAX);
+      if (rho_new > rho_bar * p.adaptive_rho_tolerance || rho_new < rho_bar / p.adaptive_rho_tolerance) {
+        rho_bar = rho_new;
+        ++n_rho_updates;
+        need_factor = !finished;
+      }
+    }
+    if (finished) break;
+    ++iter;
+  }
+
+  // ---------------- store (OSQP store_solution: NaN + cold start when infeasible) ---------------------------
+  const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF || status == ST_DINF_INACC || status == ST_NON_CVX);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (p.x_out) {
+    double* xo = p.x_out + (size_t)qp * nvar;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) xo[3 * k + j] = has_sol ? s.x[j] : qnan;
+    }
+    if (actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) xo[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] : qnan;
+    }
+  }
+  if (p.y_out) {
+    double* yo = p.y_out + (size_t)qp * mcon;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) yo[3 * k + j] = has_sol ? s.yd[j] : qnan;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) yo[3 * (N + 1) + 2 * k + r] = has_sol ? s.yg[r] : qnan;
+    }
+    if (actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) yo[5 * (N + 1) + 2 * k + j] = has_sol ? s.yb[j] : qnan;
+    }
+  }
+  if (k == 0) {
+    if (p.u0_out) { p.u0_out[2 * (size_t)qp] = has_sol ? s.u[0] : qnan; p.u0_out[2 * (size_t)qp + 1] = has_sol ? s.u[1] : qnan; }
+    if (p.status) p.status[qp] = status;
+    if (p.iters) p.iters[qp] = iter;
+    if (p.rho_updates) p.rho_updates[qp] = n_rho_updates;
+    if (p.info) {
+      double* io = p.info + 4 * (size_t)qp;
+      io[0] = obj; io[1] = pri_res; io[2] = dua_res; io[3] = rho_bar;
+    }
+    if (p.packed) {
+      double* po = p.packed + 4 * (size_t)qp;
+      po[0] = has_sol ? s.u[0] : qnan; po[1] = has_sol ? s.u[1] : qnan; po[2] = (double)status; po[3] = (double)iter;
+    }
+  }
+  if (slot) {
+    // scaled iterates for the next warm start; zeros (cold start) when there is no solution
+    double* sx_ = slot;
+    double* sz_ = slot + nvar;
+    double* sy_ = slot + nvar + mcon;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double e = scr[(SCR_ED + j) * T];
+        sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * T] : 0.0;
+        sz_[3 * k + j] = has_sol ? e * s.zd[j] : 0.0;
+        sy_[3 * k + j] = has_sol ? c * s.yd[j] / e : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double e = scr[(SCR_EG + r) * T];
+        sz_[3 * (N + 1) + 2 * k + r] = has_sol ? e * s.zg[r] : 0.0;
+        sy_[3 * (N + 1) + 2 * k + r] = has_sol ? c * s.yg[r] / e : 0.0;
+      }
+    }
+    if (actu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double e = scr[(SCR_EB + j) * T];
+        sx_[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] / scr[(SCR_DU + j) * T] : 0.0;
+        sz_[5 * (N + 1) + 2 * k + j] = has_sol ? e * s.zb[j] : 0.0;
+        sy_[5 * (N + 1) + 2 * k + j] = has_sol ? c * s.yb[j] / e : 0.0;
+      }
+    }
+    if (k == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
+  }
+}
+
+template <int NLEV, int WPQ, bool LASTFULL>
+static cudaError_t launch_one(const KParams& p, cudaStream_t stream) {
+  constexpr int T = 32 * WPQ;
+  size_t smem = (size_t)(2 * (NLEV * 9 - 1)) * T * sizeof(double);
+  if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  admm_kernel<NLEV, WPQ, LASTFULL><<<p.B, T, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace f110
