@@ -203,7 +203,9 @@ def main_product(args):
     sol = M.MpcSolver(M.default_config(N_HORIZON), M.default_settings(warm_start=0), max_batch=B, device=local)
     # ---- device-resident inputs / outputs
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d_recs, d_grid, d_off, d_rot, d_pose, d_tab = (t(wl[k]) for k in ("recs", "grids", "offs", "rots", "pose_xy", "table_xy"))
+    # records padded to an even stride: 16-byte aligned rows, which the kernel stages with one TMA bulk copy each
+    wl["recs_padded"] = np.pad(wl["recs"], ((0, 0), (0, wl["recs"].shape[1] % 2)))
+    d_recs, d_grid, d_off, d_rot, d_pose, d_tab = (t(wl[k]) for k in ("recs_padded", "grids", "offs", "rots", "pose_xy", "table_xy"))
     d_u0 = torch.empty(B, 2, dtype=torch.float64, device=dev)
     d_status = torch.empty(B, dtype=torch.int32, device=dev)
     d_iters = torch.empty(B, dtype=torch.int32, device=dev)

@@ -232,7 +232,8 @@ class MpcSolver:
             return torch.as_tensor(_Dev(ptr.value, shape, typestr), device="cuda:%d" % self.device)
         blocks2 = 100 * 100
         return dict(grid=view(ptrs[0], (scenes, blocks2), "<f4"), offset=view(ptrs[1], (scenes, 2), "<f4"),
-                    l1l2=view(ptrs[2], (scenes, 6), "<f8"), recs=view(ptrs[3], (nrec or scenes, record_doubles(self.N)), "<f8"),
+                    l1l2=view(ptrs[2], (scenes, 6), "<f8"),
+                    recs=view(ptrs[3], (nrec or scenes, (record_doubles(self.N) + 1) & ~1), "<f8")[:, :record_doubles(self.N)],
                     best_global=view(ptrs[4], (scenes,), "<i4"))
 
     def reset(self):

@@ -23,6 +23,9 @@ struct KParams {
   // OSQP settings (f110_solver_settings)
   double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval, warm_start;
+  // TMA staging of the parameter record (set by the launcher): bytes of one bulk copy (0 = plain loads) and where the
+  // record lands in dynamic shared memory (in doubles)
+  int rec_bulk_bytes, rec_smem_offset;
   // buffers (device)
   const double* recs;
   double* x_out;      // [B][5N+3] or null

@@ -14,7 +14,10 @@
 //    eliminated per stage (2x2), leaving a symmetric block-tridiagonal system in x_0..x_N with 3x3 blocks.
 //  * That system is solved by parallel cyclic reduction across the lanes of the warp: log2(N+1) levels,
 //    every lane busy at every level.  The PCR multipliers are computed once per rho (factor step) and kept
-//    in shared memory; each iteration only applies them to the right-hand side.
+//    in shared memory (negated, in 16-byte pairs); each iteration only applies them to the right-hand side
+//    as FMA chains.  The top level is one-sided (partner = stage k XOR h) and stores a single 3x3 block.
+//  * The parameter record is staged into shared memory by one bulk asynchronous copy (TMA, cp.async.bulk +
+//    mbarrier) when it is 16-byte aligned; the Ruiz passes do not wait for anything but that one transfer.
 //  * x/z/y update, projection onto [l,u], residual norms and the termination test are fused in the same
 //    kernel; all reductions are warp shuffles.  Nothing but the parameter record is read from HBM and
 //    nothing but the solution is written (a per-QP scratch line in L2 holds the scaling vectors and the
@@ -70,6 +73,32 @@ __device__ __forceinline__ double rsqrt_scaling(double x) {
   return fma(y, e, y);
 }
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return dmin(dmax(v, lo), hi); }
+
+// ---- bulk asynchronous copy (TMA) of the parameter record into shared memory ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(phase)
+      : "memory");
+}
 
 // ---- cross-stage communication ------------------------------------------------------------------------------
 // One stage per thread.  WPQ = warps per QP: 1 -> everything is a warp shuffle; 2 or 4 (horizons 32..127) -> the
@@ -266,6 +295,19 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 
   // ---------------- load the parameter record, linearise, stack -----------------------------------------
   const double* rec = p.recs + (size_t)qp * p.stride;
+  if (p.rec_bulk_bytes) {
+    // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
+    // is a shared-memory read
+    double* rec_sm = smem_all + p.rec_smem_offset;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
+    if (k == 0) {
+      mbar_init(smem_u32(bar), 1);
+      bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
+    }
+    cm.sync();
+    mbar_wait(smem_u32(bar), 0);
+    rec = rec_sm;
+  }
   const double x0[3] = {rec[0], rec[1], rec[2]};
   const double vlin = rec[3], slin = rec[4];
   if (!(vlin == vlin)) {
@@ -1048,10 +1090,20 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 }
 
 template <int NLEV, int WPQ, bool LASTFULL>
-static cudaError_t launch_one(const KParams& p, cudaStream_t stream) {
+static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
+  KParams p = pin;
   size_t smem = (size_t)(2 * (NLEV * 9 - 1)) * T * sizeof(double);
   if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
+  // TMA staging of the record: base and stride 16-byte aligned, record rounded up to 16 bytes fits inside the stride
+  const int rec_even = (11 + 3 * p.N + 1) & ~1;
+  p.rec_bulk_bytes = 0;
+  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) {
+    smem = (smem + 15) / 16 * 16;
+    p.rec_smem_offset = (int)(smem / sizeof(double));
+    p.rec_bulk_bytes = rec_even * (int)sizeof(double);
+    smem += (size_t)p.rec_bulk_bytes + 16;  // + the mbarrier
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -194,15 +194,16 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (count == 0) return F110_OK;
   const int N = s->cfg.horizon, n = 5 * N + 3, m = 7 * N + 5;
   const int rd = f110_mpc_record_doubles(N);
+  const int rdp = (rd + 1) & ~1;  // device stride: even, so every record is 16-byte aligned for the kernel's TMA staging
   if (rec_stride < rd) return fail(F110_ERR_ARG, "f110_mpc_solve_host: record stride too small");
   constexpr int kSmallBatch = 16;
   CUDA_TRY(cudaSetDevice(s->device));
   if (!s->d_recs) {
     const size_t B = s->max_batch > kSmallBatch ? s->max_batch : kSmallBatch;  // the compact small-batch layout needs kSmallBatch slots
     s->out_bytes = B * (2 * sizeof(double) + 2 * sizeof(int32_t)) + 16 + B * (size_t)(n + m) * sizeof(double);
-    CUDA_TRY(cudaMalloc(&s->d_recs, B * rd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_recs, B * rdp * sizeof(double)));
     CUDA_TRY(cudaMalloc(&s->d_out, s->out_bytes));
-    CUDA_TRY(cudaHostAlloc(&s->h_pin, kSmallBatch * (size_t)(rd + 2 + 1 + n + m) * sizeof(double) + 64, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_pin, kSmallBatch * (size_t)(rdp + 2 + 1 + n + m) * sizeof(double) + 64, cudaHostAllocDefault));
   }
   const bool small = count <= kSmallBatch;
   // small batches use a compact layout sized for kSmallBatch so the whole result is ONE device-to-host copy
@@ -217,17 +218,17 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (small) {
     // latency path: records staged through pinned memory (true async DMA)
     double* hp = reinterpret_cast<double*>(s->h_pin);
-    for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rd, recs + (size_t)b * rec_stride, rd * sizeof(double));
-    CUDA_TRY(cudaMemcpyAsync(s->d_recs, hp, (size_t)count * rd * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rdp, recs + (size_t)b * rec_stride, rd * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(s->d_recs, hp, (size_t)count * rdp * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   } else {
-    CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rd * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
+    CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rdp * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
                                cudaMemcpyHostToDevice, s->stream));
   }
-  int rc = f110_mpc_solve_device(s, count, s->d_recs, rd, x ? d_x : nullptr, y ? d_y : nullptr, d_u0, d_status, d_iters, nullptr, nullptr,
+  int rc = f110_mpc_solve_device(s, count, s->d_recs, rdp, x ? d_x : nullptr, y ? d_y : nullptr, d_u0, d_status, d_iters, nullptr, nullptr,
                                  s->stream);
   if (rc) return rc;
   if (small) {
-    unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rd * sizeof(double);
+    unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rdp * sizeof(double);
     const size_t bytes = y ? o_y + (size_t)count * m * sizeof(double) : (x ? o_x + (size_t)count * n * sizeof(double) : o_x);
     CUDA_TRY(cudaMemcpyAsync(ho, s->d_out, bytes, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -275,7 +276,7 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   if (scenes == 0) return F110_OK;
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (int)(cc->occ_size / cc->occ_discrete);           // occupancy_grid.cpp:9
-  const int N = s->cfg.horizon, rd = f110_mpc_record_doubles(N);
+  const int N = s->cfg.horizon, rd = (f110_mpc_record_doubles(N) + 1) & ~1;  // even stride: records stay 16-byte aligned (TMA staging)
   auto& c = s->cyc;
   if (c.blocks != blocks || c.paths < paths) {
     c.release();

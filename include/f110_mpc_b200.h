@@ -106,7 +106,9 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
                         double* y, double* u0, int32_t* status, int32_t* iters);
 
 /* Same, DEVICE buffers, stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream),
- * no synchronisation.  info: count x 4 = objective, primal residual, dual residual, rho at exit. */
+ * no synchronisation.  info: count x 4 = objective, primal residual, dual residual, rho at exit.
+ * When d_recs is 16-byte aligned and rec_stride is even (e.g. record_doubles + 1), the kernel stages each record into
+ * shared memory with one bulk asynchronous copy (TMA); otherwise it reads it with plain loads. */
 int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x,
                           double* d_y, double* d_u0, int32_t* d_status, int32_t* d_iters,
                           int32_t* d_rho_updates, double* d_info, void* cuda_stream);
@@ -176,7 +178,8 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
                     const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp,
                     double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid);
 /* Device buffers the last f110_cycle_device call filled (for inspection / tests): grids (scenes x blocks^2 floats),
- * offsets (x2 floats), l1l2 (x6 doubles), records (x record_doubles), best_global (int32). Any pointer may be NULL. */
+ * offsets (x2 floats), l1l2 (x6 doubles), records (row stride = record_doubles rounded up to even), best_global (int32).
+ * Any pointer may be NULL. */
 int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs,
                        int32_t** d_best_global);
 

@@ -157,6 +157,26 @@ def test_full_size_batch_kkt_properties(pkg, oracle, workloads):
     np.testing.assert_allclose(g["x"][:, :3], recs[:, :3], atol=1e-4)
 
 
+def test_device_entry_both_record_paths(pkg, workloads):
+    # f110_mpc_solve_device stages records by TMA bulk copy when they are 16-byte aligned (even stride), with plain loads otherwise
+    import torch
+    N, B = 30, 128
+    recs = workloads.tracking_batch(B, N, seed=21)
+    dev = torch.device("cuda:0")
+    outs = []
+    for pad in (0, 1, 3):                       # strides 101 (plain), 102 (TMA), 104 (TMA)
+        r = torch.from_numpy(np.pad(recs, ((0, 0), (0, pad)), constant_values=np.nan)).to(dev)
+        sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(warm_start=0), B)
+        x = torch.empty(B, sol.n, dtype=torch.float64, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        sol.solve_device(r, x, None, None, st, it, None, None)
+        torch.cuda.synchronize()
+        outs.append((x.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()))
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o[0], outs[0][0]); np.testing.assert_array_equal(o[1], outs[0][1])
+    assert (outs[0][2] == 1).all()
+
+
 def test_api_errors(pkg):
     sol = pkg.MpcSolver(max_batch=8)
     with pytest.raises(RuntimeError, match="exceeds max_batch"):
