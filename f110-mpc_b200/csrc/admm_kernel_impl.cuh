@@ -438,16 +438,8 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) tb[j] = eb[j] * du[j];
-      if (!act) {  // lanes above N: keep D = E = 1
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { tx[j] = 1.0; td[j] = 1.0; }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) tg[j] = 1.0;
-      }
-      if (!actu) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { tu[j] = 1.0; tb[j] = 1.0; }
-      }
+      // (stages above N scale themselves freely: every sum, max and neighbour read masks them out, and each pass moves a
+      //  factor by at most 1e2, so nothing overflows)
 #pragma unroll
       for (int j = 0; j < 3; ++j) dx[j] *= rsqrt_scaling(limit_scaling(tx[j]));
 #pragma unroll
@@ -723,11 +715,11 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       double gx[3], gu[2], t3[3], t2[2];
       At_mul(md, sdn, t3);
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        gx[j] = s.sx[j] * s.x[j] - s.qx[j] - sd[j] + t3[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1];
+      for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
+        gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
       Bt_mul(md, sdn, t2);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) gu[j] = s.su[j] * s.u[j] - qu[j] + t2[j] + sb[j];
+      for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
       // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
       const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
       double f[3];
@@ -806,7 +798,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 #pragma unroll
       for (int r2 = 0; r2 < 2; ++r2) {
         const double zr = al * ztg[r2] + oma * s.zg[r2];
-        const double zn = clampd(zr + s.ig[r2] * s.yg[r2], s.gl[r2], OSQP_INFTY);
+        const double zn = dmax(zr + s.ig[r2] * s.yg[r2], s.gl[r2]);  // upper bound is +INFTY: the projection is a max
         s.yg[r2] += s.rg[r2] * (zr - zn);
         s.zg[r2] = zn;
         const double zrb = al * ut[r2] + oma * s.zb[r2];
