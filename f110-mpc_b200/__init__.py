@@ -26,7 +26,7 @@ class MpcConfig(C.Structure):
     """f110_mpc_config"""
     _fields_ = [("horizon", C.c_int32), ("gap_mode", C.c_int32), ("dt", C.c_double), ("wheelbase", C.c_double),
                 ("q", C.c_double * 3), ("r", C.c_double * 2), ("u_des", C.c_double * 2), ("u_min", C.c_double * 2),
-                ("u_max", C.c_double * 2)]
+                ("u_max", C.c_double * 2), ("rate_rows", C.c_int32), ("reserved", C.c_int32), ("rate_delta", C.c_double)]
 
 
 class SolverSettings(C.Structure):
@@ -47,7 +47,7 @@ class CycleConfig(C.Structure):
 
 
 EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_record_doubles",
-           "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_last_error", "f110_device_count",
+           "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_mpc_num_rows", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
            "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma", "f110_cycle_default_config",
            "f110_cycle_device", "f110_cycle_host", "f110_cycle_buffers"]
@@ -107,11 +107,14 @@ def _check(rc, what):
         raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, lib().f110_last_error().decode()))
 
 
-def default_config(horizon=30, gap_mode=0):
+def default_config(horizon=30, gap_mode=0, rate_delta=None):
+    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; None = the reference's row set."""
     c = MpcConfig()
     lib().f110_mpc_default_config(C.byref(c))
     c.horizon = horizon
     c.gap_mode = gap_mode
+    if rate_delta is not None:
+        c.rate_rows, c.rate_delta = 1, rate_delta
     return c
 
 
@@ -160,7 +163,7 @@ class MpcSolver:
         self.settings = settings or default_settings()
         self.N = self.config.horizon
         self.n = 5 * self.N + 3
-        self.m = 7 * self.N + 5
+        self.m = 7 * self.N + 5 + (self.N if self.config.rate_rows else 0)   # f110_mpc_num_rows
         self.max_batch = max_batch
         self.device = device
         self._h = C.c_void_p()
@@ -313,6 +316,8 @@ def host():
         H.f110h_best_global_idx.argtypes = [fp, C.c_int, dp, dp]
         H.f110h_mpc_create.restype = C.c_void_p
         H.f110h_mpc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        H.f110h_mpc_create_rate.restype = C.c_void_p
+        H.f110h_mpc_create_rate.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int]
         H.f110h_mpc_destroy.argtypes = [C.c_void_p]
         H.f110h_mpc_update_scan.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, fp, C.c_int]
         H.f110h_mpc_update.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp]
@@ -376,9 +381,10 @@ def host_best_global_idx(wp_xy, pose7):
 class HostMPC:
     """The C++ `MPC` class (host/mpc.h): Update(State, Input, vector<State>&) -> solved_trajectory()."""
 
-    def __init__(self, horizon=30, gap_mode=0, device=0):
+    def __init__(self, horizon=30, gap_mode=0, device=0, steer_rate_max=0.0):
         self.N = horizon
-        self._h = host().f110h_mpc_create(horizon, gap_mode, device)
+        self.m = 7 * horizon + 5 + (horizon if steer_rate_max > 0 else 0)
+        self._h = host().f110h_mpc_create_rate(horizon, gap_mode, steer_rate_max, device)
         if not self._h:
             raise RuntimeError("MPC construction failed: " + lib().f110_last_error().decode())
 
@@ -391,7 +397,7 @@ class HostMPC:
         input2 = np.ascontiguousarray(input2, dtype=np.float64)
         desired = np.ascontiguousarray(desired, dtype=np.float64)
         N = self.N
-        inputs = np.zeros((N, 2)); x = np.zeros(5 * N + 3); y = np.zeros(7 * N + 5); l1l2 = np.zeros(6)
+        inputs = np.zeros((N, 2)); x = np.zeros(5 * N + 3); y = np.zeros(self.m); l1l2 = np.zeros(6)
         st, it = C.c_int(), C.c_int()
         n = host().f110h_mpc_update(self._h, _dp(state3), _dp(input2), _dp(desired), desired.shape[0], _dp(inputs), _dp(x), _dp(y),
                                     C.byref(st), C.byref(it), _dp(l1l2))

@@ -1,5 +1,5 @@
 // Launch dispatch of the batched ADMM solve.  The kernel template lives in admm_kernel_impl.cuh and is instantiated in
-// three translation units (one per warps-per-QP class) so the instantiations compile in parallel.
+// one translation unit per warps-per-QP class (and per row set) so the instantiations compile in parallel.
 #include "admm_kernel.cuh"
 
 namespace f110 {
@@ -7,11 +7,19 @@ namespace f110 {
 cudaError_t launch_admm_w1(const KParams& p, cudaStream_t stream, int nlev);  // horizons 1..31,  one warp per QP
 cudaError_t launch_admm_w2(const KParams& p, cudaStream_t stream);            // horizons 32..63, two warps per QP
 cudaError_t launch_admm_w4(const KParams& p, cudaStream_t stream);            // horizons 64..127, four warps per QP
+cudaError_t launch_admm_w1r(const KParams& p, cudaStream_t stream, int nlev); // + steering-rate rows, horizons 1..31
+cudaError_t launch_admm_w2r(const KParams& p, cudaStream_t stream);           // + steering-rate rows, horizons 32..63
 
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {
   int nlev = 0;
   while ((1 << nlev) <= p.N) ++nlev;
   if (launches) *launches = 1;
+  if (p.rate_rows) {
+    // the 4x4 multipliers of a 4-warp QP do not fit in one SM's shared memory: horizons above 63 are refused at create
+    if (nlev >= 1 && nlev <= 5) return launch_admm_w1r(p, stream, nlev);
+    if (nlev == 6) return launch_admm_w2r(p, stream);
+    return cudaErrorInvalidValue;
+  }
   if (nlev >= 1 && nlev <= 5) return launch_admm_w1(p, stream, nlev);
   if (nlev == 6) return launch_admm_w2(p, stream);
   if (nlev == 7) return launch_admm_w4(p, stream);

@@ -10,7 +10,7 @@
 namespace f110 {
 
 // per-QP scratch line in global memory: D, E (12) + previous iterate (12), one column per lane
-constexpr int SCR_ROWS_ALLOC = 40;                       // rows of the per-QP scratch line (37 used)
+constexpr int SCR_ROWS_ALLOC = 44;                       // rows of the per-QP scratch line (37 used, 41 with steering-rate rows)
 constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // sized for 4 warps per QP (horizon <= 127)
 
 struct KParams {
@@ -20,6 +20,9 @@ struct KParams {
   double Q[3], R[2], u_des[2], u_min[2], u_max[2];
   double qu[2];            // -R u_des
   double one_minus_alpha;
+  // steering-rate rows (f110_mpc_config.rate_rows): N extra rows  delta_k - delta_{k-1} in [-rate_delta, rate_delta]
+  int rate_rows;
+  double rate_delta;
   // OSQP settings (f110_solver_settings)
   double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval, warm_start;
@@ -29,7 +32,7 @@ struct KParams {
   // buffers (device)
   const double* recs;
   double* x_out;      // [B][5N+3] or null
-  double* y_out;      // [B][7N+5] or null
+  double* y_out;      // [B][7N+5 (+N with rate rows)] or null
   double* u0_out;     // [B][2] or null
   int32_t* status;    // [B] or null
   int32_t* iters;     // [B] or null
@@ -40,8 +43,10 @@ struct KParams {
   double* scratch;    // [B][SCRATCH_DOUBLES]
 };
 
-// doubles per warm-start slot: x(5N+3) + z(7N+5) + y(7N+5) + rho + valid flag
-__host__ __device__ inline int state_doubles(int N) { return (5 * N + 3) + 2 * (7 * N + 5) + 2; }
+// constraint rows: dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N | steering rate N (optional)
+__host__ __device__ inline int num_rows(int N, int rate_rows) { return 7 * N + 5 + (rate_rows ? N : 0); }
+// doubles per warm-start slot: x(n) + z(m) + y(m) + rho + valid flag
+__host__ __device__ inline int state_doubles(int N, int rate_rows) { return (5 * N + 3) + 2 * num_rows(N, rate_rows) + 2; }
 
 // Launch the solve for p.B QPs on `stream`. Returns the cudaError of the launch.
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches);

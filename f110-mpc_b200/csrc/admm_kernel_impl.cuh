@@ -23,7 +23,11 @@
 //    nothing but the solution is written (a per-QP scratch line in L2 holds the scaling vectors and the
 //    previous iterate, touched once per termination check).
 //
-// Lane k owns stage k: x_k(3), u_k(2) (k<N), dynamics rows k (3), gap rows k (2), input-box rows k (2).
+//  * RATE = true adds N steering-rate rows  delta_k - delta_{k-1} in [-D, D]  (row 0: delta_0 - steer_prev).  They couple
+//    consecutive inputs, so only the speed v_k is eliminated per stage (a scalar pivot) and the steering angle joins
+//    the reduced unknown: s_k = (x_k, delta_k), 4x4 blocks, same cyclic reduction (plain doubles in shared memory).
+//
+// Lane k owns stage k: x_k(3), u_k(2) (k<N), dynamics rows k (3), gap rows k (2), input-box rows k (2), rate row k (1).
 // Lanes above N hold all-zero state and never feed an active lane (every cross-lane read is masked or
 // multiplied by a zero multiplier), so no branch in the iteration depends on the lane.
 #pragma once
@@ -223,6 +227,62 @@ __device__ __forceinline__ void inv_spd3(const double* a, double* inv) {
   inv[8] = i2;
 }
 
+// ---- D x D helpers for the steering-rate variant (row-major double[D*D]) ------------------------------
+template <int D>
+__device__ __forceinline__ void mmD(const double* a, const double* b, double* c) {  // c = a b
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double v = a[D * i] * b[j];
+#pragma unroll
+      for (int t = 1; t < D; ++t) v = fma(a[D * i + t], b[D * t + j], v);
+      c[D * i + j] = v;
+    }
+}
+// inverse of a symmetric positive definite D x D via LDL^T (reads the lower triangle)
+template <int D>
+__device__ __forceinline__ void inv_spdD(const double* a, double* inv) {
+  double L[D * D], dd[D], id[D], M[D * D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double dj = a[D * j + j];
+#pragma unroll
+    for (int t = 0; t < j; ++t) dj -= L[D * j + t] * L[D * j + t] * dd[t];
+    dd[j] = dj;
+    id[j] = 1.0 / dj;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      double v = a[D * i + j];
+#pragma unroll
+      for (int t = 0; t < j; ++t) v -= L[D * i + t] * L[D * j + t] * dd[t];
+      L[D * i + j] = v * id[j];
+    }
+  }
+  // M = L^-1 (unit lower triangular)
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    M[D * j + j] = 1.0;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = j; t < i; ++t) v -= L[D * i + t] * M[D * t + j];
+      M[D * i + j] = v;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = j; t < D; ++t) v += M[D * t + i] * M[D * t + j] * id[t];
+      inv[D * i + j] = v;
+      inv[D * j + i] = v;
+    }
+}
+
 struct Model {  // Model::Linearize output (model.cpp:30-59): A = I + [0 0 a02; 0 0 a12; 0 0 0], B = [b00 0; b10 0; b20 b21]
   double a02, a12, b00, b10, b20, b21;
 };
@@ -245,7 +305,6 @@ struct Stage {
   double bd[3];            // dynamics rhs (l = u): -x_cur at k = 0, -C at k >= 1      (mpc.cpp:299,305)
   double gm[6];            // gap rows 2x3: ones at k = 0, [l1a l1b 0; l2a l2b 0] after (mpc.cpp:237-241, 260-272)
   double gl[2];            // gap lower bounds (upper is +INFTY)                       (mpc.cpp:279-300)
-  double bl[2], bu[2];     // input box                                               (mpc.cpp:281,290)
   double qx[3];            // -Q ref_k                                                 (mpc.cpp:225,228)
   // iterates (unscaled)
   double x[3], u[2];
@@ -260,21 +319,38 @@ struct Stage {
   double rdn[3];           // rho of the NEXT stage's dynamics rows
 };
 
+// What the steering-rate variant adds to a lane (empty otherwise).
+template <bool RATE>
+struct RateExt {};
+template <>
+struct RateExt<true> {
+  double zr, yr;           // rate row iterate
+  double rr, ir;           // its rho and 1/rho
+  double rrn;              // rho of the NEXT stage's rate row
+  double rlo, rhi;         // its bounds: (k == 0 ? steer_prev : 0) -/+ rate_delta
+  double wvi;              // 1 / (R_v + sigma_v + rho_box_v + b_v' R_{k+1} b_v): pivot of the speed elimination
+  double mv[3];            // R_{k+1} b_v
+};
+template <bool RATE>
+struct StageT : Stage, RateExt<RATE> {};
+
 // per-QP scratch line in global memory (L2): [24][32] doubles, element-major
 constexpr int SCR_DX = 0, SCR_DU = 3, SCR_ED = 5, SCR_EG = 8, SCR_EB = 10;       // scaling vectors D, E
 constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22;  // iterate before the last step
 constexpr int SCR_WD = 24, SCR_WG = 27, SCR_WB = 29;    // e_i^2 / c per row: rho_i = rho_bar_i * w_i (factor step only)
 constexpr int SCR_CG = 31, SCR_CB = 33;                 // row class codes of the gap / box rows (factor step only)
 constexpr int SCR_NQ = 35, SCR_SNQ = 36;                // ||q||_inf unscaled / scaled (termination checks only)
-constexpr int SCR_ROWS = 37;
+constexpr int SCR_ER = 37, SCR_WR = 38, SCR_CR = 39, SCR_PYR = 40;   // steering-rate row: E, e^2/c, class, previous y
+constexpr int SCR_ROWS = 41;
+static_assert(SCR_ROWS <= SCR_ROWS_ALLOC, "scratch line too short");
 
 }  // namespace
 
 // One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
 // NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == 32 WPQ): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
-template <int NLEV, int WPQ, bool LASTFULL>
-__global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE>
+__global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
   constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
   const int qp = blockIdx.x;
@@ -283,7 +359,10 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
   constexpr int SM_PAIRS = NLEV * 9 - 1;
   double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;
-  Comm<WPQ> cm(smem_all + 2 * SM_PAIRS * T, k);
+  // steering-rate variant: 4x4 blocks as plain doubles, element-major: 32 per level (alpha | gamma) + the final inverse
+  constexpr int SM_DOUBLES = RATE ? NLEV * 32 + 16 : 2 * SM_PAIRS;
+  double* sm_r = smem_all + k;
+  Comm<WPQ> cm(smem_all + SM_DOUBLES * T, k);
   double* scr = p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) + k;
 
   const int N = p.N;
@@ -291,7 +370,8 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   const bool actu = k < N;         // stage has an input (and box rows, and a successor)
   const bool hasp = act && k > 0;  // stage has a predecessor
   const int nvar = 5 * N + 3;
-  const int mcon = 7 * N + 5;
+  const int mcon = 7 * N + 5 + (RATE ? N : 0);
+  const int row_r0 = 7 * N + 5;    // first steering-rate row
 
   // ---------------- load the parameter record, linearise, stack -----------------------------------------
   const double* rec = p.recs + (size_t)qp * p.stride;
@@ -344,7 +424,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   }
   const double* qu = p.qu;  // -R u_des (mpc.cpp:226), precomputed on the host: lives in the constant bank
 
-  Stage s;
+  StageT<RATE> s;
   {
     const int kr = (k < N) ? k : (N - 1);  // terminal stage re-uses ref[N-1] (mpc.cpp:228)
 #pragma unroll
@@ -369,10 +449,12 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     const bool gap_on = act && (p.gap_mode == 1 || (p.gap_mode == 2 && k > 0));
     s.gl[0] = gap_on ? -l1c : -OSQP_INFTY;  // mpc.cpp:297
     s.gl[1] = gap_on ? -l2c : -OSQP_INFTY;  // mpc.cpp:298; upper bound +INFTY (mpc.cpp:288-290)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      s.bl[j] = actu ? p.u_min[j] : -HUGE_BOUND;
-      s.bu[j] = actu ? p.u_max[j] : HUGE_BOUND;
+    // input box (mpc.cpp:281,290): the same u_min / u_max on every stage, read from the constant bank.  The last stage has no
+    // input; its box rows get rho = 0 in the factor step, so whatever its z does never reaches a right-hand side.
+    if constexpr (RATE) {
+      const double base = (k == 0) ? slin : 0.0;   // row 0 is measured from the steering applied last cycle
+      s.rlo = base - p.rate_delta;
+      s.rhi = base + p.rate_delta;
     }
   }
 
@@ -382,6 +464,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   // scratch line instead of registers: the iteration loop runs at the 255-register ceiling.
   {
     double dx[3] = {1, 1, 1}, du[2] = {1, 1}, ed[3] = {1, 1, 1}, eg[2] = {1, 1}, eb[2] = {1, 1};
+    double er = 1.0;   // steering-rate row (RATE)
     const double aA02 = fabs(md.a02), aA12 = fabs(md.a12);
     const double aB[6] = {fabs(md.b00), 0.0, fabs(md.b10), 0.0, fabs(md.b20), fabs(md.b21)};
     double ag[6];
@@ -389,10 +472,19 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     for (int e = 0; e < 6; ++e) ag[e] = fabs(s.gm[e]);
     for (int it = 0; it < p.scaling; ++it) {
       double edn[3], dxp[3], dup[2];
+      double ern = 0.0;   // scale of the next stage's rate row (RATE)
       {
         const double snd[5] = {dx[0], dx[1], dx[2], du[0], du[1]};
         double rcv[5];
-        cm.template dn<3>(ed, edn, 1);
+        if constexpr (RATE) {
+          const double se[4] = {ed[0], ed[1], ed[2], er};
+          double re[4];
+          cm.template dn<4>(se, re, 1);
+          edn[0] = re[0]; edn[1] = re[1]; edn[2] = re[2];
+          ern = (k + 1 < N) ? re[3] : 0.0;
+        } else {
+          cm.template dn<3>(ed, edn, 1);
+        }
         cm.template up<5>(snd, rcv, 1);
 #pragma unroll
         for (int i = 0; i < 3; ++i) { edn[i] = actu ? edn[i] : 0.0; dxp[i] = hasp ? rcv[i] : 0.0; }
@@ -417,6 +509,12 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         for (int i = 0; i < 3; ++i) v = dmax(v, edn[i] * aB[2 * i + j] * du[j]);
         v = dmax(v, eb[j] * du[j]);
         tu[j] = v;
+      }
+      double tr = 0.0;
+      if constexpr (RATE) {
+        // column of delta_k: +1 in rate row k, -1 in rate row k+1; rate row k: +1 on delta_k, -1 on delta_{k-1}
+        tu[1] = dmax(tu[1], dmax(er, ern) * du[1]);
+        tr = er * dmax(du[1], dup[1]);
       }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {  // KKT column (= A row) of dyn row (k, i)
@@ -450,6 +548,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       for (int r = 0; r < 2; ++r) eg[r] *= rsqrt_scaling(limit_scaling(tg[r]));
 #pragma unroll
       for (int j = 0; j < 2; ++j) eb[j] *= rsqrt_scaling(limit_scaling(tb[j]));
+      if constexpr (RATE) er *= rsqrt_scaling(limit_scaling(tr));
       // cost normalisation: c_temp = 1 / max(mean column norm of P, ||q||_inf)
       double psum = 0.0, qn = 0.0;
       if (act) {
@@ -476,8 +575,14 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     for (int r = 0; r < 2; ++r) {
       const double lb = eg[r] * s.gl[r], ub = eg[r] * OSQP_INFTY;
       scr[(SCR_CG + r) * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
-      const double lbb = eb[r] * s.bl[r], ubb = eb[r] * s.bu[r];
+      const double lbb = eb[r] * p.u_min[r], ubb = eb[r] * p.u_max[r];
       scr[(SCR_CB + r) * T] = (lbb < -INF_THRESH && ubb > INF_THRESH) ? -1.0 : ((ubb - lbb < RHO_TOL) ? 1.0 : 0.0);
+    }
+    if constexpr (RATE) {
+      const double lb = er * s.rlo, ub = er * s.rhi;
+      scr[SCR_ER * T] = er;
+      scr[SCR_WR * T] = er * er * cinv;
+      scr[SCR_CR * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) scr[(SCR_WD + i) * T] = ed[i] * ed[i] * cinv;
@@ -505,8 +610,9 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
   for (int j = 0; j < 3; ++j) { s.x[j] = 0; s.zd[j] = 0; s.yd[j] = 0; }
 #pragma unroll
   for (int j = 0; j < 2; ++j) { s.u[j] = 0; s.zg[j] = 0; s.zb[j] = 0; s.yg[j] = 0; s.yb[j] = 0; }
+  if constexpr (RATE) { s.zr = 0; s.yr = 0; }
   double rho_bar = dmin(dmax(p.rho0, RHO_MIN), RHO_MAX);
-  double* slot = p.state ? p.state + (size_t)qp * state_doubles(N) : nullptr;
+  double* slot = p.state ? p.state + (size_t)qp * state_doubles(N, RATE ? 1 : 0) : nullptr;
   if (slot && p.warm_start && slot[nvar + 2 * mcon + 1] != 0.0) {
     // OSQP keeps x, z, y in SCALED coordinates across re-scalings (osqp_update_A rescales the data only):
     // x = D xbar, z = zbar / E, y = E ybar / c with the NEW D, E, c.
@@ -537,6 +643,11 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         s.zb[j] = sz_[5 * (N + 1) + 2 * k + j] / e;
         s.yb[j] = e * sy_[5 * (N + 1) + 2 * k + j] * cinv;
       }
+      if constexpr (RATE) {
+        const double e = scr[SCR_ER * T];
+        s.zr = sz_[row_r0 + k] / e;
+        s.yr = e * sy_[row_r0 + k] * cinv;
+      }
     }
   }
 
@@ -562,125 +673,231 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         const double rg = cg < 0 ? RHO_MIN : (cg > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
         const double rb = cb < 0 ? RHO_MIN : (cb > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
         s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = 1.0 / s.rg[r];
-        s.rb[r] = rb * scr[(SCR_WB + r) * T]; s.ib[r] = 1.0 / s.rb[r];
+        s.rb[r] = actu ? rb * scr[(SCR_WB + r) * T] : 0.0;
+        s.ib[r] = actu ? 1.0 / s.rb[r] : 0.0;
       }
-      cm.template dn<3>(s.rd, s.rdn, 1);
+      if constexpr (RATE) {
+        // ---- steering-rate variant: eliminate the speed v_k only; reduced unknown s_k = (x_k, delta_k), 4x4 blocks ----
+        {
+          const double cr = scr[SCR_CR * T];
+          const double rrb = cr < 0 ? RHO_MIN : (cr > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+          s.rr = actu ? rrb * scr[SCR_WR * T] : 0.0;
+          s.ir = actu ? 1.0 / s.rr : 0.0;
+          const double snd[4] = {s.rd[0], s.rd[1], s.rd[2], s.rr};
+          double rcv[4];
+          cm.template dn<4>(snd, rcv, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.rdn[i] = actu ? s.rdn[i] : 0.0;
-      double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.B) W^-1 (rdn.B)'
-      {
-        const double w00 = p.R[0] + s.su[0] + s.rb[0] + md.b00 * md.b00 * s.rdn[0] + md.b10 * md.b10 * s.rdn[1] + md.b20 * md.b20 * s.rdn[2];
-        const double w01 = md.b20 * md.b21 * s.rdn[2];
-        const double w11 = p.R[1] + s.su[1] + s.rb[1] + md.b21 * md.b21 * s.rdn[2];
-        const double idet = 1.0 / (w00 * w11 - w01 * w01);
-        s.wi[0] = actu ? w11 * idet : 0.0;
-        s.wi[1] = actu ? -w01 * idet : 0.0;
-        s.wi[2] = actu ? w00 * idet : 0.0;
-        const double M[6] = {s.rdn[0] * md.b00, 0.0, s.rdn[1] * md.b10, 0.0, s.rdn[2] * md.b20, s.rdn[2] * md.b21};
-        double MW[6];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          MW[2 * i] = M[2 * i] * s.wi[0] + M[2 * i + 1] * s.wi[1];
-          MW[2 * i + 1] = M[2 * i] * s.wi[1] + M[2 * i + 1] * s.wi[2];
+          for (int i = 0; i < 3; ++i) s.rdn[i] = actu ? rcv[i] : 0.0;
+          s.rrn = (k + 1 < N) ? rcv[3] : 0.0;
         }
+        const double bv[3] = {md.b00, md.b10, md.b20};   // column of B that multiplies the speed
+        double wv = p.R[0] + s.su[0] + s.rb[0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { s.mv[i] = s.rdn[i] * bv[i]; wv += s.mv[i] * bv[i]; }
+        s.wvi = actu ? 1.0 / wv : 0.0;
+        double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.b_v)(rdn.b_v)' / w_v
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - (MW[2 * i] * M[2 * l] + MW[2 * i + 1] * M[2 * l + 1]);
-      }
-      double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
-      cm.template up<9>(Rn, Rt, 1);
+          for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - s.mv[i] * s.mv[l] * s.wvi;
+        double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
+        cm.template up<9>(Rn, Rt, 1);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? Rt[e] : 0.0);
-      double Bm[9], Lm[9], Um[9];
-      {
-        // Hx = diag(Q + sigma_x) + G' diag(rho_g) G  (+ R~_k)
+        for (int e = 0; e < 9; ++e) Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? Rt[e] : 0.0);
+        // C = [A | b_delta] (3x4): x_{k+1} = C s_k + b_v v_k.   RnC = R~_{k+1} C,  RtC = R~_k C
+        double RnC[12], RtC[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          RnC[4 * i + 0] = Rn[3 * i]; RnC[4 * i + 1] = Rn[3 * i + 1];
+          RnC[4 * i + 2] = Rn[3 * i] * md.a02 + Rn[3 * i + 1] * md.a12 + Rn[3 * i + 2];
+          RnC[4 * i + 3] = Rn[3 * i + 2] * md.b21;
+          RtC[4 * i + 0] = Rt[3 * i]; RtC[4 * i + 1] = Rt[3 * i + 1];
+          RtC[4 * i + 2] = Rt[3 * i] * md.a02 + Rt[3 * i + 1] * md.a12 + Rt[3 * i + 2];
+          RtC[4 * i + 3] = Rt[3 * i + 2] * md.b21;
+        }
+        double Bm[16], Lm[16], Um[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // C' (R~ C)
+          const double c0 = RnC[j], c1 = RnC[4 + j], c2 = RnC[8 + j];
+          Bm[j] = c0; Bm[4 + j] = c1; Bm[8 + j] = md.a02 * c0 + md.a12 * c1 + c2; Bm[12 + j] = md.b21 * c2;
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int l = 0; l < 3; ++l)
-            Bm[3 * i + l] = (i == l ? p.Q[i] + s.sx[i] : 0.0) + s.rg[0] * s.gm[i] * s.gm[l] + s.rg[1] * s.gm[3 + i] * s.gm[3 + l] + Rt[3 * i + l];
-        double ARn[9];  // A' Rn
+            Bm[4 * i + l] += (i == l ? p.Q[i] + s.sx[i] : 0.0) + s.rg[0] * s.gm[i] * s.gm[l] + s.rg[1] * s.gm[3 + i] * s.gm[3 + l] + Rt[3 * i + l];
+        Bm[15] += p.R[1] + s.su[1] + s.rb[1] + s.rr + s.rrn;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          ARn[0 + l] = Rn[0 + l];
-          ARn[3 + l] = Rn[3 + l];
-          ARn[6 + l] = md.a02 * Rn[0 + l] + md.a12 * Rn[3 + l] + Rn[6 + l];
+        for (int j = 0; j < 3; ++j) {  // U_k = -C' R~_{k+1} [I 0] - rho_r(k+1) e4 e4'
+          Um[j] = -Rn[j]; Um[4 + j] = -Rn[3 + j];
+          Um[8 + j] = -(md.a02 * Rn[j] + md.a12 * Rn[3 + j] + Rn[6 + j]);
+          Um[12 + j] = -md.b21 * Rn[6 + j];
         }
+        Um[3] = 0.0; Um[7] = 0.0; Um[11] = 0.0; Um[15] = -s.rrn;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {  // + A' Rn A ; U_k = -A' Rn
-          const double r0 = ARn[3 * i], r1 = ARn[3 * i + 1], r2 = ARn[3 * i + 2];
-          Bm[3 * i + 0] += r0;
-          Bm[3 * i + 1] += r1;
-          Bm[3 * i + 2] += r0 * md.a02 + r1 * md.a12 + r2;
-          Um[3 * i + 0] = -r0; Um[3 * i + 1] = -r1; Um[3 * i + 2] = -r2;
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {  // L_k = -R~_k A
-          const double r0 = Rt[3 * i], r1 = Rt[3 * i + 1], r2 = Rt[3 * i + 2];
-          Lm[3 * i + 0] = hasp ? -r0 : 0.0;
-          Lm[3 * i + 1] = hasp ? -r1 : 0.0;
-          Lm[3 * i + 2] = hasp ? -(r0 * md.a02 + r1 * md.a12 + r2) : 0.0;
-        }
+        for (int e = 0; e < 12; ++e) Lm[e] = hasp ? -RtC[e] : 0.0;   // L_k = U_{k-1}'
+        Lm[12] = 0.0; Lm[13] = 0.0; Lm[14] = 0.0; Lm[15] = hasp ? -s.rr : 0.0;
         if (!act) {
 #pragma unroll
-          for (int e = 0; e < 9; ++e) { Bm[e] = (e % 4 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
+          for (int e = 0; e < 16; ++e) { Bm[e] = (e % 5 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
         }
-      }
-      // parallel cyclic reduction; multipliers alpha, gamma go to shared memory
 #pragma unroll 1
-      for (int lev = 0; lev < NLEV; ++lev) {
-        const int h = 1 << lev;
-        const bool vlo = act && (k - h >= 0);
-        const bool vhi = act && (k + h <= N);
-        double Bi[9], XU[9], XL[9];
-        inv_spd3(Bm, Bi);
-        mm3(Bi, Um, XU);
-        mm3(Bi, Lm, XL);
-        double nlo[9], nhi[9], t1[9], t2[9];
-        double alp[9], gam[9], Ln[9], Un[9];
-        cm.template both<9>(Bi, nlo, nhi, h);
-        mm3(Lm, nlo, alp);
-        mm3(Um, nhi, gam);
-        cm.template both<9>(XU, nlo, nhi, h);
-        mm3(Lm, nlo, t1);
-        mm3(Um, nhi, Un);
-        cm.template both<9>(XL, nlo, nhi, h);
-        mm3(Lm, nlo, Ln);
-        mm3(Um, nhi, t2);
+        for (int lev = 0; lev < NLEV; ++lev) {
+          const int h = 1 << lev;
+          const bool vlo = act && (k - h >= 0);
+          const bool vhi = act && (k + h <= N);
+          double Bi[16], XU[16], XL[16];
+          inv_spdD<4>(Bm, Bi);
+          mmD<4>(Bi, Um, XU);
+          mmD<4>(Bi, Lm, XL);
+          double nlo[16], nhi[16], t1[16], t2[16];
+          double alp[16], gam[16], Ln[16], Un[16];
+          cm.template both<8>(Bi, nlo, nhi, h);
+          cm.template both<8>(Bi + 8, nlo + 8, nhi + 8, h);
+          mmD<4>(Lm, nlo, alp);
+          mmD<4>(Um, nhi, gam);
+          cm.template both<8>(XU, nlo, nhi, h);
+          cm.template both<8>(XU + 8, nlo + 8, nhi + 8, h);
+          mmD<4>(Lm, nlo, t1);
+          mmD<4>(Um, nhi, Un);
+          cm.template both<8>(XL, nlo, nhi, h);
+          cm.template both<8>(XL + 8, nlo + 8, nhi + 8, h);
+          mmD<4>(Lm, nlo, Ln);
+          mmD<4>(Um, nhi, t2);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) {
-          Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
-          Lm[e] = vlo ? -Ln[e] : 0.0;
-          Um[e] = vhi ? -Un[e] : 0.0;
-          alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
-          gam[e] = vhi ? -gam[e] : 0.0;
+          for (int e = 0; e < 16; ++e) {
+            Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
+            Lm[e] = vlo ? -Ln[e] : 0.0;
+            Um[e] = vhi ? -Un[e] : 0.0;
+            sm_r[(lev * 32 + e) * T] = vlo ? -alp[e] : 0.0;        // stored negated: the solve is r += coef * neighbour
+            sm_r[(lev * 32 + 16 + e) * T] = vhi ? -gam[e] : 0.0;
+          }
         }
-        if (lev < NLEV - 1) {
-          // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+        {
+          double Bi[16];
+          inv_spdD<4>(Bm, Bi);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sm_r[(NLEV * 32 + e) * T] = Bi[e];
+        }
+      } else {
+        cm.template dn<3>(s.rd, s.rdn, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s.rdn[i] = actu ? s.rdn[i] : 0.0;
+        double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.B) W^-1 (rdn.B)'
+        {
+          const double w00 = p.R[0] + s.su[0] + s.rb[0] + md.b00 * md.b00 * s.rdn[0] + md.b10 * md.b10 * s.rdn[1] + md.b20 * md.b20 * s.rdn[2];
+          const double w01 = md.b20 * md.b21 * s.rdn[2];
+          const double w11 = p.R[1] + s.su[1] + s.rb[1] + md.b21 * md.b21 * s.rdn[2];
+          const double idet = 1.0 / (w00 * w11 - w01 * w01);
+          s.wi[0] = actu ? w11 * idet : 0.0;
+          s.wi[1] = actu ? -w01 * idet : 0.0;
+          s.wi[2] = actu ? w00 * idet : 0.0;
+          const double M[6] = {s.rdn[0] * md.b00, 0.0, s.rdn[1] * md.b10, 0.0, s.rdn[2] * md.b20, s.rdn[2] * md.b21};
+          double MW[6];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
-            sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
-            sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+            MW[2 * i] = M[2 * i] * s.wi[0] + M[2 * i + 1] * s.wi[1];
+            MW[2 * i + 1] = M[2 * i] * s.wi[1] + M[2 * i + 1] * s.wi[2];
           }
-        } else {
-          // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
-          // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
-          double one[10];
 #pragma unroll
-          for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
-          one[9] = 0.0;
+          for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int q = 0; q < 5; ++q) sm_pair[(lev * 9 + q) * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - (MW[2 * i] * M[2 * l] + MW[2 * i + 1] * M[2 * l + 1]);
         }
-      }
-      {
-        double Bi[9];
-        inv_spd3(Bm, Bi);
-        sm_pair[(NLEV * 9 - 4 + 0) * T] = make_double2(Bi[0], Bi[1]);
-        sm_pair[(NLEV * 9 - 4 + 1) * T] = make_double2(Bi[2], Bi[4]);
-        sm_pair[(NLEV * 9 - 4 + 2) * T] = make_double2(Bi[5], Bi[8]);
+        double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
+        cm.template up<9>(Rn, Rt, 1);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rt[e] = (k == 0) ? ((e % 4 == 0) ? s.rd[e / 4] : 0.0) : (act ? Rt[e] : 0.0);
+        double Bm[9], Lm[9], Um[9];
+        {
+          // Hx = diag(Q + sigma_x) + G' diag(rho_g) G  (+ R~_k)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+              Bm[3 * i + l] = (i == l ? p.Q[i] + s.sx[i] : 0.0) + s.rg[0] * s.gm[i] * s.gm[l] + s.rg[1] * s.gm[3 + i] * s.gm[3 + l] + Rt[3 * i + l];
+          double ARn[9];  // A' Rn
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            ARn[0 + l] = Rn[0 + l];
+            ARn[3 + l] = Rn[3 + l];
+            ARn[6 + l] = md.a02 * Rn[0 + l] + md.a12 * Rn[3 + l] + Rn[6 + l];
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {  // + A' Rn A ; U_k = -A' Rn
+            const double r0 = ARn[3 * i], r1 = ARn[3 * i + 1], r2 = ARn[3 * i + 2];
+            Bm[3 * i + 0] += r0;
+            Bm[3 * i + 1] += r1;
+            Bm[3 * i + 2] += r0 * md.a02 + r1 * md.a12 + r2;
+            Um[3 * i + 0] = -r0; Um[3 * i + 1] = -r1; Um[3 * i + 2] = -r2;
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {  // L_k = -R~_k A
+            const double r0 = Rt[3 * i], r1 = Rt[3 * i + 1], r2 = Rt[3 * i + 2];
+            Lm[3 * i + 0] = hasp ? -r0 : 0.0;
+            Lm[3 * i + 1] = hasp ? -r1 : 0.0;
+            Lm[3 * i + 2] = hasp ? -(r0 * md.a02 + r1 * md.a12 + r2) : 0.0;
+          }
+          if (!act) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { Bm[e] = (e % 4 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
+          }
+        }
+        // parallel cyclic reduction; multipliers alpha, gamma go to shared memory
+#pragma unroll 1
+        for (int lev = 0; lev < NLEV; ++lev) {
+          const int h = 1 << lev;
+          const bool vlo = act && (k - h >= 0);
+          const bool vhi = act && (k + h <= N);
+          double Bi[9], XU[9], XL[9];
+          inv_spd3(Bm, Bi);
+          mm3(Bi, Um, XU);
+          mm3(Bi, Lm, XL);
+          double nlo[9], nhi[9], t1[9], t2[9];
+          double alp[9], gam[9], Ln[9], Un[9];
+          cm.template both<9>(Bi, nlo, nhi, h);
+          mm3(Lm, nlo, alp);
+          mm3(Um, nhi, gam);
+          cm.template both<9>(XU, nlo, nhi, h);
+          mm3(Lm, nlo, t1);
+          mm3(Um, nhi, Un);
+          cm.template both<9>(XL, nlo, nhi, h);
+          mm3(Lm, nlo, Ln);
+          mm3(Um, nhi, t2);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) {
+            Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
+            Lm[e] = vlo ? -Ln[e] : 0.0;
+            Um[e] = vhi ? -Un[e] : 0.0;
+            alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
+            gam[e] = vhi ? -gam[e] : 0.0;
+          }
+          if (lev < NLEV - 1) {
+            // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+              sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+              sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+            }
+          } else {
+            // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
+            // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
+            double one[10];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
+            one[9] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sm_pair[(lev * 9 + q) * T] = make_double2(one[2 * q], one[2 * q + 1]);
+          }
+        }
+        {
+          double Bi[9];
+          inv_spd3(Bm, Bi);
+          sm_pair[(NLEV * 9 - 4 + 0) * T] = make_double2(Bi[0], Bi[1]);
+          sm_pair[(NLEV * 9 - 4 + 1) * T] = make_double2(Bi[2], Bi[4]);
+          sm_pair[(NLEV * 9 - 4 + 2) * T] = make_double2(Bi[5], Bi[8]);
+        }
       }
       cm.sync();
     }
@@ -696,6 +913,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
 #pragma unroll
       for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
+      if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
     }
 
     // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
@@ -706,84 +924,163 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       for (int i = 0; i < 3; ++i) sd[i] = s.rd[i] * s.zd[i] - s.yd[i];
 #pragma unroll
       for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
-      double sdn[3];
-      cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
-      if (LASTFULL) {
+      double xt[3], ut[2], ztd[3];
+      [[maybe_unused]] double ztr = 0.0;
+      if constexpr (RATE) {
+        const double sr = s.rr * s.zr - s.yr;   // 0 on stages without an input (rho = 0, y = 0)
+        double sdn[3], srn;
+        {
+          const double snd[4] = {sd[0], sd[1], sd[2], sr};
+          double rcv[4];
+          cm.template dn<4>(snd, rcv, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
-      }
-      double gx[3], gu[2], t3[3], t2[2];
-      At_mul(md, sdn, t3);
-#pragma unroll
-      for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
-        gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
-      Bt_mul(md, sdn, t2);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
-      // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
-      const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
-      double f[3];
-      B_mul(md, hh, f);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) f[i] *= s.rdn[i];
-      double r[3], fp[3];
-      At_mul(md, f, t3);
-      cm.template up<3>(f, fp, 1);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
-      // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
-#pragma unroll
-      for (int lev = 0; lev < NLEV - 1; ++lev) {
-        const int h = 1 << lev;
-        double lo[3], hi[3];
-        cm.template both<3>(r, lo, hi, h);
-        const double2* cf = sm_pair + (lev * 9) * T;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
-          double a = fma(c0.x, lo[0], r[i]);
-          double b = c1.y * hi[0];
-          a = fma(c0.y, lo[1], a);
-          b = fma(c2.x, hi[1], b);
-          a = fma(c1.x, lo[2], a);
-          b = fma(c2.y, hi[2], b);
-          r[i] = a + b;
+          for (int i = 0; i < 3; ++i) sdn[i] = (LASTFULL && !actu) ? 0.0 : rcv[i];
+          srn = rcv[3];
         }
-      }
-      {  // top level: single neighbour k ^ h
-        constexpr int h = 1 << (NLEV - 1);
-        double nb[3];
-        cm.template xr<3>(r, nb, h);
-        const double2* cf = sm_pair + ((NLEV - 1) * 9) * T;
-        const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
-        r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
-        r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
-        r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
-      }
-      double xt[3];
-      {
-        const double2 q0 = sm_pair[(NLEV * 9 - 4 + 0) * T], q1 = sm_pair[(NLEV * 9 - 4 + 1) * T], q2 = sm_pair[(NLEV * 9 - 4 + 2) * T];
-        const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
-        xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
-        xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
-        xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
-      }
-      // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
-      double axt[3], v[3], xn[3];
-      A_mul(md, xt, axt);
-      cm.template dn<3>(xt, xn, 1);
+        double gx[3], t3[3], t2[2];
+        At_mul(md, sdn, t3);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = s.rdn[i] * (axt[i] - xn[i]);
-      Bt_mul(md, v, t2);
-      const double ut[2] = {hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]), hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1])};
-      // z~ = A w~ : dynamics rows need the predecessor's prediction
-      double pred[3], ztd[3], pp[3];
-      B_mul(md, ut, pred);
+        for (int j = 0; j < 3; ++j)
+          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
+        Bt_mul(md, sdn, t2);
+        const double gv = (s.su[0] * s.u[0] - qu[0] + sb[0]) + t2[0];
+        double gd = (s.su[1] * s.u[1] - qu[1] + sb[1] + sr - srn) + t2[1];
+        gd = actu ? gd : 0.0;
+        // eliminate v_k: hv = g_v / w_v, f = R_{k+1} b_v hv
+        const double hv = s.wvi * gv;
+        const double f[3] = {s.mv[0] * hv, s.mv[1] * hv, s.mv[2] * hv};
+        double r[4], fp[3];
+        At_mul(md, f, t3);
+        cm.template up<3>(f, fp, 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) pred[i] += axt[i];
-      cm.template up<3>(pred, pp, 1);
+        for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
+        r[3] = gd - md.b21 * f[2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? pp[i] : 0.0) - xt[i];
+        for (int lev = 0; lev < NLEV; ++lev) {
+          const int h = 1 << lev;
+          double lo[4], hi[4];
+          cm.template both<4>(r, lo, hi, h);
+          const double* cf = sm_r + (lev * 32) * T;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double a = fma(cf[(4 * i) * T], lo[0], r[i]);
+            double b = cf[(16 + 4 * i) * T] * hi[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+              a = fma(cf[(4 * i + j) * T], lo[j], a);
+              b = fma(cf[(16 + 4 * i + j) * T], hi[j], b);
+            }
+            r[i] = a + b;
+          }
+        }
+        double st[4];
+        {
+          const double* cf = sm_r + (NLEV * 32) * T;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double a = cf[(4 * i) * T] * r[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) a = fma(cf[(4 * i + j) * T], r[j], a);
+            st[i] = a;
+          }
+        }
+        xt[0] = st[0]; xt[1] = st[1]; xt[2] = st[2];
+        // recover v~_k = hv - b_v' R_{k+1} (C s~_k - x~_{k+1}) / w_v   (mv = 0 on the last stage)
+        double axt[3], xn[3];
+        A_mul(md, xt, axt);
+        cm.template dn<3>(xt, xn, 1);
+        const double yv[3] = {axt[0] - xn[0], axt[1] - xn[1], axt[2] + md.b21 * st[3] - xn[2]};
+        ut[0] = hv - s.wvi * (s.mv[0] * yv[0] + s.mv[1] * yv[1] + s.mv[2] * yv[2]);
+        ut[1] = st[3];
+        // z~ = A w~
+        double pred[3];
+        B_mul(md, ut, pred);
+        const double snd[4] = {pred[0] + axt[0], pred[1] + axt[1], pred[2] + axt[2], ut[1]};
+        double rcv[4];
+        cm.template up<4>(snd, rcv, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? rcv[i] : 0.0) - xt[i];
+        ztr = ut[1] - (hasp ? rcv[3] : 0.0);
+      } else {
+        double sdn[3];
+        cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
+        if (LASTFULL) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
+        }
+        double gx[3], gu[2], t3[3], t2[2];
+        At_mul(md, sdn, t3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
+          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
+        Bt_mul(md, sdn, t2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
+        // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
+        const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
+        double f[3];
+        B_mul(md, hh, f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f[i] *= s.rdn[i];
+        double r[3], fp[3];
+        At_mul(md, f, t3);
+        cm.template up<3>(f, fp, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
+        // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
+#pragma unroll
+        for (int lev = 0; lev < NLEV - 1; ++lev) {
+          const int h = 1 << lev;
+          double lo[3], hi[3];
+          cm.template both<3>(r, lo, hi, h);
+          const double2* cf = sm_pair + (lev * 9) * T;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
+            double a = fma(c0.x, lo[0], r[i]);
+            double b = c1.y * hi[0];
+            a = fma(c0.y, lo[1], a);
+            b = fma(c2.x, hi[1], b);
+            a = fma(c1.x, lo[2], a);
+            b = fma(c2.y, hi[2], b);
+            r[i] = a + b;
+          }
+        }
+        {  // top level: single neighbour k ^ h
+          constexpr int h = 1 << (NLEV - 1);
+          double nb[3];
+          cm.template xr<3>(r, nb, h);
+          const double2* cf = sm_pair + ((NLEV - 1) * 9) * T;
+          const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
+          r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
+          r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
+          r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
+        }
+        {
+          const double2 q0 = sm_pair[(NLEV * 9 - 4 + 0) * T], q1 = sm_pair[(NLEV * 9 - 4 + 1) * T], q2 = sm_pair[(NLEV * 9 - 4 + 2) * T];
+          const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
+          xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
+          xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
+          xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+        }
+        // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
+        double axt[3], v[3], xn[3];
+        A_mul(md, xt, axt);
+        cm.template dn<3>(xt, xn, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[i] = s.rdn[i] * (axt[i] - xn[i]);
+        Bt_mul(md, v, t2);
+        ut[0] = hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]);
+        ut[1] = hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1]);
+        // z~ = A w~ : dynamics rows need the predecessor's prediction
+        double pred[3], pp[3];
+        B_mul(md, ut, pred);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pred[i] += axt[i];
+        cm.template up<3>(pred, pp, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? pp[i] : 0.0) - xt[i];
+      }
       const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
 #pragma unroll
       for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
@@ -802,9 +1099,15 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         s.yg[r2] += s.rg[r2] * (zr - zn);
         s.zg[r2] = zn;
         const double zrb = al * ut[r2] + oma * s.zb[r2];
-        const double znb = clampd(zrb + s.ib[r2] * s.yb[r2], s.bl[r2], s.bu[r2]);
+        const double znb = clampd(zrb + s.ib[r2] * s.yb[r2], p.u_min[r2], p.u_max[r2]);
         s.yb[r2] += s.rb[r2] * (zrb - znb);
         s.zb[r2] = znb;
+      }
+      if constexpr (RATE) {
+        const double zr = al * ztr + oma * s.zr;
+        const double zn = clampd(zr + s.ir * s.yr, s.rlo, s.rhi);
+        s.yr += s.rr * (zr - zn);
+        s.zr = zn;
       }
     }
     if (!info_iter) { ++iter; continue; }
@@ -815,6 +1118,8 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     const double edv[3] = {scr[(SCR_ED + 0) * T], scr[(SCR_ED + 1) * T], scr[(SCR_ED + 2) * T]};
     const double egv[2] = {scr[(SCR_EG + 0) * T], scr[(SCR_EG + 1) * T]};
     const double ebv[2] = {scr[(SCR_EB + 0) * T], scr[(SCR_EB + 1) * T]};
+    [[maybe_unused]] double erv = 0.0;
+    if constexpr (RATE) erv = scr[SCR_ER * T];
     {
       double ax[3], pred[3], t3[3], t2[2];
       A_mul(md, s.x, ax);
@@ -822,16 +1127,34 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
       double Axd[3], pp[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) pred[i] += ax[i];
-      cm.template up<3>(pred, pp, 1);
+      [[maybe_unused]] double Axr = 0.0, yrn = 0.0;
+      if constexpr (RATE) {
+        const double snd[4] = {pred[0], pred[1], pred[2], s.u[1]};
+        double rcv[4];
+        cm.template up<4>(snd, rcv, 1);
+        pp[0] = rcv[0]; pp[1] = rcv[1]; pp[2] = rcv[2];
+        Axr = s.u[1] - (hasp ? rcv[3] : 0.0);
+      } else {
+        cm.template up<3>(pred, pp, 1);
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) Axd[i] = (hasp ? pp[i] : 0.0) - s.x[i];
       const double Axg[2] = {s.gm[0] * s.x[0] + s.gm[1] * s.x[1] + s.gm[2] * s.x[2], s.gm[3] * s.x[0] + s.gm[4] * s.x[1] + s.gm[5] * s.x[2]};
       double ydn[3];
-      cm.template dn<3>(s.yd, ydn, 1);
+      if constexpr (RATE) {
+        const double snd[4] = {s.yd[0], s.yd[1], s.yd[2], s.yr};
+        double rcv[4];
+        cm.template dn<4>(snd, rcv, 1);
+        ydn[0] = rcv[0]; ydn[1] = rcv[1]; ydn[2] = rcv[2];
+        yrn = (k + 1 < N) ? rcv[3] : 0.0;
+      } else {
+        cm.template dn<3>(s.yd, ydn, 1);
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) ydn[i] = actu ? ydn[i] : 0.0;
       At_mul(md, ydn, t3);
       Bt_mul(md, ydn, t2);
+      if constexpr (RATE) t2[1] += s.yr - yrn;   // A' y on delta_k: +1 in rate row k, -1 in rate row k+1
       const double dxv[3] = {scr[(SCR_DX + 0) * T], scr[(SCR_DX + 1) * T], scr[(SCR_DX + 2) * T]};
       const double duv[2] = {scr[(SCR_DU + 0) * T], scr[(SCR_DU + 1) * T]};
       double m_pri = 0, m_z = 0, m_Ax = 0, m_dua = 0, m_Aty = 0, m_Px = 0;
@@ -877,6 +1200,12 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
           q_dua = dmax(q_dua, duv[j] * dr); q_Aty = dmax(q_Aty, duv[j] * ay); q_Px = dmax(q_Px, duv[j] * px);
           o += 0.5 * s.u[j] * Pxu + qu[j] * s.u[j];
         }
+        if constexpr (RATE) {
+          const double rr = fabs(Axr - s.zr), zz = fabs(s.zr), aa = fabs(Axr);
+          poisoned |= !(rr == rr);
+          m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
+          q_pri = dmax(q_pri, erv * rr); q_z = dmax(q_z, erv * zz); q_Ax = dmax(q_Ax, erv * aa);
+        }
       }
       poisoned = cm.any(poisoned);
       pri_res = cm.rmax(m_pri); n_z = cm.rmax(m_z); n_Ax = cm.rmax(m_Ax);
@@ -910,28 +1239,48 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
             dyb[r] = s.yb[r] - scr[(SCR_PYB + r) * T];
             // upper bound infinite (scaled test): keep the non-positive part, or nothing if the lower is infinite too
             dyg[r] = (egv[r] * s.gl[r] < -INF_THRESH) ? 0.0 : dmin(dyg[r], 0.0);
-            const double lbb = ebv[r] * s.bl[r], ubb = ebv[r] * s.bu[r];
+            const double lbb = ebv[r] * p.u_min[r], ubb = ebv[r] * p.u_max[r];
             if (ubb > INF_THRESH) dyb[r] = (lbb < -INF_THRESH) ? 0.0 : dmin(dyb[r], 0.0);
             else if (lbb < -INF_THRESH) dyb[r] = dmax(dyb[r], 0.0);
           }
           double mx = 0.0, lhs = 0.0;
+          [[maybe_unused]] double dyr = 0.0;
+          if constexpr (RATE) {
+            dyr = s.yr - scr[SCR_PYR * T];
+            const double lbr = erv * s.rlo, ubr = erv * s.rhi;
+            if (ubr > INF_THRESH) dyr = (lbr < -INF_THRESH) ? 0.0 : dmin(dyr, 0.0);
+            else if (lbr < -INF_THRESH) dyr = dmax(dyr, 0.0);
+            dyr = actu ? dyr : 0.0;
+            mx = fabs(dyr);
+            lhs = s.rhi * dmax(dyr, 0.0) + s.rlo * dmin(dyr, 0.0);
+          }
 #pragma unroll
           for (int i = 0; i < 3; ++i) { dyd[i] = act ? dyd[i] : 0.0; mx = dmax(mx, fabs(dyd[i])); lhs += s.bd[i] * dyd[i]; }
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             dyg[r] = act ? dyg[r] : 0.0; dyb[r] = actu ? dyb[r] : 0.0;
             mx = dmax(mx, dmax(fabs(dyg[r]), fabs(dyb[r])));
-            lhs += s.gl[r] * dmin(dyg[r], 0.0) + s.bu[r] * dmax(dyb[r], 0.0) + s.bl[r] * dmin(dyb[r], 0.0);
+            lhs += s.gl[r] * dmin(dyg[r], 0.0) + p.u_max[r] * dmax(dyb[r], 0.0) + p.u_min[r] * dmin(dyb[r], 0.0);
           }
           const double ndy = cm.rmax(mx);  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
           const double lhs_all = cm.rsum(lhs);
           if (c * ndy > epi && lhs_all < -epi * ndy) {
             double dn[3], t3[3], t2[2];
-            cm.template dn<3>(dyd, dn, 1);
+            [[maybe_unused]] double dyrn = 0.0;
+            if constexpr (RATE) {
+              const double snd[4] = {dyd[0], dyd[1], dyd[2], dyr};
+              double rcv[4];
+              cm.template dn<4>(snd, rcv, 1);
+              dn[0] = rcv[0]; dn[1] = rcv[1]; dn[2] = rcv[2];
+              dyrn = (k + 1 < N) ? rcv[3] : 0.0;
+            } else {
+              cm.template dn<3>(dyd, dn, 1);
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) dn[i] = actu ? dn[i] : 0.0;
             At_mul(md, dn, t3);
             Bt_mul(md, dn, t2);
+            if constexpr (RATE) t2[1] += dyr - dyrn;
             double m2 = 0.0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) m2 = dmax(m2, fabs(-dyd[j] + t3[j] + s.gm[j] * dyg[0] + s.gm[3 + j] * dyg[1]));
@@ -965,7 +1314,16 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
 #pragma unroll
             for (int i = 0; i < 3; ++i) pred[i] += ax[i];
             double pp[3];
-            cm.template up<3>(pred, pp, 1);
+            if constexpr (RATE) {
+              const double snd[4] = {pred[0], pred[1], pred[2], ddu[1]};
+              double rcv[4];
+              cm.template up<4>(snd, rcv, 1);
+              pp[0] = rcv[0]; pp[1] = rcv[1]; pp[2] = rcv[2];
+              const double a = ddu[1] - (hasp ? rcv[3] : 0.0);
+              if (actu && ((erv * s.rhi < INF_THRESH && a > th) || (erv * s.rlo > -INF_THRESH && a < -th))) bad = true;
+            } else {
+              cm.template up<3>(pred, pp, 1);
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {  // equality rows: both sides finite
               const double a = (hasp ? pp[i] : 0.0) - ddx[i];
@@ -976,7 +1334,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
               const double a = s.gm[3 * r] * ddx[0] + s.gm[3 * r + 1] * ddx[1] + s.gm[3 * r + 2] * ddx[2];
               if (act && (egv[r] * s.gl[r] > -INF_THRESH && a < -th)) bad = true;   // upper side is infinite
               const double b = ddu[r];
-              if (actu && ((ebv[r] * s.bu[r] < INF_THRESH && b > th) || (ebv[r] * s.bl[r] > -INF_THRESH && b < -th))) bad = true;
+              if (actu && ((ebv[r] * p.u_max[r] < INF_THRESH && b > th) || (ebv[r] * p.u_min[r] > -INF_THRESH && b < -th))) bad = true;
             }
             dinf = !cm.any(bad);
           }
@@ -1032,6 +1390,7 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
     if (actu) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) yo[5 * (N + 1) + 2 * k + j] = has_sol ? s.yb[j] : qnan;
+      if constexpr (RATE) yo[row_r0 + k] = has_sol ? s.yr : qnan;
     }
   }
   if (k == 0) {
@@ -1076,16 +1435,21 @@ __global__ void __launch_bounds__(32 * WPQ, WPQ == 1 ? ADMM_MIN_BLOCKS : 1) admm
         sz_[5 * (N + 1) + 2 * k + j] = has_sol ? e * s.zb[j] : 0.0;
         sy_[5 * (N + 1) + 2 * k + j] = has_sol ? c * s.yb[j] / e : 0.0;
       }
+      if constexpr (RATE) {
+        const double e = scr[SCR_ER * T];
+        sz_[row_r0 + k] = has_sol ? e * s.zr : 0.0;
+        sy_[row_r0 + k] = has_sol ? c * s.yr / e : 0.0;
+      }
     }
     if (k == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
   }
 }
 
-template <int NLEV, int WPQ, bool LASTFULL>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
-  size_t smem = (size_t)(2 * (NLEV * 9 - 1)) * T * sizeof(double);
+  size_t smem = (size_t)(RATE ? NLEV * 32 + 16 : 2 * (NLEV * 9 - 1)) * T * sizeof(double);
   if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
   // TMA staging of the record: base and stride 16-byte aligned, record rounded up to 16 bytes fits inside the stride
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
@@ -1097,10 +1461,10 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     smem += (size_t)p.rec_bulk_bytes + 16;  // + the mbarrier
   }
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  admm_kernel<NLEV, WPQ, LASTFULL><<<p.B, T, smem, stream>>>(p);
+  admm_kernel<NLEV, WPQ, LASTFULL, RATE><<<p.B, T, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -80,6 +80,7 @@ void f110_mpc_default_config(f110_mpc_config* c) {
   c->u_des[0] = 4.5; c->u_des[1] = 0.0;
   c->u_min[0] = (double)3.0f; c->u_min[1] = (double)-0.43f;  // constraints.cpp:20-21
   c->u_max[0] = (double)4.5f; c->u_max[1] = (double)0.43f;   // constraints.cpp:18-19
+  c->rate_rows = 0; c->reserved = 0; c->rate_delta = 0.0;    // the reference has no steering-rate rows
 }
 
 void f110_solver_default_settings(f110_solver_settings* s) {
@@ -95,12 +96,15 @@ void f110_solver_default_settings(f110_solver_settings* s) {
 int f110_mpc_record_doubles(int N) { return 11 + 3 * N; }
 int f110_mpc_num_variables(int N) { return 5 * N + 3; }
 int f110_mpc_num_constraints(int N) { return 7 * N + 5; }
+int f110_mpc_num_rows(const f110_mpc_config* c) { return c ? f110::num_rows(c->horizon, c->rate_rows) : 0; }
 
 int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, int max_batch, int device,
                     f110_mpc_solver** out) {
   if (!cfg || !st || !out || max_batch <= 0) return fail(F110_ERR_ARG, "f110_mpc_create: null argument or max_batch <= 0");
   if (cfg->horizon < 1 || cfg->horizon > F110_MAX_HORIZON) return fail(F110_ERR_ARG, "f110_mpc_create: horizon out of range");
   if (cfg->gap_mode < 0 || cfg->gap_mode > 2) return fail(F110_ERR_ARG, "f110_mpc_create: gap_mode must be 0, 1 or 2");
+  if (cfg->rate_rows && cfg->horizon > 63) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: steering-rate rows need horizon <= 63");
+  if (cfg->rate_rows && !(cfg->rate_delta >= 0.0)) return fail(F110_ERR_ARG, "f110_mpc_create: rate_delta must be >= 0");
   if (st->scaled_termination) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: scaled_termination = 1 is not supported");
   if (st->max_iter < 1 || st->check_termination < 0 || st->scaling < 0) return fail(F110_ERR_ARG, "f110_mpc_create: bad settings");
   int ndev = 0;
@@ -115,7 +119,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   s->max_batch = max_batch;
   s->device = device;
   const int N = cfg->horizon;
-  const size_t ssz = (size_t)max_batch * f110::state_doubles(N) * sizeof(double);
+  const size_t ssz = (size_t)max_batch * f110::state_doubles(N, cfg->rate_rows) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
@@ -145,7 +149,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
 int f110_mpc_reset(f110_mpc_solver* s) {
   if (!s) return fail(F110_ERR_ARG, "f110_mpc_reset: null solver");
   CUDA_TRY(cudaSetDevice(s->device));
-  CUDA_TRY(cudaMemset(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon) * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) * sizeof(double)));
   return F110_OK;
 }
 
@@ -172,6 +176,7 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
   for (int i = 0; i < 2; ++i) { p.R[i] = s->cfg.r[i]; p.u_des[i] = s->cfg.u_des[i]; p.u_min[i] = s->cfg.u_min[i]; p.u_max[i] = s->cfg.u_max[i]; }
   for (int i = 0; i < 2; ++i) p.qu[i] = -1.0 * s->cfg.r[i] * s->cfg.u_des[i];
   p.one_minus_alpha = 1.0 - s->st.alpha;
+  p.rate_rows = s->cfg.rate_rows ? 1 : 0; p.rate_delta = s->cfg.rate_delta;
   p.rho0 = s->st.rho; p.sigma = s->st.sigma; p.alpha = s->st.alpha; p.eps_abs = s->st.eps_abs; p.eps_rel = s->st.eps_rel;
   p.eps_prim_inf = s->st.eps_prim_inf; p.eps_dual_inf = s->st.eps_dual_inf; p.adaptive_rho_tolerance = s->st.adaptive_rho_tolerance;
   p.max_iter = s->st.max_iter; p.check_termination = s->st.check_termination; p.scaling = s->st.scaling;
@@ -192,7 +197,7 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (!s || !recs) return fail(F110_ERR_ARG, "f110_mpc_solve_host: null solver or records");
   if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_host: count exceeds max_batch");
   if (count == 0) return F110_OK;
-  const int N = s->cfg.horizon, n = 5 * N + 3, m = 7 * N + 5;
+  const int N = s->cfg.horizon, n = 5 * N + 3, m = f110::num_rows(N, s->cfg.rate_rows);
   const int rd = f110_mpc_record_doubles(N);
   const int rdp = (rd + 1) & ~1;  // device stride: even, so every record is 16-byte aligned for the kernel's TMA staging
   if (rec_stride < rd) return fail(F110_ERR_ARG, "f110_mpc_solve_host: record stride too small");

@@ -90,10 +90,12 @@ int f110h_best_global_idx(const float* wp_xy, int W, const double* pose7, double
 }
 
 // ---- MPC object -------------------------------------------------------------------------------------------
-void* f110h_mpc_create(int horizon, int gap_mode, int device) {
+void* f110h_mpc_create_rate(int horizon, int gap_mode, double steer_rate_max, int device);
+void* f110h_mpc_create(int horizon, int gap_mode, int device) { return f110h_mpc_create_rate(horizon, gap_mode, 0.0, device); }
+void* f110h_mpc_create_rate(int horizon, int gap_mode, double steer_rate_max, int device) {
   try {
     std::unique_ptr<MpcBox> b(new MpcBox());
-    b->prm.horizon = horizon; b->prm.gap_mode = gap_mode;
+    b->prm.horizon = horizon; b->prm.gap_mode = gap_mode; b->prm.steer_rate_max = steer_rate_max;
     b->mpc.reset(new MPC(b->prm, device));
     return b.release();
   } catch (const std::exception&) {

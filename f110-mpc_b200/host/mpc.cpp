@@ -15,6 +15,7 @@ f110_mpc_config config_from(const f110::Params& prm, const Constraints& con) {
   c.r[0] = prm.r0; c.r[1] = prm.r1;
   c.u_des[0] = prm.des_vel; c.u_des[1] = prm.des_steer;
   for (int j = 0; j < 2; ++j) { c.u_min[j] = con.u_min()(j); c.u_max[j] = con.u_max()(j); }
+  if (prm.steer_rate_max > 0.0) { c.rate_rows = 1; c.rate_delta = prm.steer_rate_max * c.dt; }
   return c;
 }
 
@@ -40,10 +41,11 @@ MPC::MPC(const f110::Params& prm, int device)
   num_states_ = state_size_ * (horizon_ + 1);                                 // mpc.cpp:27
   num_variables_ = num_states_ + num_inputs_;                                 // mpc.cpp:28
   num_constraints_ = num_states_ + 2 * (horizon_ + 1) + num_inputs_;          // mpc.cpp:29: dynamics + gap + input box
+  config_ = config_from(prm, constraints_);
+  num_constraints_ = f110_mpc_num_rows(&config_);                             // + N steering-rate rows when enabled
   QPsolution_.assign(num_variables_, 0.0);
   QPdual_.assign(num_constraints_, 0.0);
   record_.assign(f110_mpc_record_doubles(horizon_), 0.0);
-  config_ = config_from(prm, constraints_);
   f110_solver_default_settings(&settings_);  // OSQP defaults + warm start, the reference's configuration (mpc.cpp:98-99)
   const int rc = f110_mpc_create(&config_, &settings_, 1, device, &solver_);
   if (rc != F110_OK) throw std::runtime_error(std::string("MPC: f110_mpc_create failed: ") + f110_last_error());

@@ -80,6 +80,8 @@ struct Params {
   float lookahead = 2.5f;                  // trajectory.cpp:10
   // gap rows: 0 = as shipped (bounds +-INFTY, mpc.cpp:297-298), 1 = lower bound -l(2) restored
   int gap_mode = 0;
+  // steering-rate rows (not in the reference): |delta_k - delta_{k-1}| <= steer_rate_max * dt, 0 = off
+  double steer_rate_max = 0.0;             // rad/s
 
   // "key: value" lines of a params.yaml-style file override the defaults; unknown keys are ignored.
   static Params FromYaml(const std::string& path);

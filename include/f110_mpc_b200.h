@@ -22,6 +22,10 @@
  * Solution layout = the reference's (mpc.cpp:26-29):
  *     x[5N+3]  = [x_0(3) ... x_N(3) | u_0(2) ... u_{N-1}(2)]
  *     y[7N+5]  = [dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N]
+ * With f110_mpc_config.rate_rows = 1, N steering-rate rows follow the input box (y has 8N+5 entries):
+ *     row k:  delta_k - delta_{k-1} in [-rate_delta, +rate_delta]  (k >= 1);   row 0:  delta_0 - u_lin[1]  likewise.
+ * The reference has no such rows (its relic of an extra input constraint is the commented slip block,
+ * constraints.cpp:23-39, mpc.cpp:250); SURVEY.md section 8f rank 4 asks for them on top of the reference's row set.
  */
 #ifndef F110_MPC_B200_H
 #define F110_MPC_B200_H
@@ -65,6 +69,9 @@ typedef struct f110_mpc_config {
   double u_des[2];   /* des_vel, des_steer      (params.yaml:42-43) */
   double u_min[2];   /* umin, -0.43f            (constraints.cpp:20-21) */
   double u_max[2];   /* umax, +0.43f            (constraints.cpp:18-19) */
+  int32_t rate_rows; /* 0 = the reference's row set; 1 = append N steering-rate rows (horizon <= 63) */
+  int32_t reserved;
+  double rate_delta; /* max steering change per step (rad) = steering-rate limit (rad/s) * dt */
 } f110_mpc_config;
 
 /* The OSQP settings the reference leaves at their defaults (it only sets warm start + verbosity,
@@ -87,6 +94,7 @@ void f110_solver_default_settings(f110_solver_settings* s);
 int f110_mpc_record_doubles(int horizon); /* 11 + 3N */
 int f110_mpc_num_variables(int horizon);  /* 5N + 3  (mpc.cpp:26-28) */
 int f110_mpc_num_constraints(int horizon);/* 7N + 5  (mpc.cpp:29) */
+int f110_mpc_num_rows(const f110_mpc_config* cfg); /* 7N + 5, + N with rate_rows: length of one dual vector */
 const char* f110_last_error(void);
 int f110_device_count(void);
 

@@ -401,6 +401,12 @@ struct MpcConfig {
   double u_max[2] = {(double)4.5f, (double)0.43f};
   int gap_mode = 0;  // 0: as shipped, gap bounds (-INFTY, +INFTY) (mpc.cpp:297-298); 1: lower = -l(2) (the commented code);
                      // 2: like 1 but the stage-0 pair (all-ones rows, not half-planes — SURVEY fact 3) stays loose
+  // Steering-rate rows.  NOT in the reference (its only relic of an extra input constraint is the
+  // commented slip block, constraints.cpp:23-39, mpc.cpp:250): N rows appended after the input box,
+  //   row k:  delta_k - delta_{k-1}  in [-rate_delta, +rate_delta]   (k >= 1)
+  //   row 0:  delta_0                in [steer_prev - rate_delta, steer_prev + rate_delta],  steer_prev = u_lin[1]
+  int rate_rows = 0;
+  double rate_delta = 0.0;   // max steering change per step (rad)
 };
 
 struct QpData {
@@ -416,7 +422,7 @@ struct QpData {
 // Create{Lower,Upper}Bound (mpc.cpp:26-47, 208-219, 231-254, 275-291).
 inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
   const int N = cfg.N, ns = 3 * (N + 1), nu = 2 * N;
-  d->N = N; d->n = ns + nu; d->m = ns + 2 * (N + 1) + nu;
+  d->N = N; d->n = ns + nu; d->m = ns + 2 * (N + 1) + nu + (cfg.rate_rows ? N : 0);
   const int n = d->n, m = d->m;
   struct T { int r, c; double v; int tag; };
   // Hessian: dense diagonal blocks (upper triangle kept, OsqpEigen passes triu to OSQP)
@@ -450,6 +456,12 @@ inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
     for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) ta.push_back({ns + 2 * k + r, 3 * k + c, 1.0, 200000 + (k - 1) * 6 + r * 3 + c});                        // :249
   }
   for (int r = 0; r < nu; ++r) ta.push_back({ns + 2 * (N + 1) + r, ns + r, 1.0, 0});           // :253
+  const int rate0 = ns + 2 * (N + 1) + nu;   // first steering-rate row
+  if (cfg.rate_rows)
+    for (int k = 0; k < N; ++k) {
+      ta.push_back({rate0 + k, ns + 2 * k + 1, 1.0, 0});
+      if (k > 0) ta.push_back({rate0 + k, ns + 2 * (k - 1) + 1, -1.0, 0});
+    }
   std::vector<int> where;
   to_csc(ta, m, n, &d->A, &where);
   d->posA.assign(9 * N, -1); d->posB.assign(6 * N, -1); d->posG.assign(6 * N, -1);
@@ -469,7 +481,9 @@ inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
     d->l[ns + 2 * (N + 1) + 2 * k + r] = cfg.u_min[r];
     d->u[ns + 2 * (N + 1) + 2 * k + r] = cfg.u_max[r];
   }
-  // KKT ordering, stage by stage: [dyn rows k | x_k | gap rows k | u_k | box rows k]
+  if (cfg.rate_rows)
+    for (int k = 0; k < N; ++k) { d->l[rate0 + k] = -cfg.rate_delta; d->u[rate0 + k] = cfg.rate_delta; }
+  // KKT ordering, stage by stage: [dyn rows k | x_k | gap rows k | u_k | box rows k | rate row k]
   d->perm.clear();
   for (int k = 0; k <= N; ++k) {
     for (int r = 0; r < 3; ++r) d->perm.push_back(n + 3 * k + r);
@@ -478,6 +492,7 @@ inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
     if (k < N) {
       for (int r = 0; r < 2; ++r) d->perm.push_back(ns + 2 * k + r);
       for (int r = 0; r < 2; ++r) d->perm.push_back(n + ns + 2 * (N + 1) + 2 * k + r);
+      if (cfg.rate_rows) d->perm.push_back(n + rate0 + k);
     }
   }
 }
@@ -507,6 +522,11 @@ inline void qp_fill_values(const MpcConfig& cfg, const double* rec, QpData* d) {
     const bool on = cfg.gap_mode == 1 || (cfg.gap_mode == 2 && k > 0);
     d->l[ns + 2 * k + 0] = on ? -l1[2] : -osqp_restated::OSQP_INFTY;  // :297
     d->l[ns + 2 * k + 1] = on ? -l2[2] : -osqp_restated::OSQP_INFTY;  // :298
+  }
+  if (cfg.rate_rows) {  // row 0 is measured from the steering applied last cycle
+    const int rate0 = ns + 2 * (N + 1) + 2 * N;
+    d->l[rate0] = ulin[1] - cfg.rate_delta;
+    d->u[rate0] = ulin[1] + cfg.rate_delta;
   }
 }
 

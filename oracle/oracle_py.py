@@ -73,12 +73,20 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
 
 
-def default_cfg(N=30, gap_mode=0):
-    c = np.zeros(14)
+def default_cfg(N=30, gap_mode=0, rate_delta=None):
+    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; None = the reference's row set."""
+    c = np.zeros(16)
     lib().orc_default_cfg(_dp(c))
     c[0] = N
     c[13] = gap_mode
+    if rate_delta is not None:
+        c[14], c[15] = 1, rate_delta
     return c
+
+
+def mpc_rows(cfg):
+    N = int(cfg[0])
+    return 7 * N + 5 + (N if len(cfg) > 14 and cfg[14] else 0)
 
 
 def default_settings(**kw):
@@ -103,7 +111,7 @@ class MpcBatch:
         self.cfg = np.ascontiguousarray(cfg, dtype=np.float64)
         self.settings = np.ascontiguousarray(settings, dtype=np.float64)
         self.N = int(cfg[0])
-        self.n, self.m = 5 * self.N + 3, 7 * self.N + 5
+        self.n, self.m = 5 * self.N + 3, mpc_rows(self.cfg)
         self.B = B
         self.h = lib().orc_mpc_create(_dp(self.cfg), _dp(self.settings), B, nthreads)
         self.threads = lib().orc_mpc_threads(self.h)
@@ -158,7 +166,7 @@ def osqp_dense(P, q, A, l, u, settings=None):
 
 def mpc_assemble_dense(cfg, rec):
     N = int(cfg[0])
-    n, m = 5 * N + 3, 7 * N + 5
+    n, m = 5 * N + 3, mpc_rows(cfg)
     P, q, A, l, u = np.zeros((n, n)), np.zeros(n), np.zeros((m, n)), np.zeros(m), np.zeros(m)
     cfg = np.ascontiguousarray(cfg, dtype=np.float64)
     rec = np.ascontiguousarray(rec, dtype=np.float64)

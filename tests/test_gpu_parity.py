@@ -16,7 +16,7 @@ TOL_ABS = TOL_REL = 1e-4
 
 def assert_solution_parity(g, o, N):
     np.testing.assert_array_equal(g["status"], o["status"])
-    ok = o["status"] > 0
+    ok = ~np.isin(o["status"], [3, 4, -3, -4, -7])   # OSQP returns its last iterate unless the problem is infeasible / non-convex
     np.testing.assert_allclose(g["x"][ok], o["x"][ok], atol=TOL_ABS, rtol=TOL_REL)
     np.testing.assert_allclose(g["y"][ok], o["y"][ok], atol=TOL_ABS, rtol=TOL_REL)
     assert np.isnan(g["x"][~ok]).all() and np.isnan(g["y"][~ok]).all()     # OSQP NaN-fills infeasible solutions

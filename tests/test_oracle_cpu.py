@@ -222,3 +222,49 @@ def test_cpp_restatement_vs_independent_numpy_osqp(oracle, workloads, N, eps):
         np.testing.assert_allclose(r["x"][b], o["x"], atol=1e-7, rtol=1e-7)
         np.testing.assert_allclose(r["y"][b], o["y"], atol=1e-5, rtol=1e-6)
         assert abs(r["rho"][b] - o["rho"]) <= 1e-6 * o["rho"]
+
+
+# ---- steering-rate rows (not in the reference) ------------------------------------------------
+def test_rate_rows_structure(oracle, workloads):
+    N, D = 12, 0.02
+    rec = workloads.tracking_batch(1, N, seed=1)[0]
+    cfg0, cfg1 = oracle.default_cfg(N), oracle.default_cfg(N, 0, rate_delta=D)
+    P0, q0, A0, l0, u0 = oracle.mpc_assemble_dense(cfg0, rec)
+    P1, q1, A1, l1, u1 = oracle.mpc_assemble_dense(cfg1, rec)
+    m0 = 7 * N + 5
+    assert A1.shape == (8 * N + 5, 5 * N + 3) and oracle.mpc_rows(cfg1) == 8 * N + 5
+    np.testing.assert_array_equal(A1[:m0], A0); np.testing.assert_array_equal(P1, P0); np.testing.assert_array_equal(q1, q0)
+    np.testing.assert_array_equal(l1[:m0], l0); np.testing.assert_array_equal(u1[:m0], u0)
+    S = np.zeros((N, 5 * N + 3))                      # row k: +delta_k - delta_{k-1}
+    for k in range(N):
+        S[k, 3 * (N + 1) + 2 * k + 1] = 1.0
+        if k:
+            S[k, 3 * (N + 1) + 2 * (k - 1) + 1] = -1.0
+    np.testing.assert_array_equal(A1[m0:], S)
+    np.testing.assert_array_equal(l1[m0 + 1:], -D); np.testing.assert_array_equal(u1[m0 + 1:], D)
+    assert l1[m0] == rec[4] - D and u1[m0] == rec[4] + D     # row 0 is measured from the steering applied last cycle
+    nnzP, nnzA, nnzL = oracle.mpc_nnz(cfg1)
+    assert nnzA == 26 * N + 9 + 2 * N - 1
+
+
+@pytest.mark.parametrize("N,eps", [(5, 1e-4), (30, 1e-3), (30, 1e-5)])
+def test_rate_rows_oracle_vs_numpy_osqp_and_kkt(oracle, workloads, N, eps):
+    from osqp_numpy import solve
+    B, D = 4, 0.01
+    recs = workloads.tracking_batch(B, N, seed=950 + N)
+    cfg = oracle.default_cfg(N, 0, rate_delta=D)
+    r = oracle.MpcBatch(cfg, oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B, 1).solve(recs)
+    for b in range(B):
+        P, q, A, l, u = oracle.mpc_assemble_dense(cfg, recs[b])
+        o = solve(P, q, A, l, u, eps_abs=eps, eps_rel=eps)
+        assert o["status"] == r["status"][b] == 1
+        assert o["iters"] == r["iters"][b] and o["rho_updates"] == r["rho_updates"][b]
+        np.testing.assert_allclose(r["x"][b], o["x"], atol=1e-7, rtol=1e-7)
+        np.testing.assert_allclose(r["y"][b], o["y"], atol=1e-5, rtol=1e-6)
+    if eps <= 1e-5:
+        for b in range(B):
+            P, q, A, l, u = oracle.mpc_assemble_dense(cfg, recs[b])
+            stat, prim, comp = kkt_residuals(P, q, A, l, u, r["x"][b], r["y"][b])
+            assert stat < 1e-3 and prim < 1e-4
+            steer = r["x"][b][3 * (N + 1) + 1::2]
+            assert np.abs(np.diff(np.concatenate([[recs[b, 4]], steer]))).max() <= D + 1e-4
