@@ -380,9 +380,9 @@ def run_configs(args):
     report = {"gpu": torch.cuda.get_device_name(0), "host_threads": os.cpu_count(),
               "note": "CPU numbers: oracle/ (OSQP-algorithm restatement, not the OSQP binary). Parity UNPINNED by the reference."}
 
-    def gpu_batch_time(N, recs, gap_mode=0, reps=10, **st):
+    def gpu_batch_time(N, recs, gap_mode=0, reps=10, rate_delta=None, **st):
         B = recs.shape[0]
-        sol = M.MpcSolver(M.default_config(N, gap_mode), M.default_settings(warm_start=0, **st), max_batch=B)
+        sol = M.MpcSolver(M.default_config(N, gap_mode, rate_delta), M.default_settings(warm_start=0, **st), max_batch=B)
         r = torch.from_numpy(np.ascontiguousarray(recs)).to(dev)
         u0 = torch.empty(B, 2, dtype=torch.float64, device=dev); stt = torch.empty(B, dtype=torch.int32, device=dev)
         it = torch.empty(B, dtype=torch.int32, device=dev); ru = torch.empty(B, dtype=torch.int32, device=dev)
@@ -398,8 +398,8 @@ def run_configs(args):
         return dict(ms=ms, solves_per_s=B / (ms * 1e-3), status=stt.cpu().numpy(), iters=it.cpu().numpy(), rho_updates=ru.cpu().numpy(),
                     u0=u0.cpu().numpy())
 
-    def cpu_batch(N, recs, gap_mode=0, **st):
-        mb = O.MpcBatch(O.default_cfg(N, gap_mode), O.default_settings(warm_start=0, **st), recs.shape[0])
+    def cpu_batch(N, recs, gap_mode=0, rate_delta=None, **st):
+        mb = O.MpcBatch(O.default_cfg(N, gap_mode, rate_delta), O.default_settings(warm_start=0, **st), recs.shape[0])
         mb.solve(recs[: min(256, len(recs))], want_xy=False)
         r = mb.solve(recs, want_xy=True)
         return r, mb.threads
@@ -545,6 +545,18 @@ def run_configs(args):
                           "algorithmic_tflops": fl / (g["ms"] * 1e-3) / 1e12, "fp64_roofline_frac": fl / (g["ms"] * 1e-3) / 1e12 / peak,
                           "parity": parity(g, o, N)}
     report["config5_horizon_sweep"] = c5
+
+    # ---- steering-rate rows (not in the reference): 4x4-block variant of the kernel --------------------------
+    rd = 3.2 * float(np.float32(0.01))      # 3.2 rad/s servo limit (f1tenth simulator's max_steering_vel) x dt
+    rr = {"rate_delta_rad_per_step": rd}
+    for N in (30, 50):
+        recs6 = W.tracking_batch(B5, N, seed=20240907)
+        g = gpu_batch_time(N, recs6, rate_delta=rd)
+        o, thr = cpu_batch(N, recs6, rate_delta=rd)
+        rr["N=%d" % N] = {"qps": B5, "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B5 / o["seconds"],
+                          "cpu_threads": thr, "speedup_vs_host": g["solves_per_s"] / (B5 / o["seconds"]), "mean_iters": float(g["iters"].mean()),
+                          "parity": parity(g, o, N)}
+    report["steering_rate_rows"] = rr
 
     # ---- device-resident cycle: scan + pose in, control out, one QP per car ----------------------------
     Sc = 4096 if not args.quick else 256
