@@ -239,3 +239,48 @@ def test_collision_check_edges(pkg, oracle):
             np.testing.assert_array_equal(free[s], f)
             np.testing.assert_array_equal(endw[s].view(np.uint32), e.view(np.uint32))
         assert valid[0, 0] == 1 and valid[1].sum() == 0
+
+
+SETTINGS_VARIANTS = [
+    dict(scaling=0), dict(scaling=3), dict(adaptive_rho=0), dict(adaptive_rho_interval=50), dict(adaptive_rho_tolerance=2.0),
+    dict(check_termination=10), dict(check_termination=0, max_iter=120), dict(max_iter=30), dict(max_iter=1),
+    dict(alpha=1.0), dict(alpha=1.8), dict(rho=1.0), dict(rho=1e-3, sigma=1e-4), dict(eps_abs=1e-5, eps_rel=0.0),
+]
+
+
+@pytest.mark.parametrize("rate", [False, True])
+@pytest.mark.parametrize("variant", range(len(SETTINGS_VARIANTS)))
+def test_settings_variants_match_oracle(pkg, oracle, workloads, variant, rate):
+    # every OSQP knob the ABI exports (the reference leaves them at their defaults, mpc.cpp:98-99), on both kernel variants
+    N, B = 20, 64
+    kw = dict(eps_abs=1e-4, eps_rel=1e-4, warm_start=0)
+    kw.update(SETTINGS_VARIANTS[variant])
+    recs = workloads.tracking_batch(B, N, seed=400 + variant, gaps=True)
+    rd = 0.02 if rate else None
+    g = pkg.MpcSolver(pkg.default_config(N, 2, rate_delta=rd), pkg.default_settings(**kw), B).solve_host(recs)
+    o = oracle.MpcBatch(oracle.default_cfg(N, 2, rate_delta=rd), oracle.default_settings(**kw), B).solve(recs)
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])
+
+
+@pytest.mark.parametrize("rate", [False, True])
+def test_problem_family_variants_match_oracle(pkg, oracle, workloads, rate):
+    # weights, limits, set-points and dt other than params.yaml's
+    N, B, eps = 24, 64, 1e-4
+    recs = workloads.tracking_batch(B, N, seed=17)
+    rd = 0.015 if rate else None
+    c = pkg.default_config(N, 0, rate_delta=rd)
+    oc = oracle.default_cfg(N, 0, rate_delta=rd)
+    c.dt = oc[1] = 0.02
+    for j, v in enumerate((3.0, 7.0, 0.5)):
+        c.q[j] = oc[2 + j] = v
+    for j, v in enumerate((1.0, 0.7)):
+        c.r[j] = oc[5 + j] = v
+    for j, (d, lo, hi) in enumerate(((3.0, 1.0, 6.0), (0.05, -0.3, 0.35))):
+        c.u_des[j] = oc[7 + j] = d
+        c.u_min[j] = oc[9 + j] = lo
+        c.u_max[j] = oc[11 + j] = hi
+    g = pkg.MpcSolver(c, pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    o = oracle.MpcBatch(oc, oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
+    assert_solution_parity(g, o, N)
+    np.testing.assert_array_equal(g["iters"], o["iters"])
