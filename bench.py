@@ -354,7 +354,7 @@ def main_product(args):
             "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(wl),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": "f110_cycle_host (qp_mode 2): scans + poses in, %d kernels, controls out; %d QPs per step" % (e2e_launches, NQ)},
+                    "call": "f110_cycle_host (qp_mode 2): scans + poses in, %d kernels (5 per chunk of scenes, chunks pipelined over two streams), controls out; %d QPs per step" % (e2e_launches, NQ)},
             "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "latency_us": {"what": "B=1 f110_mpc_solve_host, warm start, sequential", "p50": float(np.percentile(lat, 50)),
                            "p90": float(np.percentile(lat, 90)), "p99": float(np.percentile(lat, 99))},

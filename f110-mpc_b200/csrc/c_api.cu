@@ -1,6 +1,7 @@
 // C ABI (include/f110_mpc_b200.h) over the CUDA kernels.  No CPU fallback: every compute entry needs a
 // CUDA device and fails with F110_ERR_CUDA otherwise.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -57,6 +58,9 @@ struct f110_mpc_solver {
     }
   } cyc;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
   cudaStream_t stream = nullptr;
+  // f110_cycle_host pipelines its scenes in chunks over two streams (copies of chunk c+1 under the kernels of chunk c)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
 };
 
 extern "C" {
@@ -143,6 +147,9 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   if (s->cyc_pin) cudaFreeHost(s->cyc_pin);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
+  if (s->ev_tab) cudaEventDestroy(s->ev_tab);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   delete s;
 }
 
@@ -161,13 +168,15 @@ int f110_mpc_set_packed_output(f110_mpc_solver* s, double* d_packed) {
   return F110_OK;
 }
 
-int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
-                          double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
-                          void* cuda_stream) {
+}  // extern "C"
+
+// Solve `count` QPs that occupy warm-start / scratch slots slot0 .. slot0 + count - 1 of the handle.
+static int solve_device_range(f110_mpc_solver* s, int slot0, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
+                              double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
+                              void* cuda_stream) {
   if (!s || !d_recs) return fail(F110_ERR_ARG, "f110_mpc_solve_device: null solver or records");
-  if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_device: count exceeds max_batch");
+  if (count < 0 || slot0 < 0 || slot0 + count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_device: count exceeds max_batch");
   if (rec_stride < f110_mpc_record_doubles(s->cfg.horizon)) return fail(F110_ERR_ARG, "f110_mpc_solve_device: record stride too small");
-  s->last_launches = 0;
   if (count == 0) return F110_OK;
   f110::KParams p;
   p.N = s->cfg.horizon; p.B = count; p.stride = rec_stride; p.gap_mode = s->cfg.gap_mode;
@@ -184,12 +193,24 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
   p.recs = d_recs; p.x_out = d_x; p.y_out = d_y; p.u0_out = d_u0; p.status = d_status; p.iters = d_iters;
   p.rho_updates = d_rho_updates; p.info = d_info; p.packed = s->d_packed_next;
   s->d_packed_next = nullptr;
-  p.state = s->st.warm_start ? s->d_state : nullptr;
-  p.scratch = s->d_scratch;
+  const int T = s->cfg.horizon < 32 ? 32 : (s->cfg.horizon < 64 ? 64 : 128);   // threads (stage slots) per QP
+  p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) : nullptr;
+  p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
   CUDA_TRY(cudaSetDevice(s->device));
-  cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &s->last_launches);
+  int launched = 0;
+  cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &launched);
   if (e != cudaSuccess) return cuda_fail(e, "admm kernel launch");
+  s->last_launches += launched;
   return F110_OK;
+}
+
+extern "C" {
+
+int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
+                          double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
+                          void* cuda_stream) {
+  if (s) s->last_launches = 0;
+  return solve_device_range(s, 0, count, d_recs, rec_stride, d_x, d_y, d_u0, d_status, d_iters, d_rho_updates, d_info, cuda_stream);
 }
 
 int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int rec_stride, double* x, double* y, double* u0,
@@ -265,10 +286,10 @@ void f110_cycle_default_config(f110_cycle_config* c) {
   c->v_lin = 4.5;
 }
 
-int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* d_pose7, const float* d_ranges,
-                      const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy, int n_wp,
-                      double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid, void* cuda_stream) {
-  if (!s || !cc || !d_pose7 || !d_ranges || !d_table_xy || !d_wp_xy || !d_chosen) return fail(F110_ERR_ARG, "f110_cycle_device: null argument");
+}  // extern "C"
+
+// Argument checks + (re)allocation of the per-scene device scratch shared by f110_cycle_device / f110_cycle_host.
+static int cycle_prepare(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, int paths, int samples, int n_wp, const double* d_table_xy) {
   if (cc->qp_mode < 0 || cc->qp_mode > 2) return fail(F110_ERR_ARG, "f110_cycle_device: bad qp_mode");
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (scenes < 0 || nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: QP count exceeds max_batch");
@@ -277,8 +298,6 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
     return fail(F110_ERR_UNSUPPORTED, "f110_cycle_device: more than 8 dilation stamps per axis");
   if (n_wp > 1500) return fail(F110_ERR_UNSUPPORTED, "f110_cycle_device: more than 1500 raceline waypoints (shared-memory staging)");
   if (reinterpret_cast<uintptr_t>(d_table_xy) % 16) return fail(F110_ERR_ARG, "f110_cycle_device: table_xy must be 16-byte aligned");
-  s->last_launches = 0;
-  if (scenes == 0) return F110_OK;
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (int)(cc->occ_size / cc->occ_discrete);           // occupancy_grid.cpp:9
   const int N = s->cfg.horizon, rd = (f110_mpc_record_doubles(N) + 1) & ~1;  // even stride: records stay 16-byte aligned (TMA staging)
@@ -300,24 +319,57 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
     CUDA_TRY(cudaMalloc(&c.best_global, B * sizeof(int32_t)));
     c.blocks = blocks; c.paths = paths;
   }
-  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return F110_OK;
+}
+
+// The 5 kernels of one cycle for scenes scene0 .. scene0 + scenes - 1.  The caller's pointers are already offset to scene0; the
+// handle's per-scene scratch and the solver's warm-start slots are offset here, so ranges of one batch can run on different streams.
+static int cycle_device_range(f110_mpc_solver* s, const f110_cycle_config* cc, int scene0, int scenes, const double* d_pose7,
+                              const float* d_ranges, const double* d_prev_steer, const double* d_table_xy, int paths, int samples,
+                              const float* d_wp_xy, int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen,
+                              uint8_t* d_valid, cudaStream_t st) {
+  if (scenes == 0) return F110_OK;
+  const int blocks = (int)(cc->occ_size / cc->occ_discrete);
+  const int N = s->cfg.horizon, rd = (f110_mpc_record_doubles(N) + 1) & ~1;
+  const size_t s0 = (size_t)scene0;
+  const size_t q0 = cc->qp_mode == 0 ? s0 : s0 * paths;                 // first QP slot of the range
+  const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
+  auto& c = s->cyc;
+  float* grid = c.grid + s0 * blocks * blocks;
+  float* offset = c.offset + s0 * 2;
+  float* endw = c.endw + s0 * paths * 2;
+  double* rot = c.rot + s0 * 4;
+  double* pose_xy = c.pose_xy + s0 * 2;
+  double* l1l2 = cc->use_half_spaces ? c.l1l2 + s0 * 6 : nullptr;
+  double* recs = c.recs + q0 * rd;
   // beam count from the float expression of occupancy_grid.cpp:66 / constraints.cpp:118
   const int num_scans = (int)((cc->angle_max - cc->angle_min) / cc->angle_increment + 1);
-  uint8_t* valid = d_valid ? d_valid : c.valid;
+  uint8_t* valid = d_valid ? d_valid : c.valid + s0 * paths;
   cudaError_t e = f110::launch_scene_prep(scenes, blocks, cc->occ_discrete, cc->occ_dilation, cc->n_beams, num_scans, cc->angle_min,
-                                          cc->angle_increment, cc->follow_gap_thresh, cc->fov_divider, cc->buffer, d_pose7, d_ranges, c.grid,
-                                          c.offset, c.rot, c.pose_xy, cc->use_half_spaces ? c.l1l2 : nullptr, c.gap, st);
-  if (e == cudaSuccess) e = f110::launch_collision(scenes, paths, samples, blocks, cc->occ_discrete, c.grid, c.offset, c.rot, c.pose_xy,
-                                                   d_table_xy, valid, c.free_cnt, c.endw, st);
-  int launches = 2;
-  if (e == cudaSuccess) e = f110::launch_select(scenes, paths, n_wp, cc->lookahead, d_pose7, d_wp_xy, valid, c.endw, d_chosen, c.best_global, st);
-  if (e == cudaSuccess) e = f110::launch_build_records(scenes, paths, samples, N, rd, cc->qp_mode, cc->v_lin, d_pose7, c.rot, valid, d_chosen,
-                                                       d_table_xy, d_prev_steer, cc->use_half_spaces ? c.l1l2 : nullptr, c.recs, st);
-  launches += 2;
+                                          cc->angle_increment, cc->follow_gap_thresh, cc->fov_divider, cc->buffer, d_pose7, d_ranges, grid,
+                                          offset, rot, pose_xy, l1l2, c.gap + s0 * 2, st);
+  if (e == cudaSuccess) e = f110::launch_collision(scenes, paths, samples, blocks, cc->occ_discrete, grid, offset, rot, pose_xy,
+                                                   d_table_xy, valid, c.free_cnt + s0 * paths, endw, st);
+  if (e == cudaSuccess) e = f110::launch_select(scenes, paths, n_wp, cc->lookahead, d_pose7, d_wp_xy, valid, endw, d_chosen, c.best_global + s0, st);
+  if (e == cudaSuccess) e = f110::launch_build_records(scenes, paths, samples, N, rd, cc->qp_mode, cc->v_lin, d_pose7, rot, valid, d_chosen,
+                                                       d_table_xy, d_prev_steer, l1l2, recs, st);
   if (e != cudaSuccess) return cuda_fail(e, "f110_cycle_device: kernel launch");
-  const int rc = f110_mpc_solve_device(s, (int)nqp, c.recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
-  s->last_launches += launches;
+  const int rc = solve_device_range(s, (int)q0, (int)nqp, recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
+  s->last_launches += 4;
   return rc;
+}
+
+extern "C" {
+
+int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* d_pose7, const float* d_ranges,
+                      const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy, int n_wp,
+                      double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid, void* cuda_stream) {
+  if (!s || !cc || !d_pose7 || !d_ranges || !d_table_xy || !d_wp_xy || !d_chosen) return fail(F110_ERR_ARG, "f110_cycle_device: null argument");
+  const int rc = cycle_prepare(s, cc, scenes, paths, samples, n_wp, d_table_xy);
+  if (rc != F110_OK) return rc;
+  s->last_launches = 0;
+  return cycle_device_range(s, cc, 0, scenes, d_pose7, d_ranges, d_prev_steer, d_table_xy, paths, samples, d_wp_xy, n_wp, d_u0, d_status,
+                            d_iters, d_chosen, d_valid, (cudaStream_t)cuda_stream);
 }
 
 int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
@@ -357,9 +409,11 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
   float* d_wp = (float*)q; q += b_wp;
   unsigned char* d_out = q;
   cudaStream_t st = s->stream;
-  CUDA_TRY(cudaMemcpyAsync(d_pose, pose7, (size_t)scenes * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_rng, ranges, (size_t)scenes * cc->n_beams * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (prev_steer) CUDA_TRY(cudaMemcpyAsync(d_prev, prev_steer, (size_t)scenes * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (!s->stream2) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_tab, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  }
   // FNV-1a over the constant tables (20 KB): cheaper than two more copies per cycle
   unsigned long long h = 1469598103934665603ull;
   auto mix = [&h](const void* ptr, size_t n) {
@@ -373,10 +427,34 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
     CUDA_TRY(cudaMemcpyAsync(d_wp, wp_xy, n_wpb, cudaMemcpyHostToDevice, st));
     s->cyc_tab_hash = h;
   }
-  const int rc = f110_cycle_device(s, cc, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp,
-                                   (double*)(d_out + o_u0), (int32_t*)(d_out + o_st), (int32_t*)(d_out + o_it), (int32_t*)(d_out + o_ch),
-                                   d_out + o_val, st);
+  int rc = cycle_prepare(s, cc, scenes, paths, samples, n_wp, d_tab);
   if (rc != F110_OK) return rc;
+  // Scenes are independent, so a large batch is pipelined as two halves over two streams: the copies and the small kernels of the
+  // second half run under the solve of the first, and the second solve fills the first one's tail.  Measured at 205 scenes x 20
+  // QPs: 1 / 2 / 4 / 8 chunks = 525 / 503 / 555 / 731 us per call — the solve kernel owns every register file while it runs, so
+  // finer chunks only add tails and launches.  F110_CYCLE_CHUNKS overrides (tuning).
+  int chunks = scenes >= 64 ? 2 : 1;
+  if (const char* ev = std::getenv("F110_CYCLE_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) chunks = v < scenes ? v : scenes; }
+  CUDA_TRY(cudaEventRecord(s->ev_tab, st));
+  CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->ev_tab, 0));   // stream2 needs the tables and must not overtake the previous call
+  s->last_launches = 0;
+  for (int ch = 0; ch < chunks; ++ch) {
+    const int a = (int)((long long)scenes * ch / chunks), b = (int)((long long)scenes * (ch + 1) / chunks);
+    const size_t q0 = cc->qp_mode == 0 ? (size_t)a : (size_t)a * paths;
+    cudaStream_t cs = (ch & 1) ? s->stream2 : st;
+    CUDA_TRY(cudaMemcpyAsync(d_pose + (size_t)a * 7, pose7 + (size_t)a * 7, (size_t)(b - a) * 7 * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_rng + (size_t)a * cc->n_beams, ranges + (size_t)a * cc->n_beams, (size_t)(b - a) * cc->n_beams * sizeof(float),
+                             cudaMemcpyHostToDevice, cs));
+    if (prev_steer) CUDA_TRY(cudaMemcpyAsync(d_prev + a, prev_steer + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    rc = cycle_device_range(s, cc, a, b - a, d_pose + (size_t)a * 7, d_rng + (size_t)a * cc->n_beams, prev_steer ? d_prev + a : nullptr, d_tab,
+                            paths, samples, d_wp, n_wp, (double*)(d_out + o_u0) + 2 * q0, (int32_t*)(d_out + o_st) + q0,
+                            (int32_t*)(d_out + o_it) + q0, (int32_t*)(d_out + o_ch) + a, d_out + o_val + (size_t)a * paths, cs);
+    if (rc != F110_OK) { cudaStreamSynchronize(st); cudaStreamSynchronize(s->stream2); return rc; }
+  }
+  if (chunks > 1) {
+    CUDA_TRY(cudaEventRecord(s->ev_join, s->stream2));
+    CUDA_TRY(cudaStreamWaitEvent(st, s->ev_join, 0));
+  }
   CUDA_TRY(cudaMemcpyAsync(s->cyc_pin, d_out, b_out, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   const unsigned char* ho = s->cyc_pin;
