@@ -349,6 +349,7 @@ static_assert(SCR_ROWS <= SCR_ROWS_ALLOC, "scratch line too short");
 // One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
 // NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == 32 WPQ): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
+// (255 registers / 8 warps per SM is the measured optimum: capping at 224 for 9 warps costs 17 % in spills)
 template <int NLEV, int WPQ, bool LASTFULL, bool RATE>
 __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];

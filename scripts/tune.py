@@ -11,7 +11,8 @@ dev = torch.device("cuda:0")
 kw = dict(warm_start=0)
 if os.environ.get("TUNE_FIXED"):      # fixed work per QP: exactly 50 iterations, one final check (for what-if experiments)
     kw.update(max_iter=50, check_termination=0, adaptive_rho=0)
-sol = M.MpcSolver(M.default_config(N), M.default_settings(**kw), max_batch=B)
+RATE = float(os.environ["TUNE_RATE"]) if os.environ.get("TUNE_RATE") else None   # steering-rate rows: max step (rad)
+sol = M.MpcSolver(M.default_config(N, 0, rate_delta=RATE), M.default_settings(**kw), max_batch=B)
 r = torch.from_numpy(recs).to(dev)
 u0 = torch.empty(B, 2, dtype=torch.float64, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
 s = torch.cuda.current_stream().cuda_stream
