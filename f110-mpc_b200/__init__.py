@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("F110_LIB", os.path.join(_HERE, "libf110mpc_b200.so"))
 
 HOST_LIB_PATH = os.path.join(_HERE, "libf110mpc_host.so")
 
-SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED = 1, 2, -2
+SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED, UNSOLVED = 1, 2, -2, -10
 PRIMAL_INFEASIBLE, DUAL_INFEASIBLE = -3, -4
 
 

@@ -52,14 +52,18 @@ enum : int {
 // plain compare-select min/max: every operand here is finite, so fmax/fmin's NaN handling is dead weight
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
-__device__ __forceinline__ double wmax(double v) {
+// Reductions over the G-lane group of the calling lane; `mask` names exactly that group's lanes, so groups of one warp may
+// sit in different branches (a QP that needs an infeasibility test next to one that does not).
+template <int G = 32>
+__device__ __forceinline__ double wmax(double v, unsigned mask = FULL) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v = dmax(v, __shfl_xor_sync(FULL, v, o));
+  for (int o = G / 2; o; o >>= 1) v = dmax(v, __shfl_xor_sync(mask, v, o));
   return v;
 }
-__device__ __forceinline__ double wsum(double v) {
+template <int G = 32>
+__device__ __forceinline__ double wsum(double v, unsigned mask = FULL) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 __device__ __forceinline__ double limit_scaling(double v) {
@@ -109,35 +113,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 // CTA is the QP, values travel through a double-buffered shared-memory exchange with one barrier per exchange
 // (a thread can only overwrite buffer b after passing the barrier of the exchange on buffer b^1, which every
 // thread reaches only after it has finished reading b).
-template <int WPQ>
+// G = lanes per QP when several short-horizon QPs share one warp (WPQ == 1 only): shuffles are confined to the
+// G-lane segment (the width argument), and every shuffle / vote names only the group's lanes in its mask.
+template <int WPQ, int G = 32>
 struct Comm;
 
-template <>
-struct Comm<1> {
-  __device__ __forceinline__ Comm(double*, int) {}
+template <int G>
+struct Comm<1, G> {
+  unsigned gmask;   // lanes of this lane's group
+  __device__ __forceinline__ Comm(double*, int tid)
+      : gmask(G == 32 ? FULL : (((1u << (G & 31)) - 1u) << ((unsigned)tid & ~(unsigned)(G - 1) & 31u))) {}
+  __device__ __forceinline__ unsigned m() const { return G == 32 ? FULL : gmask; }
   template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = __shfl_up_sync(FULL, v[i], h);
+    for (int i = 0; i < K; ++i) o[i] = __shfl_up_sync(m(), v[i], h, G);
   }
   template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = __shfl_down_sync(FULL, v[i], h);
+    for (int i = 0; i < K; ++i) o[i] = __shfl_down_sync(m(), v[i], h, G);
   }
   template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) { lo[i] = __shfl_up_sync(FULL, v[i], h); hi[i] = __shfl_down_sync(FULL, v[i], h); }
+    for (int i = 0; i < K; ++i) { lo[i] = __shfl_up_sync(m(), v[i], h, G); hi[i] = __shfl_down_sync(m(), v[i], h, G); }
   }
   template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {  // partner k ^ h
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = __shfl_xor_sync(FULL, v[i], h);
+    for (int i = 0; i < K; ++i) o[i] = __shfl_xor_sync(m(), v[i], h, G);
   }
-  __device__ __forceinline__ double rmax(double v) { return wmax(v); }
-  __device__ __forceinline__ double rsum(double v) { return wsum(v); }
-  __device__ __forceinline__ bool any(bool b) { return __any_sync(FULL, b); }
+  __device__ __forceinline__ double rmax(double v) { return wmax<G>(v, m()); }
+  __device__ __forceinline__ double rsum(double v) { return wsum<G>(v, m()); }
+  __device__ __forceinline__ bool any(bool b) { return __any_sync(m(), b); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
-template <int WPQ>
+template <int WPQ, int G>
 struct Comm {
   static constexpr int T = 32 * WPQ;
   static constexpr int KMAX = 9;
@@ -187,14 +196,14 @@ struct Comm {
     return r;
   }
   __device__ __forceinline__ double rmax(double v) {
-    const double* r = rslot(wmax(v));
+    const double* r = rslot(wmax<32>(v));
     double m = r[0];
 #pragma unroll
     for (int w = 1; w < WPQ; ++w) m = dmax(m, r[w]);
     return m;
   }
   __device__ __forceinline__ double rsum(double v) {
-    const double* r = rslot(wsum(v));
+    const double* r = rslot(wsum<32>(v));
     double m = r[0];
 #pragma unroll
     for (int w = 1; w < WPQ; ++w) m += r[w];
@@ -347,24 +356,33 @@ static_assert(SCR_ROWS <= SCR_ROWS_ALLOC, "scratch line too short");
 }  // namespace
 
 // One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
-// NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == 32 WPQ): the last thread is an active
+// NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == lanes of the QP): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
+// QPW = QPs per warp (WPQ == 1 only): short horizons (N + 1 <= 16 / 8) put 2 / 4 QPs side by side in one warp, each on its own
+// G = 32 / QPW lane segment.  The QPs of a warp iterate in lock step; one that terminates stores its result at once and idles
+// (keeps iterating, results discarded) until its neighbours are done too.
 // (255 registers / 8 warps per SM is the measured optimum: capping at 224 for 9 warps costs 17 % in spills)
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW>
 __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+  static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
   extern __shared__ __align__(16) double smem_all[];
-  constexpr int T = 32 * WPQ;              // threads (stage slots) per QP
-  const int qp = blockIdx.x;
-  const int k = threadIdx.x;
+  constexpr int T = 32 * WPQ;              // threads per CTA = columns of the shared-memory and scratch layouts
+  constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
+  const int k = QPW == 1 ? (int)threadIdx.x : (int)(threadIdx.x & (G - 1));                      // stage
+  const int qp_raw = QPW == 1 ? (int)blockIdx.x : (int)(blockIdx.x * QPW + threadIdx.x / G);
+  // a warp's trailing groups may have no QP: they shadow the batch's last record, use a dummy scratch line and never store
+  const bool live = QPW == 1 || qp_raw < p.B;
+  const int qp = live ? qp_raw : p.B - 1;
+  [[maybe_unused]] bool done = !live;
   // PCR multipliers as double2 pairs, pair-major, stage fastest: 9 pairs (-alpha, -gamma) for each of the first
   // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
   constexpr int SM_PAIRS = NLEV * 9 - 1;
-  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + k;
+  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + threadIdx.x;
   // steering-rate variant: 4x4 blocks as plain doubles, element-major: 32 per level (alpha | gamma) + the final inverse
   constexpr int SM_DOUBLES = RATE ? NLEV * 32 + 16 : 2 * SM_PAIRS;
-  double* sm_r = smem_all + k;
-  Comm<WPQ> cm(smem_all + SM_DOUBLES * T, k);
-  double* scr = p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) + k;
+  double* sm_r = smem_all + threadIdx.x;
+  Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, threadIdx.x);
+  double* scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(threadIdx.x / G) * (SCR_ROWS_ALLOC * T)) + k;
 
   const int N = p.N;
   const bool act = k <= N;         // lane owns a stage
@@ -380,21 +398,35 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
     // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
     // is a shared-memory read
     double* rec_sm = smem_all + p.rec_smem_offset;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
-    if (k == 0) {
-      mbar_init(smem_u32(bar), 1);
-      bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
+    if constexpr (QPW == 1) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
+      if (k == 0) {
+        mbar_init(smem_u32(bar), 1);
+        bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
+      }
+      cm.sync();
+      mbar_wait(smem_u32(bar), 0);
+      rec = rec_sm;
+    } else {
+      // the warp's records are consecutive rows of the batch: one bulk copy covers them all
+      const int first = blockIdx.x * QPW;
+      const int nq = (p.B - first < QPW) ? p.B - first : QPW;
+      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + (QPW - 1) * p.stride + p.rec_bulk_bytes / 8);
+      if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        bulk_copy_g2s(smem_u32(rec_sm), p.recs + (size_t)first * p.stride, (uint32_t)((nq - 1) * p.stride * 8 + p.rec_bulk_bytes), smem_u32(bar));
+      }
+      cm.sync();
+      mbar_wait(smem_u32(bar), 0);
+      rec = rec_sm + (size_t)(qp - first) * p.stride;
     }
-    cm.sync();
-    mbar_wait(smem_u32(bar), 0);
-    rec = rec_sm;
   }
   const double x0[3] = {rec[0], rec[1], rec[2]};
   const double vlin = rec[3], slin = rec[4];
   if (!(vlin == vlin)) {
     // NaN linearisation speed marks an empty slot (the planning stage found no valid mini-path for this scene,
     // project.cpp:115-119): nothing to solve, status stays UNSOLVED
-    if (k == 0) {
+    if (k == 0 && !done) {
       const double qn = __longlong_as_double(0x7ff8000000000000LL);
       if (p.u0_out) { p.u0_out[2 * (size_t)qp] = qn; p.u0_out[2 * (size_t)qp + 1] = qn; }
       if (p.status) p.status[qp] = ST_UNSOLVED;
@@ -402,7 +434,8 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       if (p.rho_updates) p.rho_updates[qp] = 0;
       if (p.packed) { double* po = p.packed + 4 * (size_t)qp; po[0] = qn; po[1] = qn; po[2] = (double)ST_UNSOLVED; po[3] = 0.0; }
     }
-    return;
+    if constexpr (QPW == 1) return;
+    done = true;   // the group idles (on NaN data, inside its own lanes) while its neighbours solve
   }
   Model md;
   double Cv[3];
@@ -613,7 +646,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   for (int j = 0; j < 2; ++j) { s.u[j] = 0; s.zg[j] = 0; s.zb[j] = 0; s.yg[j] = 0; s.yb[j] = 0; }
   if constexpr (RATE) { s.zr = 0; s.yr = 0; }
   double rho_bar = dmin(dmax(p.rho0, RHO_MIN), RHO_MAX);
-  double* slot = p.state ? p.state + (size_t)qp * state_doubles(N, RATE ? 1 : 0) : nullptr;
+  double* slot = (p.state && live) ? p.state + (size_t)qp * state_doubles(N, RATE ? 1 : 0) : nullptr;
   if (slot && p.warm_start && slot[nvar + 2 * mcon + 1] != 0.0) {
     // OSQP keeps x, z, y in SCALED coordinates across re-scalings (osqp_update_A rescales the data only):
     // x = D xbar, z = zbar / E, y = E ybar / c with the NEW D, E, c.
@@ -662,8 +695,90 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   double pri_res = 0, dua_res = 0, obj = 0;
   const double al = p.alpha, oma = p.one_minus_alpha;
 
+  // ---------------- store (OSQP store_solution: NaN + cold start when infeasible) ---------------------------
+  // Runs once per QP: after the loop, or — when several QPs share the warp — the moment this QP terminates.
+  auto store = [&]() {
+    const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF || status == ST_DINF_INACC || status == ST_NON_CVX);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (p.x_out) {
+      double* xo = p.x_out + (size_t)qp * nvar;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) xo[3 * k + j] = has_sol ? s.x[j] : qnan;
+      }
+      if (actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) xo[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] : qnan;
+      }
+    }
+    if (p.y_out) {
+      double* yo = p.y_out + (size_t)qp * mcon;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) yo[3 * k + j] = has_sol ? s.yd[j] : qnan;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) yo[3 * (N + 1) + 2 * k + r] = has_sol ? s.yg[r] : qnan;
+      }
+      if (actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) yo[5 * (N + 1) + 2 * k + j] = has_sol ? s.yb[j] : qnan;
+        if constexpr (RATE) yo[row_r0 + k] = has_sol ? s.yr : qnan;
+      }
+    }
+    if (k == 0) {
+      if (p.u0_out) { p.u0_out[2 * (size_t)qp] = has_sol ? s.u[0] : qnan; p.u0_out[2 * (size_t)qp + 1] = has_sol ? s.u[1] : qnan; }
+      if (p.status) p.status[qp] = status;
+      if (p.iters) p.iters[qp] = iter;
+      if (p.rho_updates) p.rho_updates[qp] = n_rho_updates;
+      if (p.info) {
+        double* io = p.info + 4 * (size_t)qp;
+        io[0] = obj; io[1] = pri_res; io[2] = dua_res; io[3] = rho_bar;
+      }
+      if (p.packed) {
+        double* po = p.packed + 4 * (size_t)qp;
+        po[0] = has_sol ? s.u[0] : qnan; po[1] = has_sol ? s.u[1] : qnan; po[2] = (double)status; po[3] = (double)iter;
+      }
+    }
+    if (slot) {
+      // scaled iterates for the next warm start; zeros (cold start) when there is no solution
+      double* sx_ = slot;
+      double* sz_ = slot + nvar;
+      double* sy_ = slot + nvar + mcon;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double e = scr[(SCR_ED + j) * T];
+          sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * T] : 0.0;
+          sz_[3 * k + j] = has_sol ? e * s.zd[j] : 0.0;
+          sy_[3 * k + j] = has_sol ? c * s.yd[j] / e : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double e = scr[(SCR_EG + r) * T];
+          sz_[3 * (N + 1) + 2 * k + r] = has_sol ? e * s.zg[r] : 0.0;
+          sy_[3 * (N + 1) + 2 * k + r] = has_sol ? c * s.yg[r] / e : 0.0;
+        }
+      }
+      if (actu) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double e = scr[(SCR_EB + j) * T];
+          sx_[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] / scr[(SCR_DU + j) * T] : 0.0;
+          sz_[5 * (N + 1) + 2 * k + j] = has_sol ? e * s.zb[j] : 0.0;
+          sy_[5 * (N + 1) + 2 * k + j] = has_sol ? c * s.yb[j] / e : 0.0;
+        }
+        if constexpr (RATE) {
+          const double e = scr[SCR_ER * T];
+          sz_[row_r0 + k] = has_sol ? e * s.zr : 0.0;
+          sy_[row_r0 + k] = has_sol ? c * s.yr / e : 0.0;
+        }
+      }
+      if (k == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
+    }
+  };
+
   for (;;) {
-    if (need_factor) {
+    if (QPW == 1 ? need_factor : __any_sync(FULL, need_factor)) {   // (re-factoring an unchanged rho is idempotent)
       // ---------- factor step: metric from rho_bar, input elimination, PCR multipliers -------------------------
       need_factor = false;
 #pragma unroll
@@ -1348,7 +1463,10 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       if (!finished && last) { status = ST_MAX_ITER; finished = true; }
       // OSQP leaves the loop BEFORE adapt_rho only when the in-loop exact check fires; the after-loop checks
       // (iteration max_iter) come after that iteration's adapt_rho
-      if (chk && exact_hit) break;
+      if (chk && exact_hit) {
+        if constexpr (QPW == 1) break;
+        if (!done) { store(); done = true; }
+      }
     }
     if (adp) {
       // compute_rho_estimate on the scaled residuals, adapt_rho
@@ -1359,94 +1477,22 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       if (rho_new > rho_bar * p.adaptive_rho_tolerance || rho_new < rho_bar / p.adaptive_rho_tolerance) {
         rho_bar = rho_new;
         ++n_rho_updates;
-        need_factor = !finished;
+        need_factor = !finished && !done;
       }
     }
-    if (finished) break;
+    if constexpr (QPW == 1) {
+      if (finished) break;
+    } else {
+      if (finished && !done) { store(); done = true; }
+      if (__all_sync(FULL, done)) break;
+    }
     ++iter;
   }
 
-  // ---------------- store (OSQP store_solution: NaN + cold start when infeasible) ---------------------------
-  const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF || status == ST_DINF_INACC || status == ST_NON_CVX);
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  if (p.x_out) {
-    double* xo = p.x_out + (size_t)qp * nvar;
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) xo[3 * k + j] = has_sol ? s.x[j] : qnan;
-    }
-    if (actu) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) xo[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] : qnan;
-    }
-  }
-  if (p.y_out) {
-    double* yo = p.y_out + (size_t)qp * mcon;
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) yo[3 * k + j] = has_sol ? s.yd[j] : qnan;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) yo[3 * (N + 1) + 2 * k + r] = has_sol ? s.yg[r] : qnan;
-    }
-    if (actu) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) yo[5 * (N + 1) + 2 * k + j] = has_sol ? s.yb[j] : qnan;
-      if constexpr (RATE) yo[row_r0 + k] = has_sol ? s.yr : qnan;
-    }
-  }
-  if (k == 0) {
-    if (p.u0_out) { p.u0_out[2 * (size_t)qp] = has_sol ? s.u[0] : qnan; p.u0_out[2 * (size_t)qp + 1] = has_sol ? s.u[1] : qnan; }
-    if (p.status) p.status[qp] = status;
-    if (p.iters) p.iters[qp] = iter;
-    if (p.rho_updates) p.rho_updates[qp] = n_rho_updates;
-    if (p.info) {
-      double* io = p.info + 4 * (size_t)qp;
-      io[0] = obj; io[1] = pri_res; io[2] = dua_res; io[3] = rho_bar;
-    }
-    if (p.packed) {
-      double* po = p.packed + 4 * (size_t)qp;
-      po[0] = has_sol ? s.u[0] : qnan; po[1] = has_sol ? s.u[1] : qnan; po[2] = (double)status; po[3] = (double)iter;
-    }
-  }
-  if (slot) {
-    // scaled iterates for the next warm start; zeros (cold start) when there is no solution
-    double* sx_ = slot;
-    double* sz_ = slot + nvar;
-    double* sy_ = slot + nvar + mcon;
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double e = scr[(SCR_ED + j) * T];
-        sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * T] : 0.0;
-        sz_[3 * k + j] = has_sol ? e * s.zd[j] : 0.0;
-        sy_[3 * k + j] = has_sol ? c * s.yd[j] / e : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const double e = scr[(SCR_EG + r) * T];
-        sz_[3 * (N + 1) + 2 * k + r] = has_sol ? e * s.zg[r] : 0.0;
-        sy_[3 * (N + 1) + 2 * k + r] = has_sol ? c * s.yg[r] / e : 0.0;
-      }
-    }
-    if (actu) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const double e = scr[(SCR_EB + j) * T];
-        sx_[3 * (N + 1) + 2 * k + j] = has_sol ? s.u[j] / scr[(SCR_DU + j) * T] : 0.0;
-        sz_[5 * (N + 1) + 2 * k + j] = has_sol ? e * s.zb[j] : 0.0;
-        sy_[5 * (N + 1) + 2 * k + j] = has_sol ? c * s.yb[j] / e : 0.0;
-      }
-      if constexpr (RATE) {
-        const double e = scr[SCR_ER * T];
-        sz_[row_r0 + k] = has_sol ? e * s.zr : 0.0;
-        sy_[row_r0 + k] = has_sol ? c * s.yr / e : 0.0;
-      }
-    }
-    if (k == 0) { slot[nvar + 2 * mcon] = rho_bar; slot[nvar + 2 * mcon + 1] = 1.0; }
-  }
+  if constexpr (QPW == 1) store();
 }
 
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
@@ -1459,13 +1505,13 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     smem = (smem + 15) / 16 * 16;
     p.rec_smem_offset = (int)(smem / sizeof(double));
     p.rec_bulk_bytes = rec_even * (int)sizeof(double);
-    smem += (size_t)p.rec_bulk_bytes + 16;  // + the mbarrier
+    smem += (size_t)(QPW - 1) * p.stride * sizeof(double) + (size_t)p.rec_bulk_bytes + 16;  // QPW records + the mbarrier
   }
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  admm_kernel<NLEV, WPQ, LASTFULL, RATE><<<p.B, T, smem, stream>>>(p);
+  admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -1,13 +1,13 @@
-// admm_kernel instantiations with steering-rate rows, horizons 1..31 (one warp per QP).
+// admm_kernel instantiations with steering-rate rows, horizons 1..31 (one warp per QP; 2 / 4 QPs per warp when N + 1 <= 16 / 8).
 #include "admm_kernel_impl.cuh"
 
 namespace f110 {
 cudaError_t launch_admm_w1r(const KParams& p, cudaStream_t stream, int nlev) {
   switch (nlev) {
-    case 1: return launch_one<1, 1, false, true>(p, stream);
-    case 2: return launch_one<2, 1, false, true>(p, stream);
-    case 3: return launch_one<3, 1, false, true>(p, stream);
-    case 4: return launch_one<4, 1, false, true>(p, stream);
+    case 1: return launch_one<1, 1, false, true, 4>(p, stream);
+    case 2: return launch_one<2, 1, false, true, 4>(p, stream);
+    case 3: return (p.N == 7) ? launch_one<3, 1, true, true, 4>(p, stream) : launch_one<3, 1, false, true, 4>(p, stream);
+    case 4: return (p.N == 15) ? launch_one<4, 1, true, true, 2>(p, stream) : launch_one<4, 1, false, true, 2>(p, stream);
     case 5: return (p.N == 31) ? launch_one<5, 1, true, true>(p, stream) : launch_one<5, 1, false, true>(p, stream);
     default: return cudaErrorInvalidValue;
   }

@@ -126,7 +126,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   const size_t ssz = (size_t)max_batch * f110::state_doubles(N, cfg->rate_rows) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)max_batch * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)(max_batch + 4) * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);
@@ -196,6 +196,7 @@ static int solve_device_range(f110_mpc_solver* s, int slot0, int count, const do
   const int T = s->cfg.horizon < 32 ? 32 : (s->cfg.horizon < 64 ? 64 : 128);   // threads (stage slots) per QP
   p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) : nullptr;
   p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
+  p.scratch_dummy = s->d_scratch + (size_t)s->max_batch * f110::SCR_ROWS_ALLOC * T;
   CUDA_TRY(cudaSetDevice(s->device));
   int launched = 0;
   cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &launched);

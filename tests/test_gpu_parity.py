@@ -249,10 +249,11 @@ SETTINGS_VARIANTS = [
 
 
 @pytest.mark.parametrize("rate", [False, True])
+@pytest.mark.parametrize("N", [10, 20])          # 10: two QPs share a warp, 20: one QP per warp
 @pytest.mark.parametrize("variant", range(len(SETTINGS_VARIANTS)))
-def test_settings_variants_match_oracle(pkg, oracle, workloads, variant, rate):
+def test_settings_variants_match_oracle(pkg, oracle, workloads, variant, N, rate):
     # every OSQP knob the ABI exports (the reference leaves them at their defaults, mpc.cpp:98-99), on both kernel variants
-    N, B = 20, 64
+    B = 63
     kw = dict(eps_abs=1e-4, eps_rel=1e-4, warm_start=0)
     kw.update(SETTINGS_VARIANTS[variant])
     recs = workloads.tracking_batch(B, N, seed=400 + variant, gaps=True)
@@ -284,3 +285,25 @@ def test_problem_family_variants_match_oracle(pkg, oracle, workloads, rate):
     o = oracle.MpcBatch(oc, oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve(recs)
     assert_solution_parity(g, o, N)
     np.testing.assert_array_equal(g["iters"], o["iters"])
+
+
+@pytest.mark.parametrize("N,B", [(3, 1), (3, 7), (7, 13), (10, 1), (10, 5), (15, 33), (12, 4096)])
+def test_packed_short_horizons_ragged_batches_and_empty_slots(pkg, oracle, workloads, N, B):
+    # N + 1 <= 16 / 8: 2 / 4 QPs share a warp.  Batch sizes that leave lane groups without a QP, QPs of one warp that stop at
+    # different iterations (mixed easy / hard / infeasible problems), and empty slots (NaN linearisation speed) next to live ones.
+    eps = 1e-4
+    recs = workloads.tracking_batch(B, N, seed=500 + N + B, gaps=True)
+    recs[::3, 4] = 0.9                                     # far outside the steering box: longer solves next to short ones
+    empty = np.zeros(B, dtype=bool)
+    if B > 2:
+        empty[1::5] = True
+    recs[empty, 3] = np.nan
+    gm = 1 if B % 2 else 2                                  # gap_mode 1: mostly infeasible (all-ones stage-0 pair); 2: mostly solved
+    g = pkg.MpcSolver(pkg.default_config(N, gm), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(recs)
+    live = ~empty
+    o = oracle.MpcBatch(oracle.default_cfg(N, gm), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), int(live.sum())).solve(recs[live])
+    assert (g["status"][empty] == pkg.UNSOLVED).all() and np.isnan(g["u0"][empty]).all() and (g["iters"][empty] == 0).all()
+    gl = {k: v[live] for k, v in g.items() if isinstance(v, np.ndarray)}
+    assert_solution_parity(gl, o, N)
+    np.testing.assert_array_equal(gl["iters"], o["iters"])
+    assert len(set(o["iters"].tolist())) > 1 or B < 30     # QPs sharing a warp do stop at different iterations
