@@ -9,9 +9,10 @@
 
 namespace f110 {
 
-// per-QP scratch line in global memory: D, E (12) + previous iterate (12), one column per lane
+// per-QP scratch line in global memory: scaling vectors, previous iterate, factor-step inputs (row indices SCR_* in
+// admm_kernel_impl.cuh), one column per stage
 constexpr int SCR_ROWS_ALLOC = 44;                       // rows of the per-QP scratch line (37 used, 41 with steering-rate rows)
-constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // sized for 4 warps per QP (horizon <= 127)
+constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // line length at 4 warps per QP (horizon 64..127); 32 / 64 columns below
 
 struct KParams {
   // problem family (f110_mpc_config)

@@ -42,7 +42,6 @@ constexpr double OSQP_INFTY = 1e30;
 constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_EQ_OVER_RHO_INEQ = 1e3, RHO_TOL = 1e-4;
 constexpr double MIN_SCALING = 1e-4, MAX_SCALING = 1e4;
 constexpr double INF_THRESH = OSQP_INFTY * MIN_SCALING;  // 1e26
-constexpr double HUGE_BOUND = 1e300;
 
 enum : int {
   ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4,
@@ -343,7 +342,7 @@ struct RateExt<true> {
 template <bool RATE>
 struct StageT : Stage, RateExt<RATE> {};
 
-// per-QP scratch line in global memory (L2): [24][32] doubles, element-major
+// per-QP scratch line in global memory (L2): [SCR_ROWS_ALLOC][T] doubles, element-major, one column per stage
 constexpr int SCR_DX = 0, SCR_DU = 3, SCR_ED = 5, SCR_EG = 8, SCR_EB = 10;       // scaling vectors D, E
 constexpr int SCR_PX = 12, SCR_PU = 15, SCR_PYD = 17, SCR_PYG = 20, SCR_PYB = 22;  // iterate before the last step
 constexpr int SCR_WD = 24, SCR_WG = 27, SCR_WB = 29;    // e_i^2 / c per row: rho_i = rho_bar_i * w_i (factor step only)

@@ -58,3 +58,25 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "oracle_py" not in txt and "osqp_restated" not in txt, f
+
+
+def test_header_is_plain_c_and_struct_layouts_match_bindings(pkg, tmp_path):
+    # the boundary is a C ABI: the header must compile as C99 on its own, and the ctypes mirrors in the Python harness must have
+    # the compiler's field offsets (a silent mismatch would shift every config value)
+    import ctypes as C
+    structs = {"f110_mpc_config": pkg.MpcConfig, "f110_solver_settings": pkg.SolverSettings, "f110_cycle_config": pkg.CycleConfig}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "f110_mpc_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (name, fname)]) == getattr(cls, fname).offset, (name, fname)
