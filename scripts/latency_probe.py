@@ -33,3 +33,25 @@ t0 = time.perf_counter()
 for i in range(200):
     torch.cuda.synchronize()
 print("bare synchronize: %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))
+# fixed-work kernels: where a lone warp's time goes
+for mi in (1, 2, 26, 51):
+    so = M.MpcSolver(M.default_config(N), M.default_settings(warm_start=0, max_iter=mi, check_termination=0, adaptive_rho=0), max_batch=1)
+    ts = []
+    for i in range(60):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); so.solve_device(d[i:i + 1], None, None, u0, st, it, None, None, stream=s); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    print("kernel alone, exactly %d iterations: p50 %.1f us" % (mi, np.percentile(ts[10:], 50)))
+for sc in (0, 10):
+    so = M.MpcSolver(M.default_config(N), M.default_settings(warm_start=0, max_iter=1, check_termination=0, adaptive_rho=0, scaling=sc), max_batch=1)
+    ts = []
+    for i in range(60):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); so.solve_device(d[i:i + 1], None, None, u0, st, it, None, None, stream=s); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    print("1 iteration, %d Ruiz passes: p50 %.1f us" % (sc, np.percentile(ts[10:], 50)))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ts = []
+for i in range(60):
+    a.record(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b) * 1e3)
+print("empty event pair: %.1f us" % np.percentile(ts, 50))

@@ -10,7 +10,7 @@ recs = W.tracking_batch(B, N, seed=4096)
 dev = torch.device("cuda:0")
 kw = dict(warm_start=0)
 if os.environ.get("TUNE_FIXED"):      # fixed work per QP: exactly 50 iterations, one final check (for what-if experiments)
-    kw.update(max_iter=50, check_termination=0, adaptive_rho=0)
+    kw.update(max_iter=int(os.environ.get("TUNE_ITERS", "50")), check_termination=0, adaptive_rho=0)
 RATE = float(os.environ["TUNE_RATE"]) if os.environ.get("TUNE_RATE") else None   # steering-rate rows: max step (rad)
 sol = M.MpcSolver(M.default_config(N, 0, rate_delta=RATE), M.default_settings(**kw), max_batch=B)
 r = torch.from_numpy(recs).to(dev)
