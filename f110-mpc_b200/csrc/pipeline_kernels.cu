@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
 }
 
 // ---- look-ahead point and best surviving path: one warp per scene.  The lanes evaluate the per-waypoint
-// distances; the two argmin scans stay sequential on lane 0 because their result depends on the
-// visiting order (strict <, float-narrowed running minimum — trajectory.cpp:103-107, project.cpp:132-135).
+// distances and the two order-dependent argmin scans (strict <, float-narrowed running minimum — trajectory.cpp:103-107,
+// project.cpp:132-135) in their closed forms.
 constexpr int SB_WARPS = 4;
 __global__ void __launch_bounds__(32 * SB_WARPS) select_kernel(int scenes, int paths, int n_wp, float lookahead,
                                                               const double* __restrict__ pose7, const float* __restrict__ wp_xy,
@@ -274,24 +274,60 @@ __global__ void __launch_bounds__(32 * SB_WARPS) select_kernel(int scenes, int p
     offs[i] = (fx < 0) ? -1.0 : fabs(dist - (double)lookahead);                 // :100, :102
   }
   __syncwarp();
-  int best_idx = -1, pick = -1;
-  if (lane == 0) {
-    float best = 3.402823466e+38f;  // numeric_limits<float>::max()
-    for (int i = 0; i < n_wp; ++i) {
-      const double off = offs[i];
-      if (off < 0.0) continue;                                                  // behind the car
-      if (off < (double)best) { best = (float)off; best_idx = i; }              // :103-107 (float minDistance)
+  // The reference scans the waypoints in order with a FLOAT running minimum (trajectory.cpp:103-107):
+  //     if (off_i < (double)best) { best = (float)off_i; idx = i; }
+  // Rounding is monotone, so `best` never increases and ends at F = min_i (float)off_i; the first waypoint whose rounded
+  // offset is F is always accepted (whatever `best` was before it is a float above F, hence above off_i), and after it
+  // only waypoints with off_i < F (they round up to F) are accepted.  So the scan's answer has a closed form,
+  //     idx = max( g, max{ i : (float)off_i == F and off_i < F } ),   g = min{ i : (float)off_i == F },
+  // which every lane can evaluate on its own waypoints (tests/test_host_cpu.py checks it against the literal loop).
+  float fmin_l = 3.402823466e+38f;   // numeric_limits<float>::max(): nothing ahead leaves it there
+  for (int i = lane; i < n_wp; i += 32) {
+    const double off = offs[i];
+    if (off >= 0.0) { const float f = (float)off; fmin_l = f < fmin_l ? f : fmin_l; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, fmin_l, o); fmin_l = v < fmin_l ? v : fmin_l; }
+  const float F = fmin_l;
+  int g_l = 0x7fffffff, late_l = -1;
+  for (int i = lane; i < n_wp; i += 32) {
+    const double off = offs[i];
+    if (off >= 0.0 && (float)off == F) {
+      g_l = i < g_l ? i : g_l;
+      if (off < (double)F) late_l = i;   // ascending i per lane: the last one stays
     }
-    if (best_idx >= 0) {
-      const double gx = (double)wp_xy[2 * best_idx], gy = (double)wp_xy[2 * best_idx + 1];
-      double min_dist = 1.7976931348623157e308;                                 // project.cpp:125
-      for (int i = 0; i < paths; ++i) {                                         // :127-136, strict <, first wins
-        if (!valid[(size_t)sc * paths + i]) continue;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const int a = __shfl_xor_sync(0xffffffffu, g_l, o), b = __shfl_xor_sync(0xffffffffu, late_l, o);
+    g_l = a < g_l ? a : g_l;
+    late_l = b > late_l ? b : late_l;
+  }
+  const int best_idx = (g_l == 0x7fffffff) ? -1 : (late_l > g_l ? late_l : g_l);
+  // best path: smallest end-point distance to that waypoint, strict <, first wins (project.cpp:125-136) = the lowest index
+  // among the paths at the minimum distance
+  int pick = -1;
+  if (best_idx >= 0) {
+    const double gx = (double)wp_xy[2 * best_idx], gy = (double)wp_xy[2 * best_idx + 1];
+    double dmin_all = 1.7976931348623157e308;                                   // project.cpp:125
+    for (int base = 0; base < paths; base += 32) {
+      const int i = base + lane;
+      double d = 1.7976931348623157e308;
+      if (i < paths && valid[(size_t)sc * paths + i]) {
         const double ex = (double)end_world[2 * ((size_t)sc * paths + i)], ey = (double)end_world[2 * ((size_t)sc * paths + i) + 1];
-        const double d = sqrt((ex - gx) * (ex - gx) + (ey - gy) * (ey - gy));
-        if (d < min_dist) { min_dist = d; pick = i; }
+        d = sqrt((ex - gx) * (ex - gx) + (ey - gy) * (ey - gy));
+      }
+      double m = d;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { const double v = __shfl_xor_sync(0xffffffffu, m, o); m = v < m ? v : m; }
+      if (m < dmin_all) {                                                       // a later chunk wins only with a strictly smaller distance
+        dmin_all = m;
+        const unsigned hit = __ballot_sync(0xffffffffu, d == m && i < paths && valid[(size_t)sc * paths + i]);
+        pick = base + __ffs(hit) - 1;
       }
     }
+  }
+  if (lane == 0) {
     best_global[sc] = best_idx;
     chosen[sc] = pick;
   }

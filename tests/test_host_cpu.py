@@ -56,3 +56,42 @@ def test_lookahead_index_and_headings(pkg, oracle, workloads):
         assert idx == oracle.best_global_idx(xy, pose, 2.5)
     np.testing.assert_array_equal(head, oracle.waypoint_headings(xy))
     np.testing.assert_allclose(head, ori, atol=1e-6)       # numpy's float32 arctan2 in workloads.py is within an ulp of atan2f
+
+
+def test_lookahead_scan_closed_form_equals_literal_scan():
+    # select_kernel (csrc/pipeline_kernels.cu) replaces the reference's ordered scan with a FLOAT running minimum
+    # (trajectory.cpp:103-107) by a closed form; this is the equivalence it relies on, on random and adversarial near-tie inputs
+    rng = np.random.default_rng(0)
+
+    def literal(d):
+        best, idx = np.float32(3.402823466e+38), -1
+        for i, x in enumerate(d):
+            if x >= 0 and x < float(best):
+                best, idx = np.float32(x), i
+        return idx
+
+    def closed(d):
+        ahead = d >= 0
+        if not ahead.any():
+            return -1
+        f = d.astype(np.float32)
+        F = f[ahead].min()
+        C = np.nonzero(ahead & (f == F))[0]
+        return max([C.min()] + [i for i in C if d[i] < float(F)])
+
+    for t in range(20000):
+        n = rng.integers(1, 40)
+        kind = t % 4
+        if kind == 0:
+            d = rng.uniform(0, 3, n)
+        elif kind == 1:
+            base = np.float32(rng.uniform(0.01, 3))
+            d = float(base) + rng.integers(-6, 7, n) * float(np.spacing(base)) / rng.choice([1, 2, 4, 8])
+        elif kind == 2:
+            base = np.float32(rng.uniform(0.01, 3))
+            d = float(base) + rng.uniform(-1.5, 1.5, n) * float(np.spacing(base))
+        else:
+            d = np.abs(rng.normal(0, 1e-3, n)); d[rng.integers(0, n)] = 0.0
+        d = d.astype(np.float64)
+        d[rng.random(n) < 0.2] = -1.0
+        assert literal(d) == closed(d)
