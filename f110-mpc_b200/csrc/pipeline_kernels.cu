@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(32 * SB_WARPS) select_kernel(int scenes, int p
   double q[4];
   quaternion_of(inv, q);
   const Basis w2c = basis_of(q[0], q[1], q[2], q[3]);
+#pragma unroll 4   // independent waypoints: keep several global loads and square roots in flight
   for (int i = lane; i < n_wp; i += 32) {                                       // trajectory.cpp:93, any order: values only
     const double wx = (double)wp_xy[2 * i], wy = (double)wp_xy[2 * i + 1];
     const float fx = (float)((w2c.m[0][0] * wx + w2c.m[0][1] * wy + w2c.m[0][2] * 0.0) + tx);
