@@ -181,7 +181,10 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                       int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid,
                       void* cuda_stream);
 /* Same cycle, HOST buffers (copies in, runs, copies back, synchronises): the reference-facing call for a whole
- * planning + control cycle — laser scans and poses in, controls out.  valid may be NULL. */
+ * planning + control cycle — laser scans and poses in, controls out.  valid may be NULL.
+ * Batches of 64 scenes or more run as two halves on two internal streams (the copies and small kernels of the second half
+ * under the solve of the first); results do not depend on the split.  The mini-path table and the raceline are uploaded only
+ * when their bytes change.  Environment: F110_CYCLE_CHUNKS=1..16 overrides the number of pipelined chunks (tuning only). */
 int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
                     const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp,
                     double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid);
