@@ -368,6 +368,95 @@ def main_product(args):
 # ---------------------------------------------------------------------------------------------------------------
 # --configs: the five BASELINE.json configurations, each measured on the GPU with the CPU oracle beside it.
 # Not the default bench line: writes a JSON report (profiles/configs_rNN.json).
+def config4_records(W, n_sc=64):
+    """BASELINE config 4: 7 lanes x 20 mini-paths x 64 scenarios = 8960 QPs.  Lanes are not implemented in the reference
+    (README:18); SURVEY 8d's synthetic definition: lane l = skirk shifted l x 0.25 m along the left normal, scenario s = station
+    s x (500/64), QP (s, l, p) = ego on lane l at that station tracking mini-path p.  Scenario-major, so a rank's shard is contiguous."""
+    xy, ori = W.skirk_waypoints()
+    head = W.reference_data()["skirk_heading"]
+    table20 = W.traj_table(steer_discrete=19)
+    recs = []
+    for sc in range(n_sc):
+        i = int(sc * (500 / 64))
+        for lane in range(7):
+            nx, ny = -np.sin(head[i]), np.cos(head[i])
+            x, y, yaw = float(xy[i, 0]) + lane * 0.25 * nx, float(xy[i, 1]) + lane * 0.25 * ny, float(ori[i])
+            for pidx in range(20):
+                ref = np.zeros((N_HORIZON, 3)); ref[:, :2] = W.path_to_world(table20[pidx, :N_HORIZON, :2], x, y, yaw)
+                recs.append(np.concatenate([[x, y, yaw], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
+    return np.array(recs)
+
+
+def main_config4(args):
+    """Strong scaling of BASELINE config 4 over the ranks of a torchrun launch: 64 scenarios sharded by scenario,
+    every rank solves its 140-QP scenarios, one all-gather of (u0, status, iters) per step.  Prints one JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    M = importlib.import_module("f110-mpc_b200")
+    W = importlib.import_module("f110-mpc_b200.workloads")
+    SH = importlib.import_module("f110-mpc_b200.sharding")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M.build()
+    recs = config4_records(W)
+    total, per_sc = recs.shape[0], 7 * 20
+    (s_lo, s_hi), (q_lo, q_hi) = SH.shard_by_scenario(64, per_sc, world, rank)
+    mine = np.pad(recs[q_lo:q_hi], ((0, 0), (0, recs.shape[1] % 2)))
+    b = mine.shape[0]
+    sizes = [SH.shard_by_scenario(64, per_sc, world, r)[1] for r in range(world)]
+    sizes = [hi - lo for lo, hi in sizes]
+    sol = M.MpcSolver(M.default_config(N_HORIZON), M.default_settings(warm_start=0), max_batch=b, device=local)
+    d = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+    u0 = torch.empty(b, 2, dtype=torch.float64, device=dev); st = torch.empty(b, dtype=torch.int32, device=dev)
+    it = torch.empty(b, dtype=torch.int32, device=dev)
+    packed = torch.empty(b, 4, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gathered = None
+
+    def step():
+        sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream, packed=packed)
+        return SH.gather_results(packed, world, max_rows=max(sizes), sizes=sizes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        gathered = step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record(); gathered = step(); ev[i][1].record()
+    barrier()
+    ms = torch.tensor([float(sum(a.elapsed_time(c) for a, c in ev))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    if rank == 0:
+        g = gathered.cpu().numpy()
+        from oracle import oracle_py as O
+        O.build()
+        idx = np.arange(0, total, 35)           # a sample across every rank's shard, checked against the CPU oracle
+        o = O.MpcBatch(O.default_cfg(N_HORIZON), O.default_settings(warm_start=0), len(idx)).solve(recs[idx])
+        u0o = o["x"][:, 3 * (N_HORIZON + 1):3 * (N_HORIZON + 1) + 2]
+        print(json.dumps({"metric": METRIC, "config": {"workload": "cfg4: 7 lanes x 20 mini-paths x 64 scenarios = 8960 N=30 QPs, sharded by scenario",
+                                                        "qps_total": int(total), "qps_per_rank": sizes, "l2_policy": "256 MiB flush between steps"},
+                          "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "scaling": "strong", "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                          "gathered_rows": int(g.shape[0]), "solved": int((g[:, 2] == 1).sum()),
+                          "parity_sample": {"n": int(len(idx)), "status_equal": bool((g[idx, 2] == o["status"]).all()),
+                                            "iters_equal": bool((g[idx, 3] == o["iters"]).all()),
+                                            "max_abs_du0": float(np.abs(g[idx, :2] - u0o).max())}}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_configs(args):
     import torch
     M = importlib.import_module("f110-mpc_b200")
@@ -513,19 +602,7 @@ def run_configs(args):
     report["config3_gap_constrained"] = c3
 
     # ---- config 4: 7 lanes x 20 paths x 64 scenarios = 8960 QPs (1 GPU here; bench.py --gpus N shards) ------------
-    head = W.reference_data()["skirk_heading"]
-    table20 = W.traj_table(steer_discrete=19)
-    recs4 = []
-    n_sc = 64 if not args.quick else 8
-    for sc in range(n_sc):
-        i = int(sc * (500 / 64))
-        for lane in range(7):
-            nx, ny = -np.sin(head[i]), np.cos(head[i])
-            x, y, yaw = float(xy[i, 0]) + lane * 0.25 * nx, float(xy[i, 1]) + lane * 0.25 * ny, float(ori[i])
-            for pidx in range(20):
-                ref = np.zeros((N_HORIZON, 3)); ref[:, :2] = W.path_to_world(table20[pidx, :N_HORIZON, :2], x, y, yaw)
-                recs4.append(np.concatenate([[x, y, yaw], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
-    recs4 = np.array(recs4)
+    recs4 = config4_records(W, 64 if not args.quick else 8)
     g = gpu_batch_time(N_HORIZON, recs4)
     o, thr = cpu_batch(N_HORIZON, recs4)
     report["config4_7lanes_20paths_64scenarios"] = {"qps": len(recs4), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"],
@@ -608,9 +685,12 @@ def main():
     ap.add_argument("--configs", action="store_true", help="measure the five BASELINE.json configs (report file, not the bench line)")
     ap.add_argument("--configs-out", default=None)
     ap.add_argument("--quick", action="store_true", help="smaller --configs run")
+    ap.add_argument("--config4", action="store_true", help="strong scaling of BASELINE config 4 (8960 QPs) over the ranks of a torchrun launch")
     args = ap.parse_args()
     if args.configs:
         return run_configs(args)
+    if args.config4:
+        return main_config4(args)
     if args.impl == "reference":
         return main_reference(args)
     return main_product(args)
