@@ -457,6 +457,62 @@ def main_config4(args):
     return 0
 
 
+def main_sweep(args):
+    """BASELINE config 5 across the ranks of a torchrun launch: horizon sweep, 4096 QPs per GPU (weak scaling), one all-gather of
+    (u0, status, iters) per step.  Prints one JSON line (rank 0) with a row per horizon."""
+    import torch
+    import torch.distributed as dist
+    M = importlib.import_module("f110-mpc_b200")
+    W = importlib.import_module("f110-mpc_b200.workloads")
+    SH = importlib.import_module("f110-mpc_b200.sharding")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M.build()
+    B = 4096
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = {}
+    for N in (10, 20, 30, 50, 100):
+        recs = W.tracking_batch(B, N, seed=20240905 + rank)
+        recs = np.pad(recs, ((0, 0), (0, recs.shape[1] % 2)))
+        sol = M.MpcSolver(M.default_config(N), M.default_settings(warm_start=0), max_batch=B, device=local)
+        d = torch.from_numpy(np.ascontiguousarray(recs)).to(dev)
+        u0 = torch.empty(B, 2, dtype=torch.float64, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev); packed = torch.empty(B, 4, dtype=torch.float64, device=dev)
+
+        def step():
+            sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream, packed=packed)
+            return SH.gather_results(packed, world, max_rows=B, sizes=[B] * world)
+        for _ in range(max(args.warmup, 3)):
+            g = step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record(); g = step(); ev[i][1].record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([float(sum(a.elapsed_time(c) for a, c in ev))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        gg = g.cpu().numpy()
+        rows["N=%d" % N] = {"qps_total": world * B, "ms_per_step": ms.item() / args.steps, "solves_per_s": world * B * args.steps / (ms.item() * 1e-3),
+                            "solved": int((gg[:, 2] == 1).sum()), "mean_iters": float(gg[:, 3].mean())}
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "scaling": "weak", "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "cfg5: horizon sweep, 4096 QPs per GPU, OSQP defaults, cold start", "l2_policy": "256 MiB flush between steps"},
+                          "horizons": rows}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_configs(args):
     import torch
     M = importlib.import_module("f110-mpc_b200")
@@ -685,12 +741,15 @@ def main():
     ap.add_argument("--configs", action="store_true", help="measure the five BASELINE.json configs (report file, not the bench line)")
     ap.add_argument("--configs-out", default=None)
     ap.add_argument("--quick", action="store_true", help="smaller --configs run")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5 (horizon sweep, 4096 QPs per GPU) over the ranks of a torchrun launch")
     ap.add_argument("--config4", action="store_true", help="strong scaling of BASELINE config 4 (8960 QPs) over the ranks of a torchrun launch")
     args = ap.parse_args()
     if args.configs:
         return run_configs(args)
     if args.config4:
         return main_config4(args)
+    if args.sweep:
+        return main_sweep(args)
     if args.impl == "reference":
         return main_reference(args)
     return main_product(args)
