@@ -1,6 +1,8 @@
 """CPU tests of the C++ host classes (f110-mpc_b200/host): the ROS-free mirror of the reference's Model /
 Constraints / OccGrid / Transforms / Trajectory / Traj_Plan against the oracle's independent restatement.
 Both are compiled with -ffp-contract=off from separately written sources; results must be bit-identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,19 @@ def test_lookahead_scan_closed_form_equals_literal_scan():
         d = d.astype(np.float64)
         d[rng.random(n) < 0.2] = -1.0
         assert literal(d) == closed(d)
+
+
+def test_host_classes_cpp_unit_checks(pkg, tmp_path):
+    # tests/host_unit.cpp: the C++ mirror classes exercised from C++ (State, Input, Params::FromYaml, Cost, Constraints, Model,
+    # Traj_Plan, OccGrid, Transforms, Trajectory) — no GPU involved
+    import subprocess
+    pkg.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "f110-mpc_b200", "host")
+    exe = tmp_path / "host_unit"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-I", host, "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "host_unit.cpp"), "-o", str(exe), "-L", os.path.join(root, "f110-mpc_b200"),
+                    "-lf110mpc_host", "-lf110mpc_b200", "-Wl,-rpath," + os.path.join(root, "f110-mpc_b200")], check=True)
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host unit checks passed" in r.stdout
