@@ -25,7 +25,7 @@
 //
 //  * RATE = true adds N steering-rate rows  delta_k - delta_{k-1} in [-D, D]  (row 0: delta_0 - steer_prev).  They couple
 //    consecutive inputs, so only the speed v_k is eliminated per stage (a scalar pivot) and the steering angle joins
-//    the reduced unknown: s_k = (x_k, delta_k), 4x4 blocks, same cyclic reduction (plain doubles in shared memory).
+//    the reduced unknown: s_k = (x_k, delta_k), 4x4 blocks, same cyclic reduction and shared-memory layout.
 //
 // Lane k owns stage k: x_k(3), u_k(2) (k<N), dynamics rows k (3), gap rows k (2), input-box rows k (2), rate row k (1).
 // Lanes above N hold all-zero state and never feed an active lane (every cross-lane read is masked or
@@ -335,9 +335,8 @@ struct RateExt<true> {
   double zr, yr;           // rate row iterate
   double rr, ir;           // its rho and 1/rho
   double rrn;              // rho of the NEXT stage's rate row
-  double rlo, rhi;         // its bounds: (k == 0 ? steer_prev : 0) -/+ rate_delta
+  double rbase;            // centre of its bounds: steer_prev on stage 0, else 0; the row lives in [rbase - D, rbase + D]
   double wvi;              // 1 / (R_v + sigma_v + rho_box_v + b_v' R_{k+1} b_v): pivot of the speed elimination
-  double mv[3];            // R_{k+1} b_v
 };
 template <bool RATE>
 struct StageT : Stage, RateExt<RATE> {};
@@ -377,9 +376,9 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
   constexpr int SM_PAIRS = NLEV * 9 - 1;
   double2* sm_pair = reinterpret_cast<double2*>(smem_all) + threadIdx.x;
-  // steering-rate variant: 4x4 blocks as plain doubles, element-major: 32 per level (alpha | gamma) + the final inverse
-  constexpr int SM_DOUBLES = RATE ? NLEV * 32 + 16 : 2 * SM_PAIRS;
-  double* sm_r = smem_all + threadIdx.x;
+  // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
+  // 5 for the symmetric final inverse
+  constexpr int SM_DOUBLES = RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS;
   Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, threadIdx.x);
   double* scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(threadIdx.x / G) * (SCR_ROWS_ALLOC * T)) + k;
 
@@ -485,9 +484,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
     // input box (mpc.cpp:281,290): the same u_min / u_max on every stage, read from the constant bank.  The last stage has no
     // input; its box rows get rho = 0 in the factor step, so whatever its z does never reaches a right-hand side.
     if constexpr (RATE) {
-      const double base = (k == 0) ? slin : 0.0;   // row 0 is measured from the steering applied last cycle
-      s.rlo = base - p.rate_delta;
-      s.rhi = base + p.rate_delta;
+      s.rbase = (k == 0) ? slin : 0.0;   // row 0 is measured from the steering applied last cycle
     }
   }
 
@@ -612,7 +609,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       scr[(SCR_CB + r) * T] = (lbb < -INF_THRESH && ubb > INF_THRESH) ? -1.0 : ((ubb - lbb < RHO_TOL) ? 1.0 : 0.0);
     }
     if constexpr (RATE) {
-      const double lb = er * s.rlo, ub = er * s.rhi;
+      const double lb = er * (s.rbase - p.rate_delta), ub = er * (s.rbase + p.rate_delta);
       scr[SCR_ER * T] = er;
       scr[SCR_WR * T] = er * er * cinv;
       scr[SCR_CR * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
@@ -808,13 +805,15 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         const double bv[3] = {md.b00, md.b10, md.b20};   // column of B that multiplies the speed
         double wv = p.R[0] + s.su[0] + s.rb[0];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { s.mv[i] = s.rdn[i] * bv[i]; wv += s.mv[i] * bv[i]; }
+        double mv[3];   // R_{k+1} b_v
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { mv[i] = s.rdn[i] * bv[i]; wv += mv[i] * bv[i]; }
         s.wvi = actu ? 1.0 / wv : 0.0;
         double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.b_v)(rdn.b_v)' / w_v
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - s.mv[i] * s.mv[l] * s.wvi;
+          for (int l = 0; l < 3; ++l) Rn[3 * i + l] = (i == l ? s.rdn[i] : 0.0) - mv[i] * mv[l] * s.wvi;
         double Rt[9];  // R~_k: from stage k-1, or diag(rho_d) for the x_0 = x_cur rows
         cm.template up<9>(Rn, Rt, 1);
 #pragma unroll
@@ -884,15 +883,33 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
             Lm[e] = vlo ? -Ln[e] : 0.0;
             Um[e] = vhi ? -Un[e] : 0.0;
-            sm_r[(lev * 32 + e) * T] = vlo ? -alp[e] : 0.0;        // stored negated: the solve is r += coef * neighbour
-            sm_r[(lev * 32 + 16 + e) * T] = vhi ? -gam[e] : 0.0;
+            alp[e] = vlo ? -alp[e] : 0.0;        // stored negated: the solve is r += coef * neighbour
+            gam[e] = vhi ? -gam[e] : 0.0;
+          }
+          if (lev < NLEV - 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sm_pair[(lev * 16 + 4 * i + 0) * T] = make_double2(alp[4 * i], alp[4 * i + 1]);
+              sm_pair[(lev * 16 + 4 * i + 1) * T] = make_double2(alp[4 * i + 2], alp[4 * i + 3]);
+              sm_pair[(lev * 16 + 4 * i + 2) * T] = make_double2(gam[4 * i], gam[4 * i + 1]);
+              sm_pair[(lev * 16 + 4 * i + 3) * T] = make_double2(gam[4 * i + 2], gam[4 * i + 3]);
+            }
+          } else {
+            // top level: the stage has its k-h or its k+h neighbour, never both (stage k ^ h): one 4x4 block
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              sm_pair[(lev * 16 + q) * T] = make_double2(alp[2 * q] + gam[2 * q], alp[2 * q + 1] + gam[2 * q + 1]);
           }
         }
         {
           double Bi[16];
           inv_spdD<4>(Bm, Bi);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sm_r[(NLEV * 32 + e) * T] = Bi[e];
+          constexpr int FB = (NLEV - 1) * 16 + 8;   // symmetric: 10 distinct entries
+          sm_pair[(FB + 0) * T] = make_double2(Bi[0], Bi[1]);
+          sm_pair[(FB + 1) * T] = make_double2(Bi[2], Bi[3]);
+          sm_pair[(FB + 2) * T] = make_double2(Bi[5], Bi[6]);
+          sm_pair[(FB + 3) * T] = make_double2(Bi[7], Bi[10]);
+          sm_pair[(FB + 4) * T] = make_double2(Bi[11], Bi[15]);
         }
       } else {
         cm.template dn<3>(s.rd, s.rdn, 1);
@@ -1063,7 +1080,8 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         gd = actu ? gd : 0.0;
         // eliminate v_k: hv = g_v / w_v, f = R_{k+1} b_v hv
         const double hv = s.wvi * gv;
-        const double f[3] = {s.mv[0] * hv, s.mv[1] * hv, s.mv[2] * hv};
+        const double mv[3] = {s.rdn[0] * md.b00, s.rdn[1] * md.b10, s.rdn[2] * md.b20};   // R_{k+1} b_v (as in the factor step)
+        const double f[3] = {mv[0] * hv, mv[1] * hv, mv[2] * hv};
         double r[4], fp[3];
         At_mul(md, f, t3);
         cm.template up<3>(f, fp, 1);
@@ -1071,33 +1089,45 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
         r[3] = gd - md.b21 * f[2];
 #pragma unroll
-        for (int lev = 0; lev < NLEV; ++lev) {
+        for (int lev = 0; lev < NLEV - 1; ++lev) {
           const int h = 1 << lev;
           double lo[4], hi[4];
           cm.template both<4>(r, lo, hi, h);
-          const double* cf = sm_r + (lev * 32) * T;
+          const double2* cf = sm_pair + (lev * 16) * T;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double a = fma(cf[(4 * i) * T], lo[0], r[i]);
-            double b = cf[(16 + 4 * i) * T] * hi[0];
-#pragma unroll
-            for (int j = 1; j < 4; ++j) {
-              a = fma(cf[(4 * i + j) * T], lo[j], a);
-              b = fma(cf[(16 + 4 * i + j) * T], hi[j], b);
-            }
+            const double2 c0 = cf[(4 * i + 0) * T], c1 = cf[(4 * i + 1) * T], c2 = cf[(4 * i + 2) * T], c3 = cf[(4 * i + 3) * T];
+            double a = fma(c0.x, lo[0], r[i]);
+            double b = c2.x * hi[0];
+            a = fma(c0.y, lo[1], a);
+            b = fma(c2.y, hi[1], b);
+            a = fma(c1.x, lo[2], a);
+            b = fma(c3.x, hi[2], b);
+            a = fma(c1.y, lo[3], a);
+            b = fma(c3.y, hi[3], b);
             r[i] = a + b;
+          }
+        }
+        {  // top level: single neighbour k ^ h
+          constexpr int h = 1 << (NLEV - 1);
+          double nb[4];
+          cm.template xr<4>(r, nb, h);
+          const double2* cf = sm_pair + ((NLEV - 1) * 16) * T;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 c0 = cf[(2 * i) * T], c1 = cf[(2 * i + 1) * T];
+            r[i] = fma(c1.y, nb[3], fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[i]))));
           }
         }
         double st[4];
         {
-          const double* cf = sm_r + (NLEV * 32) * T;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            double a = cf[(4 * i) * T] * r[0];
-#pragma unroll
-            for (int j = 1; j < 4; ++j) a = fma(cf[(4 * i + j) * T], r[j], a);
-            st[i] = a;
-          }
+          const double2* cf = sm_pair + ((NLEV - 1) * 16 + 8) * T;
+          const double2 q0 = cf[0 * T], q1 = cf[1 * T], q2 = cf[2 * T], q3 = cf[3 * T], q4 = cf[4 * T];
+          const double b00 = q0.x, b01 = q0.y, b02 = q1.x, b03 = q1.y, b11 = q2.x, b12 = q2.y, b13 = q3.x, b22 = q3.y, b23 = q4.x, b33 = q4.y;
+          st[0] = fma(b03, r[3], fma(b02, r[2], fma(b01, r[1], b00 * r[0])));
+          st[1] = fma(b13, r[3], fma(b12, r[2], fma(b11, r[1], b01 * r[0])));
+          st[2] = fma(b23, r[3], fma(b22, r[2], fma(b12, r[1], b02 * r[0])));
+          st[3] = fma(b33, r[3], fma(b23, r[2], fma(b13, r[1], b03 * r[0])));
         }
         xt[0] = st[0]; xt[1] = st[1]; xt[2] = st[2];
         // recover v~_k = hv - b_v' R_{k+1} (C s~_k - x~_{k+1}) / w_v   (mv = 0 on the last stage)
@@ -1105,7 +1135,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         A_mul(md, xt, axt);
         cm.template dn<3>(xt, xn, 1);
         const double yv[3] = {axt[0] - xn[0], axt[1] - xn[1], axt[2] + md.b21 * st[3] - xn[2]};
-        ut[0] = hv - s.wvi * (s.mv[0] * yv[0] + s.mv[1] * yv[1] + s.mv[2] * yv[2]);
+        ut[0] = hv - s.wvi * (mv[0] * yv[0] + mv[1] * yv[1] + mv[2] * yv[2]);
         ut[1] = st[3];
         // z~ = A w~
         double pred[3];
@@ -1220,7 +1250,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       }
       if constexpr (RATE) {
         const double zr = al * ztr + oma * s.zr;
-        const double zn = clampd(zr + s.ir * s.yr, s.rlo, s.rhi);
+        const double zn = clampd(zr + s.ir * s.yr, s.rbase - p.rate_delta, s.rbase + p.rate_delta);
         s.yr += s.rr * (zr - zn);
         s.zr = zn;
       }
@@ -1362,12 +1392,13 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           [[maybe_unused]] double dyr = 0.0;
           if constexpr (RATE) {
             dyr = s.yr - scr[SCR_PYR * T];
-            const double lbr = erv * s.rlo, ubr = erv * s.rhi;
+            const double rlo = s.rbase - p.rate_delta, rhi = s.rbase + p.rate_delta;
+            const double lbr = erv * rlo, ubr = erv * rhi;
             if (ubr > INF_THRESH) dyr = (lbr < -INF_THRESH) ? 0.0 : dmin(dyr, 0.0);
             else if (lbr < -INF_THRESH) dyr = dmax(dyr, 0.0);
             dyr = actu ? dyr : 0.0;
             mx = fabs(dyr);
-            lhs = s.rhi * dmax(dyr, 0.0) + s.rlo * dmin(dyr, 0.0);
+            lhs = rhi * dmax(dyr, 0.0) + rlo * dmin(dyr, 0.0);
           }
 #pragma unroll
           for (int i = 0; i < 3; ++i) { dyd[i] = act ? dyd[i] : 0.0; mx = dmax(mx, fabs(dyd[i])); lhs += s.bd[i] * dyd[i]; }
@@ -1435,7 +1466,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
               cm.template up<4>(snd, rcv, 1);
               pp[0] = rcv[0]; pp[1] = rcv[1]; pp[2] = rcv[2];
               const double a = ddu[1] - (hasp ? rcv[3] : 0.0);
-              if (actu && ((erv * s.rhi < INF_THRESH && a > th) || (erv * s.rlo > -INF_THRESH && a < -th))) bad = true;
+              if (actu && ((erv * (s.rbase + p.rate_delta) < INF_THRESH && a > th) || (erv * (s.rbase - p.rate_delta) > -INF_THRESH && a < -th))) bad = true;
             } else {
               cm.template up<3>(pred, pp, 1);
             }
@@ -1495,7 +1526,7 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
-  size_t smem = (size_t)(RATE ? NLEV * 32 + 16 : 2 * (NLEV * 9 - 1)) * T * sizeof(double);
+  size_t smem = (size_t)(RATE ? (NLEV - 1) * 32 + 26 : 2 * (NLEV * 9 - 1)) * T * sizeof(double);
   if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
   // TMA staging of the record: base and stride 16-byte aligned, record rounded up to 16 bytes fits inside the stride
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
