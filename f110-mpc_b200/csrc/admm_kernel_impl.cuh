@@ -31,6 +31,8 @@
 // Lanes above N hold all-zero state and never feed an active lane (every cross-lane read is masked or
 // multiplied by a zero multiplier), so no branch in the iteration depends on the lane.
 #pragma once
+#include <cstdlib>
+
 #include "admm_kernel.cuh"
 
 namespace f110 {
@@ -1539,6 +1541,16 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (RATE && WPQ == 1) {
+    // The 4x4 variant runs at the register cap with a few hundred bytes of spill per thread.  With the largest shared-memory
+    // carve-out (5 CTAs per SM) only 28 KB of L1 is left and three quarters of the spill reloads miss it; 4 CTAs inside a
+    // 164 KB carve-out leave 92 KB of L1, which holds them (ncu: profiles/r1f_rate_kernel_ncu_summary.txt).
+    static int carve = -1;
+    if (const char* ev = std::getenv("F110_RATE_CARVEOUT")) carve = std::atoi(ev);   // tuning override (percent)
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         carve >= 0 ? carve : 72);
     if (e != cudaSuccess) return e;
   }
   admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
