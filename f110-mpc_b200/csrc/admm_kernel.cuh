@@ -42,6 +42,7 @@ struct KParams {
   double* packed;     // [B][4] = (u0_v, u0_steer, status, iters) as doubles, the row that is gathered across GPUs; or null
   double* state;      // [B][state_doubles(N)] warm-start slots (scaled iterates x, z, y + rho + flag) or null
   double* scratch;    // [B][SCRATCH_DOUBLES]
+  double* mult_global;  // [B][28 * 128] top-level PCR multipliers of four-warp QPs (horizon >= 64), else null
   double* scratch_dummy;  // 4 more lines: lane groups without a QP (several short-horizon QPs per warp, odd batch) scribble here
 };
 

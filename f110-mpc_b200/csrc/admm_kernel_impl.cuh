@@ -150,13 +150,14 @@ struct Comm<1, G> {
 template <int WPQ, int G>
 struct Comm {
   static constexpr int T = 32 * WPQ;
-  static constexpr int KMAX = 9;
+  static constexpr int KMAX = WPQ == 4 ? 5 : 9;   // values per exchange; with four warps the 9-wide ones (factor step only) go in two rounds to save shared memory
   double* xb;   // [2][KMAX][T] exchange buffers
   double* rb;   // [2][WPQ] reduction slots
   int tid, xph = 0, rph = 0;
   __device__ __forceinline__ Comm(double* smem, int t) : xb(smem), rb(smem + 2 * KMAX * T), tid(t) {}
   static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ; }
   template <int K> __device__ __forceinline__ double* put(const double* v) {
+    static_assert(K <= KMAX, "exchange wider than the buffer");
     double* b = xb + xph * KMAX * T;
     xph ^= 1;
 #pragma unroll
@@ -166,28 +167,40 @@ struct Comm {
   }
   // out-of-range sources return the caller's own value, like a shuffle; callers mask them
   template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
-    const double* b = put<K>(v);
-    const int src = tid - h >= 0 ? tid - h : tid;
+    if constexpr (K > KMAX) { up<KMAX>(v, o, h); up<K - KMAX>(v + KMAX, o + KMAX, h); }
+    else {
+      const double* b = put<K>(v);
+      const int src = tid - h >= 0 ? tid - h : tid;
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+      for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+    }
   }
   template <int K> __device__ __forceinline__ void dn(const double* v, double* o, int h) {
-    const double* b = put<K>(v);
-    const int src = tid + h < T ? tid + h : tid;
+    if constexpr (K > KMAX) { dn<KMAX>(v, o, h); dn<K - KMAX>(v + KMAX, o + KMAX, h); }
+    else {
+      const double* b = put<K>(v);
+      const int src = tid + h < T ? tid + h : tid;
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+      for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+    }
   }
   template <int K> __device__ __forceinline__ void both(const double* v, double* lo, double* hi, int h) {
-    const double* b = put<K>(v);
-    const int sl = tid - h >= 0 ? tid - h : tid, sh = tid + h < T ? tid + h : tid;
+    if constexpr (K > KMAX) { both<KMAX>(v, lo, hi, h); both<K - KMAX>(v + KMAX, lo + KMAX, hi + KMAX, h); }
+    else {
+      const double* b = put<K>(v);
+      const int sl = tid - h >= 0 ? tid - h : tid, sh = tid + h < T ? tid + h : tid;
 #pragma unroll
-    for (int i = 0; i < K; ++i) { lo[i] = b[i * T + sl]; hi[i] = b[i * T + sh]; }
+      for (int i = 0; i < K; ++i) { lo[i] = b[i * T + sl]; hi[i] = b[i * T + sh]; }
+    }
   }
   template <int K> __device__ __forceinline__ void xr(const double* v, double* o, int h) {
-    const double* b = put<K>(v);
-    const int src = tid ^ h;
+    if constexpr (K > KMAX) { xr<KMAX>(v, o, h); xr<K - KMAX>(v + KMAX, o + KMAX, h); }
+    else {
+      const double* b = put<K>(v);
+      const int src = tid ^ h;
 #pragma unroll
-    for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+      for (int i = 0; i < K; ++i) o[i] = b[i * T + src];
+    }
   }
   __device__ __forceinline__ double* rslot(double v) {
     double* r = rb + rph * WPQ;
@@ -376,8 +389,14 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   [[maybe_unused]] bool done = !live;
   // PCR multipliers as double2 pairs, pair-major, stage fastest: 9 pairs (-alpha, -gamma) for each of the first
   // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
-  constexpr int SM_PAIRS = NLEV * 9 - 1;
+  // Horizons 64..127 (four warps per QP): the multipliers of the two top levels (9 + 5 pairs) live in a per-QP global line, read
+  // back through L1 / L2 by the lane that wrote them — the shared memory saved lets two QPs share an SM instead of one
+  // (N = 100: 2.75 -> 2.24 ms per 4096 QPs).  For two-warp QPs the same trade (4 CTAs per SM instead of 3) loses 5 %.
+  constexpr bool TOPG = WPQ == 4 && !RATE;
+  constexpr int SM_PAIRS = TOPG ? (NLEV - 2) * 9 + 3 : NLEV * 9 - 1;
+  constexpr int FINAL_PAIR = SM_PAIRS - 3;
   double2* sm_pair = reinterpret_cast<double2*>(smem_all) + threadIdx.x;
+  [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)blockIdx.x * (14 * T) + threadIdx.x : nullptr;
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
   constexpr int SM_DOUBLES = RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS;
@@ -1010,9 +1029,10 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-              sm_pair[(lev * 9 + 3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
-              sm_pair[(lev * 9 + 3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
-              sm_pair[(lev * 9 + 3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+              double2* dst = (TOPG && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+              dst[(3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+              dst[(3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+              dst[(3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
             }
           } else {
             // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
@@ -1022,15 +1042,15 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
             one[9] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) sm_pair[(lev * 9 + q) * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            for (int q = 0; q < 5; ++q) (TOPG ? gl_pair + 9 * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
           }
         }
         {
           double Bi[9];
           inv_spd3(Bm, Bi);
-          sm_pair[(NLEV * 9 - 4 + 0) * T] = make_double2(Bi[0], Bi[1]);
-          sm_pair[(NLEV * 9 - 4 + 1) * T] = make_double2(Bi[2], Bi[4]);
-          sm_pair[(NLEV * 9 - 4 + 2) * T] = make_double2(Bi[5], Bi[8]);
+          sm_pair[(FINAL_PAIR + 0) * T] = make_double2(Bi[0], Bi[1]);
+          sm_pair[(FINAL_PAIR + 1) * T] = make_double2(Bi[2], Bi[4]);
+          sm_pair[(FINAL_PAIR + 2) * T] = make_double2(Bi[5], Bi[8]);
         }
       }
       cm.sync();
@@ -1180,7 +1200,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const int h = 1 << lev;
           double lo[3], hi[3];
           cm.template both<3>(r, lo, hi, h);
-          const double2* cf = sm_pair + (lev * 9) * T;
+          const double2* cf = (TOPG && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
@@ -1197,14 +1217,14 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           constexpr int h = 1 << (NLEV - 1);
           double nb[3];
           cm.template xr<3>(r, nb, h);
-          const double2* cf = sm_pair + ((NLEV - 1) * 9) * T;
+          const double2* cf = TOPG ? gl_pair + 9 * T : sm_pair + ((NLEV - 1) * 9) * T;
           const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
           r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
           r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
           r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
         }
         {
-          const double2 q0 = sm_pair[(NLEV * 9 - 4 + 0) * T], q1 = sm_pair[(NLEV * 9 - 4 + 1) * T], q2 = sm_pair[(NLEV * 9 - 4 + 2) * T];
+          const double2 q0 = sm_pair[(FINAL_PAIR + 0) * T], q1 = sm_pair[(FINAL_PAIR + 1) * T], q2 = sm_pair[(FINAL_PAIR + 2) * T];
           const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
           xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
           xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
@@ -1528,8 +1548,10 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
-  size_t smem = (size_t)(RATE ? (NLEV - 1) * 32 + 26 : 2 * (NLEV * 9 - 1)) * T * sizeof(double);
-  if (WPQ > 1) smem += (size_t)(2 * 9 * T + 2 * WPQ) * sizeof(double);
+  constexpr bool TOPG = WPQ == 4 && !RATE;   // top two levels' multipliers in global memory (see the kernel)
+  size_t smem = (size_t)(RATE ? (NLEV - 1) * 32 + 26 : 2 * (TOPG ? (NLEV - 2) * 9 + 3 : NLEV * 9 - 1)) * T * sizeof(double);
+  if constexpr (WPQ > 1) smem += (size_t)Comm<WPQ, 32>::doubles() * sizeof(double);
+  if (TOPG && !p.mult_global) return cudaErrorInvalidValue;
   // TMA staging of the record: base and stride 16-byte aligned, record rounded up to 16 bytes fits inside the stride
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
   p.rec_bulk_bytes = 0;

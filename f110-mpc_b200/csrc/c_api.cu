@@ -32,6 +32,7 @@ struct f110_mpc_solver {
   int last_launches = 0;
   double* d_state = nullptr;    // warm-start slots
   double* d_scratch = nullptr;  // per-QP scratch lines (scaling vectors, previous iterate)
+  double* d_mult = nullptr;     // per-QP top-level multipliers of four-warp QPs (horizon >= 64)
   // staging for the host-buffer entry: one device block [u0 | status | iters | x | y] so results come back in
   // one copy, plus a small pinned mirror used for latency-critical small batches
   double* d_recs = nullptr;
@@ -127,6 +128,8 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)(max_batch + 4) * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
+  if (e == cudaSuccess && cfg->horizon >= 64 && !cfg->rate_rows)
+    e = cudaMalloc(&s->d_mult, (size_t)max_batch * 28 * 128 * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);
@@ -141,6 +144,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaSetDevice(s->device);
   cudaFree(s->d_state);
   cudaFree(s->d_scratch);
+  cudaFree(s->d_mult);
   cudaFree(s->d_recs); cudaFree(s->d_out);
   s->cyc.release();
   cudaFree(s->cyc_stage);
@@ -197,6 +201,7 @@ static int solve_device_range(f110_mpc_solver* s, int slot0, int count, const do
   p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) : nullptr;
   p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
   p.scratch_dummy = s->d_scratch + (size_t)s->max_batch * f110::SCR_ROWS_ALLOC * T;
+  p.mult_global = s->d_mult ? s->d_mult + (size_t)slot0 * 28 * T : nullptr;
   CUDA_TRY(cudaSetDevice(s->device));
   int launched = 0;
   cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &launched);
