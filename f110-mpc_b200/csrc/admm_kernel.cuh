@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef ADMM_W2_GLOBAL_LEVELS
+#define ADMM_W2_GLOBAL_LEVELS 1   // two-warp QPs: top PCR levels whose multipliers live in global memory (0 or 1; 1 = 4 QPs per SM, 2-4 % faster)
+#endif
 #ifndef ADMM_MIN_BLOCKS
 #define ADMM_MIN_BLOCKS 8   // resident CTAs per SM the register allocation must allow
 #endif
@@ -42,7 +45,7 @@ struct KParams {
   double* packed;     // [B][4] = (u0_v, u0_steer, status, iters) as doubles, the row that is gathered across GPUs; or null
   double* state;      // [B][state_doubles(N)] warm-start slots (scaled iterates x, z, y + rho + flag) or null
   double* scratch;    // [B][SCRATCH_DOUBLES]
-  double* mult_global;  // [B][28 * 128] top-level PCR multipliers of four-warp QPs (horizon >= 64), else null
+  double* mult_global;  // [B][28 * 128] top-level PCR multipliers of multi-warp QPs (horizon >= 32; used from 64 up), else null
   double* scratch_dummy;  // 4 more lines: lane groups without a QP (several short-horizon QPs per warp, odd batch) scribble here
 };
 

@@ -150,7 +150,7 @@ struct Comm<1, G> {
 template <int WPQ, int G>
 struct Comm {
   static constexpr int T = 32 * WPQ;
-  static constexpr int KMAX = WPQ == 4 ? 5 : 9;   // values per exchange; with four warps the 9-wide ones (factor step only) go in two rounds to save shared memory
+  static constexpr int KMAX = (WPQ == 4 || ADMM_W2_GLOBAL_LEVELS > 0) ? 5 : 9;   // values per exchange; with four warps the 9-wide ones (factor step only) go in two rounds to save shared memory
   double* xb;   // [2][KMAX][T] exchange buffers
   double* rb;   // [2][WPQ] reduction slots
   int tid, xph = 0, rph = 0;
@@ -389,14 +389,18 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   [[maybe_unused]] bool done = !live;
   // PCR multipliers as double2 pairs, pair-major, stage fastest: 9 pairs (-alpha, -gamma) for each of the first
   // NLEV-1 levels, 5 pairs for the one-sided top level, 3 pairs for the final block inverse
-  // Horizons 64..127 (four warps per QP): the multipliers of the two top levels (9 + 5 pairs) live in a per-QP global line, read
-  // back through L1 / L2 by the lane that wrote them — the shared memory saved lets two QPs share an SM instead of one
-  // (N = 100: 2.75 -> 2.24 ms per 4096 QPs).  For two-warp QPs the same trade (4 CTAs per SM instead of 3) loses 5 %.
-  constexpr bool TOPG = WPQ == 4 && !RATE;
-  constexpr int SM_PAIRS = TOPG ? (NLEV - 2) * 9 + 3 : NLEV * 9 - 1;
+  // Multi-warp QPs keep the multipliers of their top PCR levels in a per-QP global line, read back through L1 / L2 by the lane
+  // that wrote them; the shared memory saved buys residency.  Four warps (N 64..127): the two top levels (9 + 5 pairs) -> two QPs
+  // per SM instead of one (N = 100: 2.75 -> 2.24 ms per 4096 QPs).  Two warps (N 32..63): only the one-sided top level (5 pairs)
+  // -> four QPs per SM instead of three (2-4 % faster; moving both levels loses 5 %).  GL = number of levels kept there.
+  constexpr int GL = RATE ? 0 : (WPQ == 4 ? 2 : (WPQ == 2 ? ADMM_W2_GLOBAL_LEVELS : 0));
+  constexpr bool TOPG = GL > 0;
+  constexpr int GLP = GL == 2 ? 14 : 5;            // pairs per stage in the global line
+  constexpr int GTOP = GL == 2 ? 9 : 0;            // where the top level starts in it
+  constexpr int SM_PAIRS = NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
   constexpr int FINAL_PAIR = SM_PAIRS - 3;
   double2* sm_pair = reinterpret_cast<double2*>(smem_all) + threadIdx.x;
-  [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)blockIdx.x * (14 * T) + threadIdx.x : nullptr;
+  [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)blockIdx.x * (GLP * T) + threadIdx.x : nullptr;
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
   constexpr int SM_DOUBLES = RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS;
@@ -1029,7 +1033,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-              double2* dst = (TOPG && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+              double2* dst = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
               dst[(3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
               dst[(3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
               dst[(3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
@@ -1042,7 +1046,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
             one[9] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) (TOPG ? gl_pair + 9 * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            for (int q = 0; q < 5; ++q) (TOPG ? gl_pair + GTOP * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
           }
         }
         {
@@ -1200,7 +1204,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const int h = 1 << lev;
           double lo[3], hi[3];
           cm.template both<3>(r, lo, hi, h);
-          const double2* cf = (TOPG && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+          const double2* cf = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
@@ -1217,7 +1221,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           constexpr int h = 1 << (NLEV - 1);
           double nb[3];
           cm.template xr<3>(r, nb, h);
-          const double2* cf = TOPG ? gl_pair + 9 * T : sm_pair + ((NLEV - 1) * 9) * T;
+          const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
           const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
           r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
           r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
@@ -1548,8 +1552,9 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
-  constexpr bool TOPG = WPQ == 4 && !RATE;   // top two levels' multipliers in global memory (see the kernel)
-  size_t smem = (size_t)(RATE ? (NLEV - 1) * 32 + 26 : 2 * (TOPG ? (NLEV - 2) * 9 + 3 : NLEV * 9 - 1)) * T * sizeof(double);
+  constexpr int GL = RATE ? 0 : (WPQ == 4 ? 2 : (WPQ == 2 ? ADMM_W2_GLOBAL_LEVELS : 0));   // top levels' multipliers in global memory (see the kernel)
+  constexpr bool TOPG = GL > 0;
+  size_t smem = (size_t)(RATE ? (NLEV - 1) * 32 + 26 : 2 * (NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0))) * T * sizeof(double);
   if constexpr (WPQ > 1) smem += (size_t)Comm<WPQ, 32>::doubles() * sizeof(double);
   if (TOPG && !p.mult_global) return cudaErrorInvalidValue;
   // TMA staging of the record: base and stride 16-byte aligned, record rounded up to 16 bytes fits inside the stride

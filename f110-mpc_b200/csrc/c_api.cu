@@ -128,7 +128,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)(max_batch + 4) * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
-  if (e == cudaSuccess && cfg->horizon >= 64 && !cfg->rate_rows)
+  if (e == cudaSuccess && cfg->horizon >= (ADMM_W2_GLOBAL_LEVELS > 0 ? 32 : 64) && !cfg->rate_rows)
     e = cudaMalloc(&s->d_mult, (size_t)max_batch * 28 * 128 * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
