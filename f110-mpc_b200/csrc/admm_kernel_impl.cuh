@@ -55,11 +55,23 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 // Reductions over the G-lane group of the calling lane; `mask` names exactly that group's lanes, so groups of one warp may
 // sit in different branches (a QP that needs an infeasibility test next to one that does not).
+// Max over the group.  Every caller reduces norms (non-negative values): for those the IEEE-754 order is the order of the bit
+// patterns as unsigned integers, so the hardware integer warp reduction (REDUX) does it in two steps — the high words, then the
+// low words of the lanes that hold the winning high word — instead of a five-step shuffle butterfly.  A NaN pattern sorts above
+// every finite value and therefore propagates.
+// (Lane groups narrower than the warp keep the butterfly: REDUX would run once per distinct member mask.)
 template <int G = 32>
 __device__ __forceinline__ double wmax(double v, unsigned mask = FULL) {
+  if constexpr (G == 32) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned H = __reduce_max_sync(FULL, hi);
+    const unsigned L = __reduce_max_sync(FULL, hi == H ? lo : 0u);
+    return __hiloint2double((int)H, (int)L);
+  } else {
 #pragma unroll
-  for (int o = G / 2; o; o >>= 1) v = dmax(v, __shfl_xor_sync(mask, v, o));
-  return v;
+    for (int o = G / 2; o; o >>= 1) v = dmax(v, __shfl_xor_sync(mask, v, o));
+    return v;
+  }
 }
 template <int G = 32>
 __device__ __forceinline__ double wsum(double v, unsigned mask = FULL) {
