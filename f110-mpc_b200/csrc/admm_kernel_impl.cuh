@@ -1096,6 +1096,9 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
       double xt[3], ut[2], ztd[3];
       [[maybe_unused]] double ztr = 0.0;
+      // 1 where the stage has a predecessor: values shuffled in from stage k-1 enter through an FMA with this factor (exact: the
+      // factor is 0 or 1), one select instead of two per masked value
+      const double hm = hasp ? 1.0 : 0.0;
       if constexpr (RATE) {
         const double sr = s.rr * s.zr - s.yr;   // 0 on stages without an input (rho = 0, y = 0)
         double sdn[3], srn;
@@ -1124,7 +1127,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         At_mul(md, f, t3);
         cm.template up<3>(f, fp, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
+        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
         r[3] = gd - md.b21 * f[2];
 #pragma unroll
         for (int lev = 0; lev < NLEV - 1; ++lev) {
@@ -1182,8 +1185,8 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         double rcv[4];
         cm.template up<4>(snd, rcv, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? rcv[i] : 0.0) - xt[i];
-        ztr = ut[1] - (hasp ? rcv[3] : 0.0);
+        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, rcv[i], -xt[i]);
+        ztr = fma(-hm, rcv[3], ut[1]);
       } else {
         double sdn[3];
         cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
@@ -1209,7 +1212,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         At_mul(md, f, t3);
         cm.template up<3>(f, fp, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = gx[i] - t3[i] + (hasp ? fp[i] : 0.0);
+        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
         // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
 #pragma unroll
         for (int lev = 0; lev < NLEV - 1; ++lev) {
@@ -1262,7 +1265,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         for (int i = 0; i < 3; ++i) pred[i] += axt[i];
         cm.template up<3>(pred, pp, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ztd[i] = (hasp ? pp[i] : 0.0) - xt[i];
+        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, pp[i], -xt[i]);
       }
       const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
 #pragma unroll
