@@ -60,6 +60,8 @@ struct f110_mpc_solver {
   } cyc;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
   cudaStream_t stream = nullptr;
   // f110_cycle_host pipelines its scenes in chunks over two streams (copies of chunk c+1 under the kernels of chunk c)
+  // single-QP latency path: the copy-in / solve / copy-out triple captured once as a CUDA graph per output shape (u0 only, +x, +x+y)
+  cudaGraphExec_t lat_graph[3] = {nullptr, nullptr, nullptr};
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
 };
@@ -151,6 +153,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   if (s->cyc_pin) cudaFreeHost(s->cyc_pin);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
+  for (cudaGraphExec_t g : s->lat_graph) if (g) cudaGraphExecDestroy(g);
   if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->ev_tab) cudaEventDestroy(s->ev_tab);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
@@ -251,6 +254,38 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
     // latency path: records staged through pinned memory (true async DMA)
     double* hp = reinterpret_cast<double*>(s->h_pin);
     for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rdp, recs + (size_t)b * rec_stride, rd * sizeof(double));
+    if (count == 1 && !s->cfg.rate_rows && N <= 31) {   // (longer horizons set a function attribute at launch: not captured)
+      // one QP (the reference's own call pattern, mpc.cpp:69-143): copy-in, solve and copy-out are replayed as one captured graph,
+      // one driver call instead of three.  Every address and size in it is fixed for the handle's lifetime.
+      unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rdp * sizeof(double);
+      const int shape = y ? 2 : (x ? 1 : 0);
+      if (!s->lat_graph[shape]) {
+        const size_t bytes = y ? o_y + (size_t)m * sizeof(double) : (x ? o_x + (size_t)n * sizeof(double) : o_x);
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t ce = cudaMemcpyAsync(s->d_recs, hp, (size_t)rdp * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+        int rcg = F110_OK;
+        if (ce == cudaSuccess)
+          rcg = f110_mpc_solve_device(s, 1, s->d_recs, rdp, shape >= 1 ? d_x : nullptr, shape == 2 ? d_y : nullptr, d_u0, d_status, d_iters, nullptr,
+                                      nullptr, s->stream);
+        if (ce == cudaSuccess && rcg == F110_OK) ce = cudaMemcpyAsync(ho, s->d_out, bytes, cudaMemcpyDeviceToHost, s->stream);
+        const cudaError_t ee = cudaStreamEndCapture(s->stream, &g);
+        if (rcg != F110_OK) { if (g) cudaGraphDestroy(g); return rcg; }
+        if (ce != cudaSuccess || ee != cudaSuccess) { if (g) cudaGraphDestroy(g); return cuda_fail(ce != cudaSuccess ? ce : ee, "f110_mpc_solve_host: graph capture"); }
+        ce = cudaGraphInstantiate(&s->lat_graph[shape], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return cuda_fail(ce, "f110_mpc_solve_host: graph instantiate");
+      }
+      s->last_launches = 1;
+      CUDA_TRY(cudaGraphLaunch(s->lat_graph[shape], s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      if (u0) std::memcpy(u0, ho, 2 * sizeof(double));
+      if (status) std::memcpy(status, ho + o_status, sizeof(int32_t));
+      if (iters) std::memcpy(iters, ho + o_iters, sizeof(int32_t));
+      if (x) std::memcpy(x, ho + o_x, (size_t)n * sizeof(double));
+      if (y) std::memcpy(y, ho + o_y, (size_t)m * sizeof(double));
+      return F110_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(s->d_recs, hp, (size_t)count * rdp * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   } else {
     CUDA_TRY(cudaMemcpy2DAsync(s->d_recs, rdp * sizeof(double), recs, (size_t)rec_stride * sizeof(double), rd * sizeof(double), count,
