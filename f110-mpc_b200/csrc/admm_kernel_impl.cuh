@@ -1018,21 +1018,21 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const int h = 1 << lev;
           const bool vlo = act && (k - h >= 0);
           const bool vhi = act && (k + h <= N);
-          double Bi[9], XU[9], XL[9];
+          // alpha = L_k B_{k-h}^-1, gamma = U_k B_{k+h}^-1; the reduced blocks follow from them and the neighbours' L, U:
+          //   B_k -= alpha U_{k-h} + gamma L_{k+h},   L_k <- -alpha L_{k-h},   U_k <- -gamma U_{k+h}      (6 products per level)
+          double Bi[9];
           inv_spd3(Bm, Bi);
-          mm3(Bi, Um, XU);
-          mm3(Bi, Lm, XL);
           double nlo[9], nhi[9], t1[9], t2[9];
           double alp[9], gam[9], Ln[9], Un[9];
           cm.template both<9>(Bi, nlo, nhi, h);
           mm3(Lm, nlo, alp);
           mm3(Um, nhi, gam);
-          cm.template both<9>(XU, nlo, nhi, h);
-          mm3(Lm, nlo, t1);
-          mm3(Um, nhi, Un);
-          cm.template both<9>(XL, nlo, nhi, h);
-          mm3(Lm, nlo, Ln);
-          mm3(Um, nhi, t2);
+          cm.template both<9>(Um, nlo, nhi, h);
+          mm3(alp, nlo, t1);
+          mm3(gam, nhi, Un);
+          cm.template both<9>(Lm, nlo, nhi, h);
+          mm3(alp, nlo, Ln);
+          mm3(gam, nhi, t2);
 #pragma unroll
           for (int e = 0; e < 9; ++e) {
             Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
