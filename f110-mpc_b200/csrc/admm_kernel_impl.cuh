@@ -897,24 +897,23 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const int h = 1 << lev;
           const bool vlo = act && (k - h >= 0);
           const bool vhi = act && (k + h <= N);
-          double Bi[16], XU[16], XL[16];
+          // six products per level, as in the 3x3 variant: alpha, gamma, then the reduced blocks from the neighbours' U, L
+          double Bi[16];
           inv_spdD<4>(Bm, Bi);
-          mmD<4>(Bi, Um, XU);
-          mmD<4>(Bi, Lm, XL);
           double nlo[16], nhi[16], t1[16], t2[16];
           double alp[16], gam[16], Ln[16], Un[16];
           cm.template both<8>(Bi, nlo, nhi, h);
           cm.template both<8>(Bi + 8, nlo + 8, nhi + 8, h);
           mmD<4>(Lm, nlo, alp);
           mmD<4>(Um, nhi, gam);
-          cm.template both<8>(XU, nlo, nhi, h);
-          cm.template both<8>(XU + 8, nlo + 8, nhi + 8, h);
-          mmD<4>(Lm, nlo, t1);
-          mmD<4>(Um, nhi, Un);
-          cm.template both<8>(XL, nlo, nhi, h);
-          cm.template both<8>(XL + 8, nlo + 8, nhi + 8, h);
-          mmD<4>(Lm, nlo, Ln);
-          mmD<4>(Um, nhi, t2);
+          cm.template both<8>(Um, nlo, nhi, h);
+          cm.template both<8>(Um + 8, nlo + 8, nhi + 8, h);
+          mmD<4>(alp, nlo, t1);
+          mmD<4>(gam, nhi, Un);
+          cm.template both<8>(Lm, nlo, nhi, h);
+          cm.template both<8>(Lm + 8, nlo + 8, nhi + 8, h);
+          mmD<4>(alp, nlo, Ln);
+          mmD<4>(gam, nhi, t2);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
