@@ -898,29 +898,49 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const bool vlo = act && (k - h >= 0);
           const bool vhi = act && (k + h <= N);
           // six products per level, as in the 3x3 variant: alpha, gamma, then the reduced blocks from the neighbours' U, L
-          double Bi[16];
-          inv_spdD<4>(Bm, Bi);
-          double nlo[16], nhi[16], t1[16], t2[16];
-          double alp[16], gam[16], Ln[16], Un[16];
-          cm.template both<8>(Bi, nlo, nhi, h);
-          cm.template both<8>(Bi + 8, nlo + 8, nhi + 8, h);
+          // (ordered so that few 4x4 temporaries are alive at once: the register peak of this rare step decides what the hot loop spills)
+          double alp[16], gam[16], nlo[16], nhi[16];
+          {
+            double Bi[16];
+            inv_spdD<4>(Bm, Bi);
+            cm.template both<8>(Bi, nlo, nhi, h);
+            cm.template both<8>(Bi + 8, nlo + 8, nhi + 8, h);
+          }
           mmD<4>(Lm, nlo, alp);
           mmD<4>(Um, nhi, gam);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {   // a missing neighbour contributes nothing: masking alpha, gamma masks every product below
+            alp[e] = vlo ? alp[e] : 0.0;
+            gam[e] = vhi ? gam[e] : 0.0;
+          }
           cm.template both<8>(Um, nlo, nhi, h);
           cm.template both<8>(Um + 8, nlo + 8, nhi + 8, h);
-          mmD<4>(alp, nlo, t1);
+          {
+            double t1[16];
+            mmD<4>(alp, nlo, t1);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) Bm[e] -= t1[e];
+          }
+          double Un[16];
           mmD<4>(gam, nhi, Un);
           cm.template both<8>(Lm, nlo, nhi, h);
           cm.template both<8>(Lm + 8, nlo + 8, nhi + 8, h);
-          mmD<4>(alp, nlo, Ln);
-          mmD<4>(gam, nhi, t2);
+          {
+            double t2[16];
+            mmD<4>(gam, nhi, t2);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) Bm[e] -= t2[e];
+          }
+          {
+            double Ln[16];
+            mmD<4>(alp, nlo, Ln);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { Lm[e] = -Ln[e]; Um[e] = -Un[e]; }
+          }
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
-            Lm[e] = vlo ? -Ln[e] : 0.0;
-            Um[e] = vhi ? -Un[e] : 0.0;
-            alp[e] = vlo ? -alp[e] : 0.0;        // stored negated: the solve is r += coef * neighbour
-            gam[e] = vhi ? -gam[e] : 0.0;
+            alp[e] = -alp[e];        // stored negated: the solve is r += coef * neighbour
+            gam[e] = -gam[e];
           }
           if (lev < NLEV - 1) {
 #pragma unroll
