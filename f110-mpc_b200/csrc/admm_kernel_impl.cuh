@@ -1039,26 +1039,46 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const bool vhi = act && (k + h <= N);
           // alpha = L_k B_{k-h}^-1, gamma = U_k B_{k+h}^-1; the reduced blocks follow from them and the neighbours' L, U:
           //   B_k -= alpha U_{k-h} + gamma L_{k+h},   L_k <- -alpha L_{k-h},   U_k <- -gamma U_{k+h}      (6 products per level)
-          double Bi[9];
-          inv_spd3(Bm, Bi);
-          double nlo[9], nhi[9], t1[9], t2[9];
-          double alp[9], gam[9], Ln[9], Un[9];
-          cm.template both<9>(Bi, nlo, nhi, h);
+          // (ordered so that few temporaries are alive at once: the register peak of this rare step decides what the hot loop spills)
+          double alp[9], gam[9], nlo[9], nhi[9];
+          {
+            double Bi[9];
+            inv_spd3(Bm, Bi);
+            cm.template both<9>(Bi, nlo, nhi, h);
+          }
           mm3(Lm, nlo, alp);
           mm3(Um, nhi, gam);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) {   // a missing neighbour contributes nothing: masking alpha, gamma masks every product below
+            alp[e] = vlo ? alp[e] : 0.0;
+            gam[e] = vhi ? gam[e] : 0.0;
+          }
           cm.template both<9>(Um, nlo, nhi, h);
-          mm3(alp, nlo, t1);
+          {
+            double t1[9];
+            mm3(alp, nlo, t1);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Bm[e] -= t1[e];
+          }
+          double Un[9];
           mm3(gam, nhi, Un);
           cm.template both<9>(Lm, nlo, nhi, h);
-          mm3(alp, nlo, Ln);
-          mm3(gam, nhi, t2);
+          {
+            double t2[9];
+            mm3(gam, nhi, t2);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Bm[e] -= t2[e];
+          }
+          {
+            double Ln[9];
+            mm3(alp, nlo, Ln);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { Lm[e] = -Ln[e]; Um[e] = -Un[e]; }
+          }
 #pragma unroll
           for (int e = 0; e < 9; ++e) {
-            Bm[e] = Bm[e] - (vlo ? t1[e] : 0.0) - (vhi ? t2[e] : 0.0);
-            Lm[e] = vlo ? -Ln[e] : 0.0;
-            Um[e] = vhi ? -Un[e] : 0.0;
-            alp[e] = vlo ? -alp[e] : 0.0;   // stored negated: the solve is r += coef * neighbour
-            gam[e] = vhi ? -gam[e] : 0.0;
+            alp[e] = -alp[e];   // stored negated: the solve is r += coef * neighbour
+            gam[e] = -gam[e];
           }
           if (lev < NLEV - 1) {
             // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
