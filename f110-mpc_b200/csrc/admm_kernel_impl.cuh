@@ -1111,9 +1111,13 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       cm.sync();
     }
 
-    const bool last = (iter == p.max_iter);
-    const bool chk = (--ct_left == 0);
-    const bool adp = (--ar_left == 0);
+    // Plain iterations run in their own inner loop (its back edge touches none of the rare blocks around it), up to and including
+    // the next iteration that needs residuals.
+    bool last, chk, adp;
+    for (;;) {
+    last = (iter == p.max_iter);
+    chk = (--ct_left == 0);
+    adp = (--ar_left == 0);
     if (chk) ct_left = p.check_termination;
     if (adp) ar_left = ari;
     const bool info_iter = chk || adp || last;
@@ -1335,7 +1339,9 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         s.zr = zn;
       }
     }
-    if (!info_iter) { ++iter; continue; }
+    if (info_iter) break;
+    ++iter;
+    }
 
     // ---------- residuals & norms (OSQP update_info + the norms of compute_rho_estimate) -----------------------
     double n_z, n_Ax, n_Aty, n_Px;                      // unscaled (termination)
