@@ -111,9 +111,9 @@ def test_golden_vectors(pkg, name):
     np.testing.assert_array_equal(g["iters"], gd["iters"])
 
 
-def test_warm_start_sequence_matches_oracle(pkg, oracle, workloads):
+@pytest.mark.parametrize("N,B", [(30, 64), (10, 37), (5, 23), (50, 16)])   # 10, 5: several QPs share a warp (ragged last warp)
+def test_warm_start_sequence_matches_oracle(pkg, oracle, workloads, N, B):
     # reference steady state: update q / A / bounds, keep iterates and rho (mpc.cpp:83-94, 98)
-    N, B = 30, 64
     recs = workloads.tracking_batch(B, N, seed=9)
     sol = pkg.MpcSolver(pkg.default_config(N), pkg.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=1), B)
     mb = oracle.MpcBatch(oracle.default_cfg(N), oracle.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=1), B)
