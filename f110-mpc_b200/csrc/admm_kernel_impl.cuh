@@ -86,7 +86,8 @@ __device__ __forceinline__ double limit_scaling(double v) {
 // 1/sqrt(x) for x in [1e-4, 1e4] (the range limit_scaling leaves): float seed + two Newton steps, no special cases.
 // Within ~2 ulp of 1.0 / sqrt(x), which is all the Ruiz scaling vectors need.
 __device__ __forceinline__ double rsqrt_scaling(double x) {
-  double y = (double)rsqrtf((float)x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // one MUFU on the high word (about 2^-22 relative), no float round trip
   const double hx = 0.5 * x;
   double e = fma(-hx * y, y, 0.5);
   y = fma(y, e, y);
@@ -94,6 +95,16 @@ __device__ __forceinline__ double rsqrt_scaling(double x) {
   return fma(y, e, y);
 }
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return dmin(dmax(v, lo), hi); }
+// 1/x for the positive, well-scaled pivots and rho values of the factor step: MUFU seed (about 2^-20 relative) + two Newton steps
+// -> within an ulp of the quotient, without the special-case tail of a full division.
+__device__ __forceinline__ double rcp_pos(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
 
 // ---- bulk asynchronous copy (TMA) of the parameter record into shared memory ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -248,11 +259,11 @@ __device__ __forceinline__ void mm3(const double* a, const double* b, double* c)
 }
 // inverse of a symmetric positive definite 3x3 via LDL^T (reads the lower triangle)
 __device__ __forceinline__ void inv_spd3(const double* a, double* inv) {
-  const double d0 = a[0], i0 = 1.0 / d0;
+  const double d0 = a[0], i0 = rcp_pos(d0);
   const double l10 = a[3] * i0, l20 = a[6] * i0;
-  const double d1 = a[4] - l10 * a[3], i1 = 1.0 / d1;
+  const double d1 = a[4] - l10 * a[3], i1 = rcp_pos(d1);
   const double l21 = (a[7] - l20 * a[3]) * i1;
-  const double d2 = a[8] - l20 * a[6] - l21 * (a[7] - l20 * a[3]), i2 = 1.0 / d2;
+  const double d2 = a[8] - l20 * a[6] - l21 * (a[7] - l20 * a[3]), i2 = rcp_pos(d2);
   const double m10 = -l10, m20 = l10 * l21 - l20, m21 = -l21;  // L^-1 = [[1,0,0],[m10,1,0],[m20,m21,1]]
   inv[0] = i0 + m10 * m10 * i1 + m20 * m20 * i2;
   inv[1] = inv[3] = m10 * i1 + m20 * m21 * i2;
@@ -285,7 +296,7 @@ __device__ __forceinline__ void inv_spdD(const double* a, double* inv) {
 #pragma unroll
     for (int t = 0; t < j; ++t) dj -= L[D * j + t] * L[D * j + t] * dd[t];
     dd[j] = dj;
-    id[j] = 1.0 / dj;
+    id[j] = rcp_pos(dj);
 #pragma unroll
     for (int i = j + 1; i < D; ++i) {
       double v = a[D * i + j];
@@ -629,7 +640,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       const double mean = cm.rsum(psum) / (double)nvar;
       const double qinf = limit_scaling(c * cm.rmax(qn));
       const double ct = limit_scaling(dmax(mean, qinf));
-      c *= 1.0 / ct;
+      c *= rcp_pos(ct);
     }
     cinv = 1.0 / c;
     // park D, E in the scratch line: only the rho estimate, infeasibility tests and the state store read them again
@@ -821,9 +832,9 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         const double cg = scr[(SCR_CG + r) * T], cb = scr[(SCR_CB + r) * T];
         const double rg = cg < 0 ? RHO_MIN : (cg > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
         const double rb = cb < 0 ? RHO_MIN : (cb > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
-        s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = 1.0 / s.rg[r];
+        s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = rcp_pos(s.rg[r]);
         s.rb[r] = actu ? rb * scr[(SCR_WB + r) * T] : 0.0;
-        s.ib[r] = actu ? 1.0 / s.rb[r] : 0.0;
+        s.ib[r] = actu ? rcp_pos(s.rb[r]) : 0.0;
       }
       if constexpr (RATE) {
         // ---- steering-rate variant: eliminate the speed v_k only; reduced unknown s_k = (x_k, delta_k), 4x4 blocks ----
@@ -831,7 +842,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const double cr = scr[SCR_CR * T];
           const double rrb = cr < 0 ? RHO_MIN : (cr > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
           s.rr = actu ? rrb * scr[SCR_WR * T] : 0.0;
-          s.ir = actu ? 1.0 / s.rr : 0.0;
+          s.ir = actu ? rcp_pos(s.rr) : 0.0;
           const double snd[4] = {s.rd[0], s.rd[1], s.rd[2], s.rr};
           double rcv[4];
           cm.template dn<4>(snd, rcv, 1);
@@ -845,7 +856,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         double mv[3];   // R_{k+1} b_v
 #pragma unroll
         for (int i = 0; i < 3; ++i) { mv[i] = s.rdn[i] * bv[i]; wv += mv[i] * bv[i]; }
-        s.wvi = actu ? 1.0 / wv : 0.0;
+        s.wvi = actu ? rcp_pos(wv) : 0.0;
         double Rn[9];  // R~_{k+1} = diag(rdn) - (rdn.b_v)(rdn.b_v)' / w_v
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -976,7 +987,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           const double w00 = p.R[0] + s.su[0] + s.rb[0] + md.b00 * md.b00 * s.rdn[0] + md.b10 * md.b10 * s.rdn[1] + md.b20 * md.b20 * s.rdn[2];
           const double w01 = md.b20 * md.b21 * s.rdn[2];
           const double w11 = p.R[1] + s.su[1] + s.rb[1] + md.b21 * md.b21 * s.rdn[2];
-          const double idet = 1.0 / (w00 * w11 - w01 * w01);
+          const double idet = rcp_pos(w00 * w11 - w01 * w01);
           s.wi[0] = actu ? w11 * idet : 0.0;
           s.wi[1] = actu ? -w01 * idet : 0.0;
           s.wi[2] = actu ? w00 * idet : 0.0;
