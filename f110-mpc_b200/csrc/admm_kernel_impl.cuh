@@ -1278,12 +1278,11 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           for (int i = 0; i < 3; ++i) {
             const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
             double a = fma(c0.x, lo[0], r[i]);
-            double b = c1.y * hi[0];
+            a = fma(c1.y, hi[0], a);
             a = fma(c0.y, lo[1], a);
-            b = fma(c2.x, hi[1], b);
+            a = fma(c2.x, hi[1], a);
             a = fma(c1.x, lo[2], a);
-            b = fma(c2.y, hi[2], b);
-            r[i] = a + b;
+            r[i] = fma(c2.y, hi[2], a);
           }
         }
         {  // top level: single neighbour k ^ h
