@@ -1193,14 +1193,13 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
           for (int i = 0; i < 4; ++i) {
             const double2 c0 = cf[(4 * i + 0) * T], c1 = cf[(4 * i + 1) * T], c2 = cf[(4 * i + 2) * T], c3 = cf[(4 * i + 3) * T];
             double a = fma(c0.x, lo[0], r[i]);
-            double b = c2.x * hi[0];
+            a = fma(c2.x, hi[0], a);
             a = fma(c0.y, lo[1], a);
-            b = fma(c2.y, hi[1], b);
+            a = fma(c2.y, hi[1], a);
             a = fma(c1.x, lo[2], a);
-            b = fma(c3.x, hi[2], b);
+            a = fma(c3.x, hi[2], a);
             a = fma(c1.y, lo[3], a);
-            b = fma(c3.y, hi[3], b);
-            r[i] = a + b;
+            r[i] = fma(c3.y, hi[3], a);
           }
         }
         {  // top level: single neighbour k ^ h
