@@ -40,6 +40,13 @@ def main():
             np.savez_compressed(os.path.join(OUT, "qp_N%d_gap%d_eps%g.npz" % (N, gap_mode, eps)), recs=recs, x=r["x"],
                                 y=r["y"], status=r["status"], iters=r["iters"], rho_updates=r["rho_updates"],
                                 rho=r["rho"], N=N, gap_mode=gap_mode, eps=eps)
+    # --- steering-rate rows (not in the reference): the oracle's own stacking, limits that bind ---
+    for N, B, delta in ((30, 24, 0.01), (12, 16, 0.02)):
+        recs = W.tracking_batch(B, N, seed=20240950 + N)
+        mb = O.MpcBatch(O.default_cfg(N, 0, rate_delta=delta), O.default_settings(eps_abs=1e-4, eps_rel=1e-4, warm_start=0), B, 1)
+        r = mb.solve(recs)
+        np.savez_compressed(os.path.join(OUT, "qprate_N%d_delta%g.npz" % (N, delta)), recs=recs, x=r["x"], y=r["y"], status=r["status"],
+                            iters=r["iters"], N=N, rate_delta=delta, eps=1e-4)
     # --- pipeline pieces ---
     tab = O.traj_table()
     A, Bm, Cv = O.linearize(0.3, 4.5, -0.1, W.DT_F32)

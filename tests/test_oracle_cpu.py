@@ -268,3 +268,13 @@ def test_rate_rows_oracle_vs_numpy_osqp_and_kkt(oracle, workloads, N, eps):
             assert stat < 1e-3 and prim < 1e-4
             steer = r["x"][b][3 * (N + 1) + 1::2]
             assert np.abs(np.diff(np.concatenate([[recs[b, 4]], steer]))).max() <= D + 1e-4
+
+
+@pytest.mark.parametrize("name", ["qprate_N30_delta0.01.npz", "qprate_N12_delta0.02.npz"])
+def test_oracle_reproduces_rate_golden_vectors(oracle, name):
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    N, delta, eps = int(gd["N"]), float(gd["rate_delta"]), float(gd["eps"])
+    B = gd["recs"].shape[0]
+    r = oracle.MpcBatch(oracle.default_cfg(N, 0, rate_delta=delta), oracle.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B, 1).solve(gd["recs"])
+    np.testing.assert_array_equal(r["status"], gd["status"]); np.testing.assert_array_equal(r["iters"], gd["iters"])
+    np.testing.assert_allclose(r["x"], gd["x"], atol=1e-9, rtol=1e-9, equal_nan=True)

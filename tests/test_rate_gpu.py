@@ -97,3 +97,15 @@ def test_host_mpc_with_rate_limit(pkg, oracle, workloads):
     np.testing.assert_allclose(r["y"], o["y"][0], atol=1e-4, rtol=1e-4)
     assert r["y"].shape[0] == 8 * N + 5
     m.close()
+
+
+@pytest.mark.parametrize("name", ["qprate_N30_delta0.01.npz", "qprate_N12_delta0.02.npz"])
+def test_golden_rate_vectors(pkg, name):
+    # committed fixtures (scripts/make_golden.py): N = 12 runs two QPs per warp, N = 30 one
+    import os
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    N, delta, eps = int(gd["N"]), float(gd["rate_delta"]), float(gd["eps"])
+    B = gd["recs"].shape[0]
+    g = pkg.MpcSolver(pkg.default_config(N, 0, rate_delta=delta), pkg.default_settings(eps_abs=eps, eps_rel=eps, warm_start=0), B).solve_host(gd["recs"])
+    assert_solution_parity(g, dict(status=gd["status"], x=gd["x"], y=gd["y"]), N)
+    np.testing.assert_array_equal(g["iters"], gd["iters"])
