@@ -30,3 +30,24 @@ def test_reference_arm_other_ranks_are_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_bench_lines_follow_the_contract():
+    # profiles/r1_bench_product.json / _reference.json are verbatim bench.py lines from a B200; every key the driver reads is there
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prod = json.load(open(os.path.join(root, "profiles", "r1_bench_product.json")))
+    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in prod, k
+    assert prod["metric"] == ref["metric"] and prod["unit"] == ref["unit"] and prod["config"]["workload"] == ref["config"]["workload"]
+    assert prod["dtype"] == "f64" and prod["data"] == "synthetic" and prod["vs_baseline"] is None and prod["higher_is_better"] is True
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(prod["e2e"])
+    assert prod["e2e"]["h2d_bytes_per_step"] > 0 and prod["e2e"]["d2h_bytes_per_step"] > 0 and prod["e2e"]["value"] < prod["value"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(prod["roofline"])
+    assert abs(prod["roofline"]["frac"] - prod["roofline"]["achieved"] / prod["roofline"]["peak"]) < 1e-9
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(prod["cpu_baseline"]) and prod["cpu_baseline"]["kind"] == "port"
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(prod["clocks"])
+    assert prod["gpu_launches"] >= prod["steps"] and prod["warmup"] >= 3
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
