@@ -1643,10 +1643,9 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     // The 4x4 variant runs at the register cap with a few hundred bytes of spill per thread.  With the largest shared-memory
     // carve-out (5 CTAs per SM) only 28 KB of L1 is left and three quarters of the spill reloads miss it; 4 CTAs inside a
     // 164 KB carve-out leave 92 KB of L1, which holds them (ncu: profiles/r1f_rate_kernel_ncu_summary.txt).
-    static int carve = -1;
-    if (const char* ev = std::getenv("F110_RATE_CARVEOUT")) carve = std::atoi(ev);   // tuning override (percent)
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         carve >= 0 ? carve : 72);
+    int carve = 72;
+    if (const char* ev = std::getenv("F110_RATE_CARVEOUT")) { const int v = std::atoi(ev); if (v >= 0 && v <= 100) carve = v; }   // tuning override (percent)
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
   }
   admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
