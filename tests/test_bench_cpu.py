@@ -51,3 +51,30 @@ def test_committed_bench_lines_follow_the_contract():
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(prod["clocks"])
     assert prod["gpu_launches"] >= prod["steps"] and prod["warmup"] >= 3
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
+
+
+def test_config4_batch_definition_and_sharding():
+    # BASELINE config 4: 7 lanes x 20 mini-paths x 64 scenarios = 8960 QPs, scenario-major so whole scenarios shard per rank
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    W = importlib.import_module("f110-mpc_b200.workloads")
+    SH = importlib.import_module("f110-mpc_b200.sharding")
+    recs = bench.config4_records(W)
+    assert recs.shape == (8960, 11 + 3 * 30)
+    assert (recs[:, 3] == 4.5).all() and (recs[:, 4] == 0.0).all()
+    per_sc = 7 * 20
+    # within a scenario: 7 distinct start states (lanes), each repeated for its 20 paths; references differ per path
+    sc0 = recs[:per_sc]
+    assert len({tuple(r[:3]) for r in sc0}) == 7
+    assert (sc0[:20, :3] == sc0[0, :3]).all() and len({tuple(r[11:14 + 3 * 28]) for r in sc0[:20]}) == 20
+    lane_step = sc0[20, :2] - sc0[0, :2]
+    assert abs(float((lane_step ** 2).sum()) ** 0.5 - 0.25) < 1e-9          # lanes 0.25 m apart along the left normal
+    covered = []
+    for world in (1, 2, 4, 8):
+        for rank in range(world):
+            (s_lo, s_hi), (q_lo, q_hi) = SH.shard_by_scenario(64, per_sc, world, rank)
+            assert (q_lo, q_hi) == (s_lo * per_sc, s_hi * per_sc) and s_hi - s_lo == 64 // world
+            if world == 8:
+                covered += list(range(q_lo, q_hi))
+    assert covered == list(range(8960))
