@@ -1235,12 +1235,12 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       if (!finished && last) { status = ST_MAX_ITER; finished = true; }
       // OSQP leaves the loop BEFORE adapt_rho only when the in-loop exact check fires; the after-loop checks
       // (iteration max_iter) come after that iteration's adapt_rho
-      if (chk && exact_hit) {
-        if constexpr (QPW == 1) break;
-        if (!done) { store(); done = true; }
+      if constexpr (QPW == 1) {
+        if (chk && exact_hit) break;
       }
     }
-    if (adp) {
+    // (several QPs per warp: a QP whose in-loop check fired skips adapt_rho like OSQP's break does, and is stored below)
+    if (adp && (QPW == 1 || !(chk && exact_hit))) {
       // compute_rho_estimate on the scaled residuals, adapt_rho
       const double pr = s_pri / (dmax(s_z, s_Ax) + 1e-10);
       const double dr = s_dua / (dmax(scr[SCR_SNQ * T], dmax(s_Aty, s_Px)) + 1e-10);
