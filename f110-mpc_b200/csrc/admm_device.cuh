@@ -101,6 +101,79 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
       : "memory");
 }
 
+// ---- tensor memory (TMEM) as a per-lane store for the PCR multipliers ---------------------------------------------
+// The multipliers are written once per factor step and read once per ADMM iteration, by the lane that wrote them, and nothing
+// else touches them: shared memory is the wrong place for that — at 128 B/clk/SM it was the round-1 kernel's binding resource
+// (44 LDS.128 = 176 wavefronts per warp-iteration).  Tensor memory is 128 lanes x 512 32-bit columns per SM with its own read
+// path (tcgen05.ld, measured 64 B/clk per SM sub-partition, scripts/ubench/tmem_bw.cu); shape .32x32b gives lane i of warp w
+// the row 32 (w % 4) + i, so one warp of a four-warp CTA owns a quarter of the CTA's columns x 32 rows: a private strip of
+// `cols` x 4 bytes per lane.  No tensor-core instruction is involved.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {   // one full warp; cols a power of two >= 32
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t cols) {          // the warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_pair(uint32_t addr, double a, double b) {   // one 16-byte pair -> 4 columns
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(__double2loint(a)), "r"(__double2hiint(a)),
+               "r"(__double2loint(b)), "r"(__double2hiint(b))
+               : "memory");
+}
+// Asynchronous loads of NP consecutive pairs (NP = 1, 2, 4 or 8 -> .x4 / .x8 / .x16 / .x32).  The registers are valid only after
+// tmem_wait_ld(); tmem_tie() then makes every consumer depend on that wait (the compiler knows nothing about the asynchrony).
+__device__ __forceinline__ void tmem_ld1(uint32_t addr, double2* o) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+  o[0] = make_double2(__hiloint2double((int)r[1], (int)r[0]), __hiloint2double((int)r[3], (int)r[2]));
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t addr, double2* o) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
+#pragma unroll
+  for (int j = 0; j < 2; ++j) o[j] = make_double2(__hiloint2double((int)r[4 * j + 1], (int)r[4 * j]), __hiloint2double((int)r[4 * j + 3], (int)r[4 * j + 2]));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t addr, double2* o) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = make_double2(__hiloint2double((int)r[4 * j + 1], (int)r[4 * j]), __hiloint2double((int)r[4 * j + 3], (int)r[4 * j + 2]));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, double2* o) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(addr));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = make_double2(__hiloint2double((int)r[4 * j + 1], (int)r[4 * j]), __hiloint2double((int)r[4 * j + 3], (int)r[4 * j + 2]));
+}
+template <int NP>
+__device__ __forceinline__ void tmem_ld_pairs(uint32_t addr, double2* o) {   // pair j sits in columns 4 j .. 4 j + 3
+  if constexpr (NP >= 8) { tmem_ld8(addr, o); tmem_ld_pairs<NP - 8>(addr + 32, o + 8); }
+  else if constexpr (NP >= 4) { tmem_ld4(addr, o); tmem_ld_pairs<NP - 4>(addr + 16, o + 4); }
+  else if constexpr (NP >= 2) { tmem_ld2(addr, o); tmem_ld_pairs<NP - 2>(addr + 8, o + 2); }
+  else if constexpr (NP == 1) { tmem_ld1(addr, o); }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int NP>
+__device__ __forceinline__ void tmem_tie(double2* v) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) asm volatile("" : "+d"(v[j].x), "+d"(v[j].y));
+}
+
 // ---- cross-stage communication ------------------------------------------------------------------------------
 // One stage per thread.  WPQ = warps per QP: 1 -> everything is a warp shuffle; 2 or 4 (horizons 32..127) -> the
 // CTA is the QP, values travel through a double-buffered shared-memory exchange with one barrier per exchange

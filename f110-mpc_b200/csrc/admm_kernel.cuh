@@ -16,6 +16,8 @@ namespace f110 {
 // admm_kernel_impl.cuh), one column per stage
 constexpr int SCR_ROWS_ALLOC = 44;                       // rows of the per-QP scratch line (37 used, 41 with steering-rate rows)
 constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // line length at 4 warps per QP (horizon 64..127); 32 / 64 columns below
+constexpr int TM_COLS = 256;                             // tensor-memory columns one persistent CTA of the TMEM variant allocates (two CTAs per SM own all 512)
+constexpr int WORK_SLOTS = 64;                           // work-counter pairs a handle cycles through (one per launch in flight) + one for the captured B = 1 graph
 
 struct KParams {
   // problem family (f110_mpc_config)
@@ -47,6 +49,7 @@ struct KParams {
   double* scratch;    // [B][SCRATCH_DOUBLES]
   double* mult_global;  // [B][28 * 128] top-level PCR multipliers of multi-warp QPs (horizon >= 32; used from 64 up), else null
   double* scratch_dummy;  // 4 more lines: lane groups without a QP (several short-horizon QPs per warp, odd batch) scribble here
+  int* work;              // tensor-memory variant: {next QP, warps run dry}, both 0 at launch; the kernel re-arms them itself
 };
 
 // constraint rows: dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N | steering rate N (optional)

@@ -38,21 +38,25 @@
 
 namespace f110 {
 
-// One CTA = one QP = WPQ warps, one horizon stage per thread (stage k = threadIdx.x).
+// One unit of work = one QP on WPQ warps, one horizon stage per thread (stage k = tid) — or QPW short-horizon QPs side by side in one warp.
 // NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == lanes of the QP): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
 // QPW = QPs per warp (WPQ == 1 only): short horizons (N + 1 <= 16 / 8) put 2 / 4 QPs side by side in one warp, each on its own
 // G = 32 / QPW lane segment.  The QPs of a warp iterate in lock step; one that terminates stores its result at once and idles
 // (keeps iterating, results discarded) until its neighbours are done too.
-// (255 registers / 8 warps per SM is the measured optimum: capping at 224 for 9 warps costs 17 % in spills)
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW>
-__global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+// TM = the tensor-memory variant (one-warp QPs, horizons 16..31): the PCR multipliers live in the warp's TMEM strip (`tmb`) instead
+// of shared memory, the per-QP scratch line lives in shared memory instead of global memory, and the caller is a persistent
+// four-warp CTA whose warps fetch QPs from a work counter (admm_kernel_tm below).  `unit` = blockIdx.x for the one-CTA-per-unit
+// kernels, the fetched index for the persistent one; `smem_all` = this unit's shared-memory region; `tid` = thread within the unit.
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM>
+__device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
+                                           const int tid, [[maybe_unused]] const uint32_t rec_parity) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
-  extern __shared__ __align__(16) double smem_all[];
-  constexpr int T = 32 * WPQ;              // threads per CTA = columns of the shared-memory and scratch layouts
+  static_assert(!TM || (WPQ == 1 && QPW == 1 && !RATE), "tensor-memory variant: one warp per QP, base row set");
+  constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
   constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
-  const int k = QPW == 1 ? (int)threadIdx.x : (int)(threadIdx.x & (G - 1));                      // stage
-  const int qp_raw = QPW == 1 ? (int)blockIdx.x : (int)(blockIdx.x * QPW + threadIdx.x / G);
+  const int k = QPW == 1 ? tid : (tid & (G - 1));                      // stage
+  const int qp_raw = QPW == 1 ? unit : (unit * QPW + tid / G);
   // a warp's trailing groups may have no QP: they shadow the batch's last record, use a dummy scratch line and never store
   const bool live = QPW == 1 || qp_raw < p.B;
   const int qp = live ? qp_raw : p.B - 1;
@@ -69,13 +73,17 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   constexpr int GTOP = GL == 2 ? 9 : 0;            // where the top level starts in it
   constexpr int SM_PAIRS = NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
   constexpr int FINAL_PAIR = SM_PAIRS - 3;
-  double2* sm_pair = reinterpret_cast<double2*>(smem_all) + threadIdx.x;
-  [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)blockIdx.x * (GLP * T) + threadIdx.x : nullptr;
+  static_assert(!TM || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
+  [[maybe_unused]] double2* sm_pair = reinterpret_cast<double2*>(smem_all) + tid;
+  [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)unit * (GLP * T) + tid : nullptr;
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
-  constexpr int SM_DOUBLES = RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS;
-  Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, threadIdx.x);
-  double* scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(threadIdx.x / G) * (SCR_ROWS_ALLOC * T)) + k;
+  constexpr int SM_DOUBLES = TM ? 0 : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
+  Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, tid);
+  // scratch line: global memory (L2), or — tensor-memory variant — the shared memory the multipliers no longer occupy
+  double* scr;
+  if constexpr (TM) scr = smem_all + k;
+  else scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(tid / G) * (SCR_ROWS_ALLOC * T)) + k;
 
   const int N = p.N;
   const bool act = k <= N;         // lane owns a stage
@@ -91,7 +99,13 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
     // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
     // is a shared-memory read
     double* rec_sm = smem_all + p.rec_smem_offset;
-    if constexpr (QPW == 1) {
+    if constexpr (TM) {
+      // persistent warp: the mbarrier was initialised once by the caller, its phase alternates from QP to QP
+      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
+      if (k == 0) bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
+      mbar_wait(smem_u32(bar), rec_parity);
+      rec = rec_sm;
+    } else if constexpr (QPW == 1) {
       uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
       if (k == 0) {
         mbar_init(smem_u32(bar), 1);
@@ -102,10 +116,10 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
       rec = rec_sm;
     } else {
       // the warp's records are consecutive rows of the batch: one bulk copy covers them all
-      const int first = blockIdx.x * QPW;
+      const int first = unit * QPW;
       const int nq = (p.B - first < QPW) ? p.B - first : QPW;
       uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + (QPW - 1) * p.stride + p.rec_bulk_bytes / 8);
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         mbar_init(smem_u32(bar), 1);
         bulk_copy_g2s(smem_u32(rec_sm), p.recs + (size_t)first * p.stride, (uint32_t)((nq - 1) * p.stride * 8 + p.rec_bulk_bytes), smem_u32(bar));
       }
@@ -739,13 +753,20 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             gam[e] = -gam[e];
           }
           if (lev < NLEV - 1) {
-            // 9 pairs per level, each pair one 16-byte shared-memory word per stage: (a0,a1) (a2,g0) (g1,g2) per row
+            // 9 pairs per level, each pair one 16-byte word per stage: (a0,a1) (a2,g0) (g1,g2) per row
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-              double2* dst = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
-              dst[(3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
-              dst[(3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
-              dst[(3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+              if constexpr (TM) {
+                const uint32_t dst = tmb + 4 * (lev * 9 + 3 * i);
+                tmem_st_pair(dst, alp[3 * i], alp[3 * i + 1]);
+                tmem_st_pair(dst + 4, alp[3 * i + 2], gam[3 * i]);
+                tmem_st_pair(dst + 8, gam[3 * i + 1], gam[3 * i + 2]);
+              } else {
+                double2* dst = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+                dst[(3 * i + 0) * T] = make_double2(alp[3 * i], alp[3 * i + 1]);
+                dst[(3 * i + 1) * T] = make_double2(alp[3 * i + 2], gam[3 * i]);
+                dst[(3 * i + 2) * T] = make_double2(gam[3 * i + 1], gam[3 * i + 2]);
+              }
             }
           } else {
             // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
@@ -755,17 +776,27 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
             one[9] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) (TOPG ? gl_pair + GTOP * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            for (int q = 0; q < 5; ++q) {
+              if constexpr (TM) tmem_st_pair(tmb + 4 * (lev * 9 + q), one[2 * q], one[2 * q + 1]);
+              else (TOPG ? gl_pair + GTOP * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            }
           }
         }
         {
           double Bi[9];
           inv_spd3(Bm, Bi);
-          sm_pair[(FINAL_PAIR + 0) * T] = make_double2(Bi[0], Bi[1]);
-          sm_pair[(FINAL_PAIR + 1) * T] = make_double2(Bi[2], Bi[4]);
-          sm_pair[(FINAL_PAIR + 2) * T] = make_double2(Bi[5], Bi[8]);
+          if constexpr (TM) {
+            tmem_st_pair(tmb + 4 * (FINAL_PAIR + 0), Bi[0], Bi[1]);
+            tmem_st_pair(tmb + 4 * (FINAL_PAIR + 1), Bi[2], Bi[4]);
+            tmem_st_pair(tmb + 4 * (FINAL_PAIR + 2), Bi[5], Bi[8]);
+          } else {
+            sm_pair[(FINAL_PAIR + 0) * T] = make_double2(Bi[0], Bi[1]);
+            sm_pair[(FINAL_PAIR + 1) * T] = make_double2(Bi[2], Bi[4]);
+            sm_pair[(FINAL_PAIR + 2) * T] = make_double2(Bi[5], Bi[8]);
+          }
         }
       }
+      if constexpr (TM) tmem_wait_st();   // the iteration below reads the strip back
       cm.sync();
     }
 
@@ -789,6 +820,12 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
 
     // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
     {
+      // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
+      [[maybe_unused]] double2 mc[9];
+      if constexpr (TM) {
+        if constexpr (NLEV > 1) tmem_ld_pairs<9>(tmb, mc);
+        else { tmem_ld_pairs<8>(tmb, mc); mc[8] = make_double2(0.0, 0.0); }
+      }
       // s = rho (z - y/rho) = rho z - y per row; right-hand side of the condensed system
       double sd[3], sg[2], sb[2];
 #pragma unroll
@@ -913,16 +950,24 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
         cm.template up<3>(f, fp, 1);
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
-        // PCR: apply the stored multipliers level by level (fully unrolled, constant shared-memory offsets)
+        // PCR: apply the stored multipliers level by level (fully unrolled, constant offsets)
+        if constexpr (TM) { tmem_wait_ld(); tmem_tie<9>(mc); }
 #pragma unroll
         for (int lev = 0; lev < NLEV - 1; ++lev) {
           const int h = 1 << lev;
           double lo[3], hi[3];
+          [[maybe_unused]] double2 nx[9];
+          if constexpr (TM) {   // next level (or: one-sided top level + final inverse, 8 pairs in a row) while this one is applied
+            if (lev + 1 < NLEV - 1) tmem_ld_pairs<9>(tmb + 36 * (lev + 1), nx);
+            else { tmem_ld_pairs<8>(tmb + 36 * (NLEV - 1), nx); nx[8] = make_double2(0.0, 0.0); }
+          }
           cm.template both<3>(r, lo, hi, h);
-          const double2* cf = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+          [[maybe_unused]] const double2* cf = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            const double2 c0 = cf[(3 * i + 0) * T], c1 = cf[(3 * i + 1) * T], c2 = cf[(3 * i + 2) * T];
+            double2 c0, c1, c2;
+            if constexpr (TM) { c0 = mc[3 * i]; c1 = mc[3 * i + 1]; c2 = mc[3 * i + 2]; }
+            else { c0 = cf[(3 * i + 0) * T]; c1 = cf[(3 * i + 1) * T]; c2 = cf[(3 * i + 2) * T]; }
             double a = fma(c0.x, lo[0], r[i]);
             a = fma(c1.y, hi[0], a);
             a = fma(c0.y, lo[1], a);
@@ -930,19 +975,31 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
             a = fma(c1.x, lo[2], a);
             r[i] = fma(c2.y, hi[2], a);
           }
+          if constexpr (TM) {
+            tmem_wait_ld();
+            tmem_tie<9>(nx);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) mc[j] = nx[j];
+          }
         }
         {  // top level: single neighbour k ^ h
           constexpr int h = 1 << (NLEV - 1);
           double nb[3];
           cm.template xr<3>(r, nb, h);
-          const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
-          const double2 c0 = cf[0 * T], c1 = cf[1 * T], c2 = cf[2 * T], c3 = cf[3 * T], c4 = cf[4 * T];
+          double2 c0, c1, c2, c3, c4;
+          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; }
+          else {
+            const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
+            c0 = cf[0 * T]; c1 = cf[1 * T]; c2 = cf[2 * T]; c3 = cf[3 * T]; c4 = cf[4 * T];
+          }
           r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
           r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
           r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
         }
         {
-          const double2 q0 = sm_pair[(FINAL_PAIR + 0) * T], q1 = sm_pair[(FINAL_PAIR + 1) * T], q2 = sm_pair[(FINAL_PAIR + 2) * T];
+          double2 q0, q1, q2;
+          if constexpr (TM) { q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
+          else { q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T]; }
           const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
           xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
           xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
@@ -1264,6 +1321,51 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCK
   if constexpr (QPW == 1) store();
 }
 
+// One CTA per unit: a QP on WPQ warps (horizons 32..127, steering-rate rows), or QPW short-horizon QPs in one warp.
+// (255 registers / 8 warps per SM is the measured optimum: capping at 224 for 9 warps costs 17 % in spills)
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW>
+__global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+  extern __shared__ __align__(16) double smem_all[];
+  solve_unit<NLEV, WPQ, LASTFULL, RATE, QPW, false>(p, (int)blockIdx.x, smem_all, 0u, (int)threadIdx.x, 0u);
+}
+
+// Tensor-memory variant (horizons 16..31, base row set): persistent CTAs of four warps, two per SM.  Each CTA allocates TM_COLS
+// columns of tensor memory once; each warp owns a 32-row strip of it for its multipliers and fetches QPs from a work counter until
+// the batch is exhausted, so warps whose QPs stop after 25 iterations take up the slack of those that need 75.  Per-warp shared
+// memory: the QP's scratch line and the TMA landing zone of its parameter record.
+template <int NLEV, bool LASTFULL>
+__global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
+  extern __shared__ __align__(16) double smem_all[];
+  __shared__ uint32_t tmem_base;
+  const int w = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  if (w == 0) tmem_alloc(&tmem_base, TM_COLS);
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
+  double* const smem_w = smem_all + (size_t)w * (SCR_ROWS_ALLOC * 32 + p.rec_bulk_bytes / 8 + 2);
+  if (p.rec_bulk_bytes && lane == 0) mbar_init(smem_u32(smem_w + p.rec_smem_offset + p.rec_bulk_bytes / 8), 1);
+  __syncwarp();
+  uint32_t parity = 0;
+  for (;;) {
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(p.work, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= p.B) break;
+    solve_unit<NLEV, 1, LASTFULL, false, 1, true>(p, unit, smem_w, tmb, lane, parity);
+    if (p.rec_bulk_bytes) parity ^= 1u;
+    __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
+  }
+  // the last warp to run dry re-arms the counter pair for the next launch that uses it
+  if (lane == 0) {
+    const int finished = atomicAdd(p.work + 1, 1);
+    if (finished == (int)gridDim.x * 4 - 1) { p.work[0] = 0; p.work[1] = 0; }
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (w == 0) tmem_free(tmem_base, TM_COLS);
+}
+
 template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
@@ -1296,6 +1398,40 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Launch of the tensor-memory variant: at most two CTAs per SM (they own the SM's 512 tensor-memory columns between them),
+// fewer when the batch has fewer than 8 QPs per SM.
+template <int NLEV, bool LASTFULL>
+static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
+  KParams p = pin;
+  if (!p.work) return cudaErrorInvalidValue;
+  static int sms_of[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!sms_of[dev]) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    sms_of[dev] = n;
+  }
+  const int rec_even = (11 + 3 * p.N + 1) & ~1;
+  p.rec_bulk_bytes = 0;
+  p.rec_smem_offset = SCR_ROWS_ALLOC * 32;
+  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) p.rec_bulk_bytes = rec_even * (int)sizeof(double);
+  const size_t smem = 4 * (size_t)(SCR_ROWS_ALLOC * 32 + p.rec_bulk_bytes / 8 + 2) * sizeof(double);
+  static bool attr_set[64] = {false};
+  if (!attr_set[dev]) {
+    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  int grid = (p.B + 3) / 4;
+  if (grid > 2 * sms_of[dev]) grid = 2 * sms_of[dev];
+  admm_kernel_tm<NLEV, LASTFULL><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

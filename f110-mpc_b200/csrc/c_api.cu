@@ -33,6 +33,8 @@ struct f110_mpc_solver {
   double* d_state = nullptr;    // warm-start slots
   double* d_scratch = nullptr;  // per-QP scratch lines (scaling vectors, previous iterate)
   double* d_mult = nullptr;     // per-QP top-level multipliers of four-warp QPs (horizon >= 64)
+  int* d_work = nullptr;        // work-counter pairs of the persistent tensor-memory kernel: WORK_SLOTS round-robin + 1 for the B = 1 graph
+  unsigned work_seq = 0;
   // staging for the host-buffer entry: one device block [u0 | status | iters | x | y] so results come back in
   // one copy, plus a small pinned mirror used for latency-critical small batches
   double* d_recs = nullptr;
@@ -128,11 +130,17 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   const int N = cfg->horizon;
   const size_t ssz = (size_t)max_batch * f110::state_doubles(N, cfg->rate_rows) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
-  if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, ssz);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)(max_batch + 4) * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
   if (e == cudaSuccess && cfg->horizon >= (ADMM_W2_GLOBAL_LEVELS > 0 ? 32 : 64) && !cfg->rate_rows)
     e = cudaMalloc(&s->d_mult, (size_t)max_batch * 28 * 128 * sizeof(double));
+  const size_t wsz = (size_t)(f110::WORK_SLOTS + 1) * 2 * sizeof(int);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_work, wsz);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_work, 0, wsz, s->stream);
+  // the slots are cleared on the handle's own (non-blocking) stream and the clear is waited for: a memset on the legacy default
+  // stream would not be ordered against solves on s->stream or on a caller's stream
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_state, 0, ssz, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) {
     f110_mpc_destroy(s);
     return cuda_fail(e, "f110_mpc_create: device allocation");
@@ -147,6 +155,7 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   cudaFree(s->d_state);
   cudaFree(s->d_scratch);
   cudaFree(s->d_mult);
+  cudaFree(s->d_work);
   cudaFree(s->d_recs); cudaFree(s->d_out);
   s->cyc.release();
   cudaFree(s->cyc_stage);
@@ -163,7 +172,10 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
 int f110_mpc_reset(f110_mpc_solver* s) {
   if (!s) return fail(F110_ERR_ARG, "f110_mpc_reset: null solver");
   CUDA_TRY(cudaSetDevice(s->device));
-  CUDA_TRY(cudaMemset(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) * sizeof(double)));
+  // Ordered after everything already queued on the handle's stream, and complete when this returns.  Work the caller queued on
+  // its OWN streams (solve_device / cycle_device) is not waited for: synchronise those before calling reset.
+  CUDA_TRY(cudaMemsetAsync(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) * sizeof(double), s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
   return F110_OK;
 }
 
@@ -205,6 +217,11 @@ static int solve_device_range(f110_mpc_solver* s, int slot0, int count, const do
   p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
   p.scratch_dummy = s->d_scratch + (size_t)s->max_batch * f110::SCR_ROWS_ALLOC * T;
   p.mult_global = s->d_mult ? s->d_mult + (size_t)slot0 * 28 * T : nullptr;
+  // each launch gets its own counter pair (launches of one handle may overlap on different streams); the kernel leaves it zeroed.
+  // The captured single-QP graph replays with a fixed pointer, so it owns the extra slot.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing((cudaStream_t)cuda_stream, &cap);
+  p.work = s->d_work + 2 * (cap == cudaStreamCaptureStatusActive ? f110::WORK_SLOTS : (int)(s->work_seq++ % f110::WORK_SLOTS));
   CUDA_TRY(cudaSetDevice(s->device));
   int launched = 0;
   cudaError_t e = f110::launch_admm(p, (cudaStream_t)cuda_stream, &launched);
@@ -254,7 +271,8 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
     // latency path: records staged through pinned memory (true async DMA)
     double* hp = reinterpret_cast<double*>(s->h_pin);
     for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rdp, recs + (size_t)b * rec_stride, rd * sizeof(double));
-    if (count == 1 && !s->cfg.rate_rows && N <= 31) {   // (longer horizons set a function attribute at launch: not captured)
+    if (count == 1 && !s->cfg.rate_rows && N <= 31 && !s->d_packed_next) {   // (longer horizons set a function attribute at launch: not captured;
+                                                                          //  a packed-output request is per call and must not be frozen into the graph)
       // one QP (the reference's own call pattern, mpc.cpp:69-143): copy-in, solve and copy-out are replayed as one captured graph,
       // one driver call instead of three.  Every address and size in it is fixed for the handle's lifetime.
       unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rdp * sizeof(double);
@@ -421,7 +439,7 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
   CUDA_TRY(cudaSetDevice(s->device));
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_host: QP count exceeds max_batch");
-  // One staging block on the device (grown on demand): [inputs | table | waypoints | outputs].  The outputs are contiguous so
+  // One staging block on the device (grown on demand): [table | waypoints | inputs | outputs].  The outputs are contiguous so
   // they come back in ONE copy (into a pinned mirror, then scattered to the caller's arrays).  The mini-path table and the
   // raceline are start-up constants in the reference (project.cpp:34-37): they are uploaded only when their bytes change.
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -442,12 +460,14 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
     CUDA_TRY(cudaHostAlloc(&s->cyc_pin, b_out, cudaHostAllocDefault));
     s->cyc_pin_bytes = b_out;
   }
+  // The constant tables come FIRST: their device addresses depend only on (paths, samples, n_wp), which the content hash covers,
+  // so a later call with fewer scenes or beams on the same handle finds them where they were uploaded.
   unsigned char* q = s->cyc_stage;
+  double* d_tab = (double*)q; q += b_tab;
+  float* d_wp = (float*)q; q += b_wp;
   double* d_pose = (double*)q; q += b_pose;
   float* d_rng = (float*)q; q += b_rng;
   double* d_prev = (double*)q; q += b_prev;
-  double* d_tab = (double*)q; q += b_tab;
-  float* d_wp = (float*)q; q += b_wp;
   unsigned char* d_out = q;
   cudaStream_t st = s->stream;
   if (!s->stream2) {

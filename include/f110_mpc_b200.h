@@ -121,7 +121,10 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
                           double* d_y, double* d_u0, int32_t* d_status, int32_t* d_iters,
                           int32_t* d_rho_updates, double* d_info, void* cuda_stream);
 
-/* Forget the warm-start state of every slot (next solve starts from x = z = y = 0, rho = settings.rho). */
+/* Forget the warm-start state of every slot (next solve starts from x = z = y = 0, rho = settings.rho).
+ * Ordering: the clear is queued on the handle's internal stream — i.e. after every f110_mpc_solve_host / f110_cycle_host call
+ * made so far — and has completed when the call returns.  Solves the caller queued on its OWN streams through
+ * f110_mpc_solve_device / f110_cycle_device are not waited for: synchronise those streams before calling reset. */
 int f110_mpc_reset(f110_mpc_solver* s);
 /* Multi-GPU helper: the NEXT f110_mpc_solve_device call also writes count x 4 doubles
  * (u0_v, u0_steer, status, iters) to d_packed — the row each rank contributes to the final gather of the
