@@ -396,15 +396,17 @@ struct Stage {
   double qx[3];            // -Q ref_k                                                 (mpc.cpp:225,228)
   // iterates (unscaled)
   double x[3], u[2];
-  double zd[3], zg[2], zb[2];
+  double zg[2], zb[2];      // (z of the dynamics rows is their right-hand side bd; the first iteration's value sits in the scratch line)
   double yd[3], yg[2], yb[2];
   // metric
   double sx[3], su[2];                 // sigma_j
   double rd[3], rg[2], rb[2];          // rho_i
+  double rda[3];                       // alpha * rho_i of the dynamics rows
   double ig[2], ib[2];                 // 1 / rho_i (inequality rows only; equality rows project to l = u)
   // input elimination
   double wi[3];            // inverse of W_k = R + Sigma_u + rho_box + B' R_{k+1} B   (00, 01, 11)
   double rdn[3];           // rho of the NEXT stage's dynamics rows
+  double rbm[4];           // R_{k+1} B: (rdn0 b00, rdn1 b10, rdn2 b20, rdn2 b21)
 };
 
 // What the steering-rate variant adds to a lane (empty otherwise).
@@ -428,7 +430,8 @@ constexpr int SCR_WD = 24, SCR_WG = 27, SCR_WB = 29;    // e_i^2 / c per row: rh
 constexpr int SCR_CG = 31, SCR_CB = 33;                 // row class codes of the gap / box rows (factor step only)
 constexpr int SCR_NQ = 35, SCR_SNQ = 36;                // ||q||_inf unscaled / scaled (termination checks only)
 constexpr int SCR_ER = 37, SCR_WR = 38, SCR_CR = 39, SCR_PYR = 40;   // steering-rate row: E, e^2/c, class, previous y
-constexpr int SCR_ROWS = 41;
+constexpr int SCR_ZD = 41;                              // z of the dynamics rows before the first iteration
+constexpr int SCR_ROWS = 44;
 static_assert(SCR_ROWS <= SCR_ROWS_ALLOC, "scratch line too short");
 
 }  // namespace

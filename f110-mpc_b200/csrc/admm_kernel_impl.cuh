@@ -32,6 +32,7 @@
 // multiplied by a zero multiplier), so no branch in the iteration depends on the lane.
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 
 #include "admm_kernel.cuh"
 #include "admm_device.cuh"
@@ -346,7 +347,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { s.x[j] = 0; s.zd[j] = 0; s.yd[j] = 0; }
+  for (int j = 0; j < 3; ++j) { s.x[j] = 0; s.yd[j] = 0; }
+  // z of the dynamics rows is their right-hand side after the first projection (l = u); only a solve's FIRST iteration sees anything
+  // else (0 on a cold start, the slot's value on a warm start), and it reads that from the scratch line
+  double zd0[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < 2; ++j) { s.u[j] = 0; s.zg[j] = 0; s.zb[j] = 0; s.yg[j] = 0; s.yb[j] = 0; }
   if constexpr (RATE) { s.zr = 0; s.yr = 0; }
@@ -364,7 +368,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       for (int j = 0; j < 3; ++j) {
         const double e = scr[(SCR_ED + j) * T];
         s.x[j] = scr[(SCR_DX + j) * T] * sx_[3 * k + j];
-        s.zd[j] = sz_[3 * k + j] / e;
+        zd0[j] = sz_[3 * k + j] / e;
         s.yd[j] = e * sy_[3 * k + j] * cinv;
       }
 #pragma unroll
@@ -389,6 +393,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       }
     }
   }
+
+#pragma unroll
+  for (int j = 0; j < 3; ++j) scr[(SCR_ZD + j) * T] = zd0[j];
+  bool first_iter = true;   // uniform over the warp (QPs that share a warp start together)
 
   // ---------------- main loop (OSQP osqp_solve); factor / update_info / check each have ONE call site ----------
   int status = ST_UNSOLVED;
@@ -454,7 +462,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         for (int j = 0; j < 3; ++j) {
           const double e = scr[(SCR_ED + j) * T];
           sx_[3 * k + j] = has_sol ? s.x[j] / scr[(SCR_DX + j) * T] : 0.0;
-          sz_[3 * k + j] = has_sol ? e * s.zd[j] : 0.0;
+          sz_[3 * k + j] = has_sol ? e * s.bd[j] : 0.0;   // z = l = u on the dynamics rows
           sy_[3 * k + j] = has_sol ? c * s.yd[j] / e : 0.0;
         }
 #pragma unroll
@@ -482,12 +490,254 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     }
   };
 
+  // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
+  // A solve's FIRST iteration is its own instantiation: it alone sees a z on the dynamics rows that is not their right-hand side
+  // (0 on a cold start, the slot's value on a warm start; read from the scratch line).  Every later iteration uses z = b.
+  auto iterate = [&](auto first_c) {
+    constexpr bool FIRST = decltype(first_c)::value;
+      // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
+      [[maybe_unused]] double2 mc[9];
+      if constexpr (TM) {
+        if constexpr (NLEV > 1) tmem_ld_pairs<9>(tmb, mc);
+        else { tmem_ld_pairs<8>(tmb, mc); mc[8] = make_double2(0.0, 0.0); }
+      }
+      // s = rho (z - y/rho) = rho z - y per row; right-hand side of the condensed system
+      double sd[3], sg[2], sb[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sd[i] = s.rd[i] * (FIRST ? scr[(SCR_ZD + i) * T] : s.bd[i]) - s.yd[i];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
+      double xt[3], ut[2], ztd[3];
+      [[maybe_unused]] double ztr = 0.0;
+      // 1 where the stage has a predecessor: values shuffled in from stage k-1 enter through an FMA with this factor (exact: the
+      // factor is 0 or 1), one select instead of two per masked value
+      const double hm = hasp ? 1.0 : 0.0;
+      if constexpr (RATE) {
+        const double sr = s.rr * s.zr - s.yr;   // 0 on stages without an input (rho = 0, y = 0)
+        double sdn[3], srn;
+        {
+          const double snd[4] = {sd[0], sd[1], sd[2], sr};
+          double rcv[4];
+          cm.template dn<4>(snd, rcv, 1);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sdn[i] = (LASTFULL && !actu) ? 0.0 : rcv[i];
+          srn = rcv[3];
+        }
+        double gx[3], t3[3], t2[2];
+        At_mul(md, sdn, t3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
+        Bt_mul(md, sdn, t2);
+        const double gv = (s.su[0] * s.u[0] - qu[0] + sb[0]) + t2[0];
+        double gd = (s.su[1] * s.u[1] - qu[1] + sb[1] + sr - srn) + t2[1];
+        gd = actu ? gd : 0.0;
+        // eliminate v_k: hv = g_v / w_v, f = R_{k+1} b_v hv
+        const double hv = s.wvi * gv;
+        const double mv[3] = {s.rdn[0] * md.b00, s.rdn[1] * md.b10, s.rdn[2] * md.b20};   // R_{k+1} b_v (as in the factor step)
+        const double f[3] = {mv[0] * hv, mv[1] * hv, mv[2] * hv};
+        double r[4], fp[3];
+        At_mul(md, f, t3);
+        cm.template up<3>(f, fp, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
+        r[3] = gd - md.b21 * f[2];
+#pragma unroll
+        for (int lev = 0; lev < NLEV - 1; ++lev) {
+          const int h = 1 << lev;
+          double lo[4], hi[4];
+          cm.template both<4>(r, lo, hi, h);
+          const double2* cf = sm_pair + (lev * 16) * T;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 c0 = cf[(4 * i + 0) * T], c1 = cf[(4 * i + 1) * T], c2 = cf[(4 * i + 2) * T], c3 = cf[(4 * i + 3) * T];
+            double a = fma(c0.x, lo[0], r[i]);
+            a = fma(c2.x, hi[0], a);
+            a = fma(c0.y, lo[1], a);
+            a = fma(c2.y, hi[1], a);
+            a = fma(c1.x, lo[2], a);
+            a = fma(c3.x, hi[2], a);
+            a = fma(c1.y, lo[3], a);
+            r[i] = fma(c3.y, hi[3], a);
+          }
+        }
+        {  // top level: single neighbour k ^ h
+          constexpr int h = 1 << (NLEV - 1);
+          double nb[4];
+          cm.template xr<4>(r, nb, h);
+          const double2* cf = sm_pair + ((NLEV - 1) * 16) * T;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 c0 = cf[(2 * i) * T], c1 = cf[(2 * i + 1) * T];
+            r[i] = fma(c1.y, nb[3], fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[i]))));
+          }
+        }
+        double st[4];
+        {
+          const double2* cf = sm_pair + ((NLEV - 1) * 16 + 8) * T;
+          const double2 q0 = cf[0 * T], q1 = cf[1 * T], q2 = cf[2 * T], q3 = cf[3 * T], q4 = cf[4 * T];
+          const double b00 = q0.x, b01 = q0.y, b02 = q1.x, b03 = q1.y, b11 = q2.x, b12 = q2.y, b13 = q3.x, b22 = q3.y, b23 = q4.x, b33 = q4.y;
+          st[0] = fma(b03, r[3], fma(b02, r[2], fma(b01, r[1], b00 * r[0])));
+          st[1] = fma(b13, r[3], fma(b12, r[2], fma(b11, r[1], b01 * r[0])));
+          st[2] = fma(b23, r[3], fma(b22, r[2], fma(b12, r[1], b02 * r[0])));
+          st[3] = fma(b33, r[3], fma(b23, r[2], fma(b13, r[1], b03 * r[0])));
+        }
+        xt[0] = st[0]; xt[1] = st[1]; xt[2] = st[2];
+        // recover v~_k = hv - b_v' R_{k+1} (C s~_k - x~_{k+1}) / w_v   (mv = 0 on the last stage)
+        double axt[3], xn[3];
+        A_mul(md, xt, axt);
+        cm.template dn<3>(xt, xn, 1);
+        const double yv[3] = {axt[0] - xn[0], axt[1] - xn[1], axt[2] + md.b21 * st[3] - xn[2]};
+        ut[0] = hv - s.wvi * (mv[0] * yv[0] + mv[1] * yv[1] + mv[2] * yv[2]);
+        ut[1] = st[3];
+        // z~ = A w~
+        double pred[3];
+        B_mul(md, ut, pred);
+        const double snd[4] = {pred[0] + axt[0], pred[1] + axt[1], pred[2] + axt[2], ut[1]};
+        double rcv[4];
+        cm.template up<4>(snd, rcv, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, rcv[i], -xt[i]);
+        ztr = fma(-hm, rcv[3], ut[1]);
+      } else {
+        double sdn[3];
+        cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
+        if (LASTFULL) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
+        }
+        double gx[3], gu[2], t3[3], t2[2];
+        At_mul(md, sdn, t3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
+          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
+        Bt_mul(md, sdn, t2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
+        // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
+        const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
+        const double f[3] = {s.rbm[0] * hh[0], s.rbm[1] * hh[0], s.rbm[2] * hh[0] + s.rbm[3] * hh[1]};
+        double r[3], fp[3];
+        At_mul(md, f, t3);
+        cm.template up<3>(f, fp, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
+        // PCR: apply the stored multipliers level by level (fully unrolled, constant offsets)
+        if constexpr (TM) { tmem_wait_ld(); tmem_tie<9>(mc); }
+#pragma unroll
+        for (int lev = 0; lev < NLEV - 1; ++lev) {
+          const int h = 1 << lev;
+          double lo[3], hi[3];
+          [[maybe_unused]] double2 nx[9];
+          if constexpr (TM) {   // next level (or: one-sided top level + final inverse, 8 pairs in a row) while this one is applied
+            if (lev + 1 < NLEV - 1) tmem_ld_pairs<9>(tmb + 36 * (lev + 1), nx);
+            else { tmem_ld_pairs<8>(tmb + 36 * (NLEV - 1), nx); nx[8] = make_double2(0.0, 0.0); }
+          }
+          cm.template both<3>(r, lo, hi, h);
+          [[maybe_unused]] const double2* cf = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            double2 c0, c1, c2;
+            if constexpr (TM) { c0 = mc[3 * i]; c1 = mc[3 * i + 1]; c2 = mc[3 * i + 2]; }
+            else { c0 = cf[(3 * i + 0) * T]; c1 = cf[(3 * i + 1) * T]; c2 = cf[(3 * i + 2) * T]; }
+            double a = fma(c0.x, lo[0], r[i]);
+            a = fma(c1.y, hi[0], a);
+            a = fma(c0.y, lo[1], a);
+            a = fma(c2.x, hi[1], a);
+            a = fma(c1.x, lo[2], a);
+            r[i] = fma(c2.y, hi[2], a);
+          }
+          if constexpr (TM) {
+            tmem_wait_ld();
+            tmem_tie<9>(nx);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) mc[j] = nx[j];
+          }
+        }
+        {  // top level: single neighbour k ^ h
+          constexpr int h = 1 << (NLEV - 1);
+          double nb[3];
+          cm.template xr<3>(r, nb, h);
+          double2 c0, c1, c2, c3, c4;
+          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; }
+          else {
+            const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
+            c0 = cf[0 * T]; c1 = cf[1 * T]; c2 = cf[2 * T]; c3 = cf[3 * T]; c4 = cf[4 * T];
+          }
+          r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
+          r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
+          r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
+        }
+        {
+          double2 q0, q1, q2;
+          if constexpr (TM) { q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
+          else { q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T]; }
+          const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
+          xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
+          xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
+          xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+        }
+        // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
+        double axt[3], v[3], xn[3];
+        A_mul(md, xt, axt);
+        cm.template dn<3>(xt, xn, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[i] = axt[i] - xn[i];
+        t2[0] = s.rbm[0] * v[0] + s.rbm[1] * v[1] + s.rbm[2] * v[2];   // (R_{k+1} B)' v
+        t2[1] = s.rbm[3] * v[2];
+        ut[0] = hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]);
+        ut[1] = hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1]);
+        // z~ = A w~ : dynamics rows need the predecessor's prediction
+        double pred[3], pp[3];
+        B_mul(md, ut, pred);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pred[i] += axt[i];
+        cm.template up<3>(pred, pp, 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, pp[i], -xt[i]);
+      }
+      const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s.u[j] = al * ut[j] + oma * s.u[j];
+#pragma unroll
+      if constexpr (FIRST) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {  // equality rows: the projection onto [l, u] = {b} is b itself
+          const double zr = al * ztd[i] + oma * scr[(SCR_ZD + i) * T];
+          s.yd[i] += s.rd[i] * (zr - s.bd[i]);
+        }
+      } else {
+        // z = b from the second iteration on:  alpha z~ + (1 - alpha) b - b = alpha (z~ - b)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s.yd[i] = fma(s.rda[i], ztd[i] - s.bd[i], s.yd[i]);
+      }
+#pragma unroll
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const double zr = al * ztg[r2] + oma * s.zg[r2];
+        const double zn = dmax(zr + s.ig[r2] * s.yg[r2], s.gl[r2]);  // upper bound is +INFTY: the projection is a max
+        s.yg[r2] += s.rg[r2] * (zr - zn);
+        s.zg[r2] = zn;
+        const double zrb = al * ut[r2] + oma * s.zb[r2];
+        const double znb = clampd(zrb + s.ib[r2] * s.yb[r2], p.u_min[r2], p.u_max[r2]);
+        s.yb[r2] += s.rb[r2] * (zrb - znb);
+        s.zb[r2] = znb;
+      }
+      if constexpr (RATE) {
+        const double zr = al * ztr + oma * s.zr;
+        const double zn = clampd(zr + s.ir * s.yr, s.rbase - p.rate_delta, s.rbase + p.rate_delta);
+        s.yr += s.rr * (zr - zn);
+        s.zr = zn;
+      }
+      };
+
   for (;;) {
     if (QPW == 1 ? need_factor : __any_sync(FULL, need_factor)) {   // (re-factoring an unchanged rho is idempotent)
       // ---------- factor step: metric from rho_bar, input elimination, PCR multipliers -------------------------
       need_factor = false;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.rd[i] = RHO_EQ_OVER_RHO_INEQ * rho_bar * scr[(SCR_WD + i) * T];
+      for (int i = 0; i < 3; ++i) { s.rd[i] = RHO_EQ_OVER_RHO_INEQ * rho_bar * scr[(SCR_WD + i) * T]; s.rda[i] = s.rd[i] * al; }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const double cg = scr[(SCR_CG + r) * T], cb = scr[(SCR_CB + r) * T];
@@ -653,6 +903,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           s.wi[1] = actu ? -w01 * idet : 0.0;
           s.wi[2] = actu ? w00 * idet : 0.0;
           const double M[6] = {s.rdn[0] * md.b00, 0.0, s.rdn[1] * md.b10, 0.0, s.rdn[2] * md.b20, s.rdn[2] * md.b21};
+          s.rbm[0] = M[0]; s.rbm[1] = M[2]; s.rbm[2] = M[4]; s.rbm[3] = M[5];   // R_{k+1} B, used by every iteration
           double MW[6];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -818,240 +1069,8 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
     }
 
-    // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
-    {
-      // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
-      [[maybe_unused]] double2 mc[9];
-      if constexpr (TM) {
-        if constexpr (NLEV > 1) tmem_ld_pairs<9>(tmb, mc);
-        else { tmem_ld_pairs<8>(tmb, mc); mc[8] = make_double2(0.0, 0.0); }
-      }
-      // s = rho (z - y/rho) = rho z - y per row; right-hand side of the condensed system
-      double sd[3], sg[2], sb[2];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) sd[i] = s.rd[i] * s.zd[i] - s.yd[i];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) { sg[r] = s.rg[r] * s.zg[r] - s.yg[r]; sb[r] = s.rb[r] * s.zb[r] - s.yb[r]; }
-      double xt[3], ut[2], ztd[3];
-      [[maybe_unused]] double ztr = 0.0;
-      // 1 where the stage has a predecessor: values shuffled in from stage k-1 enter through an FMA with this factor (exact: the
-      // factor is 0 or 1), one select instead of two per masked value
-      const double hm = hasp ? 1.0 : 0.0;
-      if constexpr (RATE) {
-        const double sr = s.rr * s.zr - s.yr;   // 0 on stages without an input (rho = 0, y = 0)
-        double sdn[3], srn;
-        {
-          const double snd[4] = {sd[0], sd[1], sd[2], sr};
-          double rcv[4];
-          cm.template dn<4>(snd, rcv, 1);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) sdn[i] = (LASTFULL && !actu) ? 0.0 : rcv[i];
-          srn = rcv[3];
-        }
-        double gx[3], t3[3], t2[2];
-        At_mul(md, sdn, t3);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
-        Bt_mul(md, sdn, t2);
-        const double gv = (s.su[0] * s.u[0] - qu[0] + sb[0]) + t2[0];
-        double gd = (s.su[1] * s.u[1] - qu[1] + sb[1] + sr - srn) + t2[1];
-        gd = actu ? gd : 0.0;
-        // eliminate v_k: hv = g_v / w_v, f = R_{k+1} b_v hv
-        const double hv = s.wvi * gv;
-        const double mv[3] = {s.rdn[0] * md.b00, s.rdn[1] * md.b10, s.rdn[2] * md.b20};   // R_{k+1} b_v (as in the factor step)
-        const double f[3] = {mv[0] * hv, mv[1] * hv, mv[2] * hv};
-        double r[4], fp[3];
-        At_mul(md, f, t3);
-        cm.template up<3>(f, fp, 1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
-        r[3] = gd - md.b21 * f[2];
-#pragma unroll
-        for (int lev = 0; lev < NLEV - 1; ++lev) {
-          const int h = 1 << lev;
-          double lo[4], hi[4];
-          cm.template both<4>(r, lo, hi, h);
-          const double2* cf = sm_pair + (lev * 16) * T;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double2 c0 = cf[(4 * i + 0) * T], c1 = cf[(4 * i + 1) * T], c2 = cf[(4 * i + 2) * T], c3 = cf[(4 * i + 3) * T];
-            double a = fma(c0.x, lo[0], r[i]);
-            a = fma(c2.x, hi[0], a);
-            a = fma(c0.y, lo[1], a);
-            a = fma(c2.y, hi[1], a);
-            a = fma(c1.x, lo[2], a);
-            a = fma(c3.x, hi[2], a);
-            a = fma(c1.y, lo[3], a);
-            r[i] = fma(c3.y, hi[3], a);
-          }
-        }
-        {  // top level: single neighbour k ^ h
-          constexpr int h = 1 << (NLEV - 1);
-          double nb[4];
-          cm.template xr<4>(r, nb, h);
-          const double2* cf = sm_pair + ((NLEV - 1) * 16) * T;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double2 c0 = cf[(2 * i) * T], c1 = cf[(2 * i + 1) * T];
-            r[i] = fma(c1.y, nb[3], fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[i]))));
-          }
-        }
-        double st[4];
-        {
-          const double2* cf = sm_pair + ((NLEV - 1) * 16 + 8) * T;
-          const double2 q0 = cf[0 * T], q1 = cf[1 * T], q2 = cf[2 * T], q3 = cf[3 * T], q4 = cf[4 * T];
-          const double b00 = q0.x, b01 = q0.y, b02 = q1.x, b03 = q1.y, b11 = q2.x, b12 = q2.y, b13 = q3.x, b22 = q3.y, b23 = q4.x, b33 = q4.y;
-          st[0] = fma(b03, r[3], fma(b02, r[2], fma(b01, r[1], b00 * r[0])));
-          st[1] = fma(b13, r[3], fma(b12, r[2], fma(b11, r[1], b01 * r[0])));
-          st[2] = fma(b23, r[3], fma(b22, r[2], fma(b12, r[1], b02 * r[0])));
-          st[3] = fma(b33, r[3], fma(b23, r[2], fma(b13, r[1], b03 * r[0])));
-        }
-        xt[0] = st[0]; xt[1] = st[1]; xt[2] = st[2];
-        // recover v~_k = hv - b_v' R_{k+1} (C s~_k - x~_{k+1}) / w_v   (mv = 0 on the last stage)
-        double axt[3], xn[3];
-        A_mul(md, xt, axt);
-        cm.template dn<3>(xt, xn, 1);
-        const double yv[3] = {axt[0] - xn[0], axt[1] - xn[1], axt[2] + md.b21 * st[3] - xn[2]};
-        ut[0] = hv - s.wvi * (mv[0] * yv[0] + mv[1] * yv[1] + mv[2] * yv[2]);
-        ut[1] = st[3];
-        // z~ = A w~
-        double pred[3];
-        B_mul(md, ut, pred);
-        const double snd[4] = {pred[0] + axt[0], pred[1] + axt[1], pred[2] + axt[2], ut[1]};
-        double rcv[4];
-        cm.template up<4>(snd, rcv, 1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, rcv[i], -xt[i]);
-        ztr = fma(-hm, rcv[3], ut[1]);
-      } else {
-        double sdn[3];
-        cm.template dn<3>(sd, sdn, 1);  // stages above N hold zeros, so only a full last warp needs the mask
-        if (LASTFULL) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) sdn[i] = actu ? sdn[i] : 0.0;
-        }
-        double gx[3], gu[2], t3[3], t2[2];
-        At_mul(md, sdn, t3);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
-          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
-        Bt_mul(md, sdn, t2);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
-        // eliminate u_k: h = W^-1 gu, f = R_{k+1} B h
-        const double hh[2] = {s.wi[0] * gu[0] + s.wi[1] * gu[1], s.wi[1] * gu[0] + s.wi[2] * gu[1]};
-        double f[3];
-        B_mul(md, hh, f);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) f[i] *= s.rdn[i];
-        double r[3], fp[3];
-        At_mul(md, f, t3);
-        cm.template up<3>(f, fp, 1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
-        // PCR: apply the stored multipliers level by level (fully unrolled, constant offsets)
-        if constexpr (TM) { tmem_wait_ld(); tmem_tie<9>(mc); }
-#pragma unroll
-        for (int lev = 0; lev < NLEV - 1; ++lev) {
-          const int h = 1 << lev;
-          double lo[3], hi[3];
-          [[maybe_unused]] double2 nx[9];
-          if constexpr (TM) {   // next level (or: one-sided top level + final inverse, 8 pairs in a row) while this one is applied
-            if (lev + 1 < NLEV - 1) tmem_ld_pairs<9>(tmb + 36 * (lev + 1), nx);
-            else { tmem_ld_pairs<8>(tmb + 36 * (NLEV - 1), nx); nx[8] = make_double2(0.0, 0.0); }
-          }
-          cm.template both<3>(r, lo, hi, h);
-          [[maybe_unused]] const double2* cf = (GL == 2 && lev == NLEV - 2) ? gl_pair : sm_pair + (lev * 9) * T;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            double2 c0, c1, c2;
-            if constexpr (TM) { c0 = mc[3 * i]; c1 = mc[3 * i + 1]; c2 = mc[3 * i + 2]; }
-            else { c0 = cf[(3 * i + 0) * T]; c1 = cf[(3 * i + 1) * T]; c2 = cf[(3 * i + 2) * T]; }
-            double a = fma(c0.x, lo[0], r[i]);
-            a = fma(c1.y, hi[0], a);
-            a = fma(c0.y, lo[1], a);
-            a = fma(c2.x, hi[1], a);
-            a = fma(c1.x, lo[2], a);
-            r[i] = fma(c2.y, hi[2], a);
-          }
-          if constexpr (TM) {
-            tmem_wait_ld();
-            tmem_tie<9>(nx);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) mc[j] = nx[j];
-          }
-        }
-        {  // top level: single neighbour k ^ h
-          constexpr int h = 1 << (NLEV - 1);
-          double nb[3];
-          cm.template xr<3>(r, nb, h);
-          double2 c0, c1, c2, c3, c4;
-          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; }
-          else {
-            const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
-            c0 = cf[0 * T]; c1 = cf[1 * T]; c2 = cf[2 * T]; c3 = cf[3 * T]; c4 = cf[4 * T];
-          }
-          r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
-          r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
-          r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
-        }
-        {
-          double2 q0, q1, q2;
-          if constexpr (TM) { q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
-          else { q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T]; }
-          const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
-          xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
-          xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
-          xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
-        }
-        // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
-        double axt[3], v[3], xn[3];
-        A_mul(md, xt, axt);
-        cm.template dn<3>(xt, xn, 1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) v[i] = s.rdn[i] * (axt[i] - xn[i]);
-        Bt_mul(md, v, t2);
-        ut[0] = hh[0] - (s.wi[0] * t2[0] + s.wi[1] * t2[1]);
-        ut[1] = hh[1] - (s.wi[1] * t2[0] + s.wi[2] * t2[1]);
-        // z~ = A w~ : dynamics rows need the predecessor's prediction
-        double pred[3], pp[3];
-        B_mul(md, ut, pred);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) pred[i] += axt[i];
-        cm.template up<3>(pred, pp, 1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ztd[i] = fma(hm, pp[i], -xt[i]);
-      }
-      const double ztg[2] = {s.gm[0] * xt[0] + s.gm[1] * xt[1] + s.gm[2] * xt[2], s.gm[3] * xt[0] + s.gm[4] * xt[1] + s.gm[5] * xt[2]};
-#pragma unroll
-      for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) s.u[j] = al * ut[j] + oma * s.u[j];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {  // equality rows: the projection onto [l, u] = {b} is b itself
-        const double zr = al * ztd[i] + oma * s.zd[i];
-        s.yd[i] += s.rd[i] * (zr - s.bd[i]);
-        s.zd[i] = s.bd[i];
-      }
-#pragma unroll
-      for (int r2 = 0; r2 < 2; ++r2) {
-        const double zr = al * ztg[r2] + oma * s.zg[r2];
-        const double zn = dmax(zr + s.ig[r2] * s.yg[r2], s.gl[r2]);  // upper bound is +INFTY: the projection is a max
-        s.yg[r2] += s.rg[r2] * (zr - zn);
-        s.zg[r2] = zn;
-        const double zrb = al * ut[r2] + oma * s.zb[r2];
-        const double znb = clampd(zrb + s.ib[r2] * s.yb[r2], p.u_min[r2], p.u_max[r2]);
-        s.yb[r2] += s.rb[r2] * (zrb - znb);
-        s.zb[r2] = znb;
-      }
-      if constexpr (RATE) {
-        const double zr = al * ztr + oma * s.zr;
-        const double zn = clampd(zr + s.ir * s.yr, s.rbase - p.rate_delta, s.rbase + p.rate_delta);
-        s.yr += s.rr * (zr - zn);
-        s.zr = zn;
-      }
-    }
+    if (first_iter) { iterate(std::true_type{}); first_iter = false; }
+    else iterate(std::false_type{});
     if (info_iter) break;
     ++iter;
     }
@@ -1107,7 +1126,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       if (act) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const double rr = fabs(Axd[i] - s.zd[i]), zz = fabs(s.zd[i]), aa = fabs(Axd[i]);
+          const double rr = fabs(Axd[i] - s.bd[i]), zz = fabs(s.bd[i]), aa = fabs(Axd[i]);   // z = b (at least one iteration has run)
           poisoned |= !(rr == rr);
           m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
           q_pri = dmax(q_pri, edv[i] * rr); q_z = dmax(q_z, edv[i] * zz); q_Ax = dmax(q_Ax, edv[i] * aa);
