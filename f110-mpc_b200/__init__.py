@@ -50,7 +50,11 @@ EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_
            "f110_mpc_num_variables", "f110_mpc_num_constraints", "f110_mpc_num_rows", "f110_last_error", "f110_device_count",
            "f110_mpc_create", "f110_mpc_destroy", "f110_mpc_solve_host", "f110_mpc_solve_device", "f110_mpc_reset",
            "f110_mpc_last_launches", "f110_mpc_set_packed_output", "f110_collision_check_device", "f110_collision_check_host", "f110_bench_fp64_fma", "f110_cycle_default_config",
-           "f110_cycle_device", "f110_cycle_host", "f110_cycle_buffers"]
+           "f110_cycle_device", "f110_cycle_host", "f110_cycle_buffers", "f110_cycle_submit", "f110_cycle_wait",
+           "f110_mpc_create_multi", "f110_mpc_destroy_multi", "f110_mpc_solve_multi_host", "f110_mpc_multi_devices",
+           "f110_mpc_multi_uses_peer_stores", "f110_mpc_multi_last_shard", "f110_gather_bytes", "f110_gather_create",
+           "f110_gather_open", "f110_gather_close", "f110_gather_slot", "f110_stream_signal", "f110_stream_wait_flags",
+           "f110_cycle_set_gather"]
 
 
 def build(force=False, verbose=False):
@@ -98,6 +102,22 @@ def lib():
                                         vp, vp, vp, vp, vp, vp]
         L.f110_cycle_host.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
         L.f110_cycle_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
+        L.f110_cycle_submit.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+        L.f110_cycle_wait.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.f110_mpc_create_multi.argtypes = [C.POINTER(MpcConfig), C.POINTER(SolverSettings), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        L.f110_mpc_destroy_multi.argtypes = [vp]
+        L.f110_mpc_solve_multi_host.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int, dp, ip, ip]
+        L.f110_mpc_multi_devices.argtypes = [vp]
+        L.f110_mpc_multi_uses_peer_stores.argtypes = [vp, C.c_int]
+        L.f110_mpc_multi_last_shard.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.f110_gather_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.f110_gather_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.c_char_p]
+        L.f110_gather_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+        L.f110_gather_close.argtypes = [C.c_int, vp, C.c_int]
+        L.f110_gather_slot.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(vp), C.POINTER(vp)]
+        L.f110_stream_signal.argtypes = [vp, vp, C.c_int32]
+        L.f110_stream_wait_flags.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int32]
+        L.f110_cycle_set_gather.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -220,6 +240,40 @@ class MpcSolver:
                                      vp(wp_xy), wp_xy.shape[0], vp(u0), vp(status), vp(iters), vp(chosen), vp(valid)), "f110_cycle_host")
         return dict(u0=u0, status=status, iters=iters, chosen=chosen, valid=valid)
 
+    def cycle_submit(self, cc, pose7, ranges, prev_steer, table_xy, wp_xy):
+        """f110_cycle_submit: queue one cycle (inputs must be C-contiguous numpy arrays of the ABI's dtypes; pinned arrays are read
+        in place and must stay untouched until cycle_wait).  Returns the ticket."""
+        S, P = pose7.shape[0], table_xy.shape[0]
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        for a, dt in ((pose7, np.float64), (ranges, np.float32), (table_xy, np.float64), (wp_xy, np.float32)):
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
+        t = C.c_int(-1)
+        _check(lib().f110_cycle_submit(self._h, C.byref(cc), S, vp(pose7), vp(ranges), vp(prev_steer), vp(table_xy), P, table_xy.shape[1],
+                                       vp(wp_xy), wp_xy.shape[0], C.byref(t)), "f110_cycle_submit")
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (S, P, S if cc.qp_mode == 0 else S * P)
+        return t.value
+
+    def cycle_wait(self, ticket, out=None, gathered=None):
+        """f110_cycle_wait: block until the cycle's results are on the host.  Returns dict(u0, status, iters, chosen, valid)."""
+        info = getattr(self, "_inflight", {}).pop(ticket, None)
+        if info is None:   # not a ticket of this handle: let the library say so
+            _check(lib().f110_cycle_wait(self._h, ticket, None, None, None, None, None, None), "f110_cycle_wait")
+            raise RuntimeError("f110_cycle_wait: unknown ticket %d" % ticket)
+        S, P, nqp = info
+        out = out or {}
+        u0 = out.get("u0", np.empty((nqp, 2))); status = out.get("status", np.empty(nqp, dtype=np.int32))
+        iters = out.get("iters", np.empty(nqp, dtype=np.int32)); chosen = out.get("chosen", np.empty(S, dtype=np.int32))
+        valid = out.get("valid", np.empty((S, P), dtype=np.uint8))
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        _check(lib().f110_cycle_wait(self._h, ticket, vp(u0), vp(status), vp(iters), vp(chosen), vp(valid), vp(gathered)), "f110_cycle_wait")
+        return dict(u0=u0, status=status, iters=iters, chosen=chosen, valid=valid)
+
+    def set_gather(self, ring_ptr, world, rank, rows_per_rank, slots):
+        """Attach (or, with ring_ptr None, detach) a gather ring to the asynchronous cycle entry."""
+        _check(lib().f110_cycle_set_gather(self._h, C.c_void_p(ring_ptr) if ring_ptr else None, world, rank, rows_per_rank, slots),
+               "f110_cycle_set_gather")
+
     def cycle_buffers(self, scenes, nrec=None):
         """Torch views (no copy) of the device buffers the last cycle filled:
         dict(grid (S, blocks^2) f32, offset (S,2) f32, l1l2 (S,6) f64, recs (S, 11+3N) f64, best_global (S,) i32)."""
@@ -256,6 +310,86 @@ class MpcSolver:
             self.close()
         except Exception:
             pass
+
+
+class MultiGpuSolver:
+    """f110_mpc_create_multi: one process, several GPUs; shards of whole units, gather by peer stores into devices[0]."""
+
+    def __init__(self, config=None, settings=None, max_batch=4096, devices=(0,)):
+        self.config = config or default_config()
+        self.settings = settings or default_settings()
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        _check(lib().f110_mpc_create_multi(C.byref(self.config), C.byref(self.settings), max_batch, arr, len(self.devices), C.byref(self._h)),
+               "f110_mpc_create_multi")
+
+    def solve_host(self, recs, unit=1):
+        recs = np.ascontiguousarray(recs, dtype=np.float64)
+        B = recs.shape[0]
+        u0, status, iters = np.empty((B, 2)), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+        _check(lib().f110_mpc_solve_multi_host(self._h, B, unit, _dp(recs), recs.shape[1], _dp(u0), _ip(status), _ip(iters)),
+               "f110_mpc_solve_multi_host")
+        return dict(u0=u0, status=status, iters=iters)
+
+    def last_shards(self):
+        out = []
+        for i in range(len(self.devices)):
+            a, b = C.c_int(), C.c_int()
+            _check(lib().f110_mpc_multi_last_shard(self._h, i, C.byref(a), C.byref(b)), "f110_mpc_multi_last_shard")
+            out.append((a.value, b.value))
+        return out
+
+    def uses_peer_stores(self, i):
+        return bool(lib().f110_mpc_multi_uses_peer_stores(self._h, i))
+
+    def close(self):
+        if self._h:
+            lib().f110_mpc_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GatherRing:
+    """The NVLink gather ring (f110_gather_*).  Root: GatherRing.create(...) -> .handle (64 bytes) goes to the peers; peers:
+    GatherRing.open(handle, ...).  `slot(cycle)` -> (device pointer of this rank's rows, device pointer of its flag)."""
+
+    def __init__(self, ptr, device, world, rank, rows, slots, opened, handle=None):
+        self.ptr, self.device, self.world, self.rank, self.rows, self.slots, self.opened, self.handle = ptr, device, world, rank, rows, slots, opened, handle
+
+    @classmethod
+    def create(cls, device, world, rows, slots):
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(lib().f110_gather_create(device, world, rows, slots, C.byref(p), h), "f110_gather_create")
+        return cls(p.value, device, world, 0, rows, slots, False, h.raw)
+
+    @classmethod
+    def open(cls, handle, device, world, rank, rows, slots):
+        p = C.c_void_p()
+        _check(lib().f110_gather_open(device, handle, C.byref(p)), "f110_gather_open")
+        return cls(p.value, device, world, rank, rows, slots, True, handle)
+
+    def slot(self, cycle):
+        rows, flag = C.c_void_p(), C.c_void_p()
+        _check(lib().f110_gather_slot(C.c_void_p(self.ptr), self.world, self.rank, self.rows, self.slots, cycle, C.byref(rows), C.byref(flag)),
+               "f110_gather_slot")
+        return rows.value, flag.value
+
+    def nbytes(self):
+        n = C.c_size_t()
+        _check(lib().f110_gather_bytes(self.world, self.rows, self.slots, C.byref(n)), "f110_gather_bytes")
+        return n.value
+
+    def close(self):
+        if self.ptr:
+            lib().f110_gather_close(self.device, C.c_void_p(self.ptr), 1 if self.opened else 0)
+            self.ptr = None
 
 
 def fp64_fma_peak_tflops(device=0, iters=20000):

@@ -5,68 +5,20 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/f110_mpc_b200.h"
-#include "admm_kernel.cuh"
+#include "api_internal.h"
 
 namespace {
 thread_local std::string g_err;
+}
+namespace f110api {
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-int cuda_fail(cudaError_t e, const char* what) {
-  return fail(F110_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-}
-#define CUDA_TRY(expr)                                    \
-  do {                                                    \
-    cudaError_t e__ = (expr);                             \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
-  } while (0)
-}  // namespace
-
-struct f110_mpc_solver {
-  f110_mpc_config cfg;
-  f110_solver_settings st;
-  int max_batch = 0;
-  int device = 0;
-  int last_launches = 0;
-  double* d_state = nullptr;    // warm-start slots
-  double* d_scratch = nullptr;  // per-QP scratch lines (scaling vectors, previous iterate)
-  double* d_mult = nullptr;     // per-QP top-level multipliers of four-warp QPs (horizon >= 64)
-  int* d_work = nullptr;        // work-counter pairs of the persistent tensor-memory kernel: WORK_SLOTS round-robin + 1 for the B = 1 graph
-  unsigned work_seq = 0;
-  // staging for the host-buffer entry: one device block [u0 | status | iters | x | y] so results come back in
-  // one copy, plus a small pinned mirror used for latency-critical small batches
-  double* d_recs = nullptr;
-  unsigned char* d_out = nullptr;
-  unsigned char* h_pin = nullptr;   // pinned: records of <= kSmallBatch QPs, then their outputs
-  size_t out_bytes = 0;
-  double* d_packed_next = nullptr;
-  unsigned char* cyc_stage = nullptr;  // device staging of f110_cycle_host
-  size_t cyc_stage_bytes = 0;
-  unsigned char* cyc_pin = nullptr;    // pinned mirror of the output block
-  size_t cyc_pin_bytes = 0;
-  unsigned long long cyc_tab_hash = 0; // content hash of the uploaded mini-path table + raceline
-  // f110_cycle_device scratch (allocated on first use, sized for max_batch scenes)
-  struct Cycle {
-    int blocks = 0, paths = 0;
-    float *grid = nullptr, *offset = nullptr, *endw = nullptr;
-    double *rot = nullptr, *pose_xy = nullptr, *state3 = nullptr, *l1l2 = nullptr, *recs = nullptr;
-    uint8_t* valid = nullptr;
-    int32_t *free_cnt = nullptr, *gap = nullptr, *best_global = nullptr;
-    void release() {
-      cudaFree(grid); cudaFree(offset); cudaFree(endw); cudaFree(rot); cudaFree(pose_xy); cudaFree(state3); cudaFree(l1l2);
-      cudaFree(recs); cudaFree(valid); cudaFree(free_cnt); cudaFree(gap); cudaFree(best_global);
-      *this = Cycle();
-    }
-  } cyc;  // optional packed result rows for the NEXT solve_device call (f110_mpc_set_packed_output)
-  cudaStream_t stream = nullptr;
-  // f110_cycle_host pipelines its scenes in chunks over two streams (copies of chunk c+1 under the kernels of chunk c)
-  // single-QP latency path: the copy-in / solve / copy-out triple captured once as a CUDA graph per output shape (u0 only, +x, +x+y)
-  cudaGraphExec_t lat_graph[3] = {nullptr, nullptr, nullptr};
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
-};
+int cuda_fail(cudaError_t e, const char* what) { return fail(F110_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+}  // namespace f110api
+using f110api::cuda_fail;
+using f110api::fail;
 
 extern "C" {
 
@@ -137,6 +89,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   if (e == cudaSuccess) e = cudaMalloc(&s->d_work, wsz);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_work, 0, wsz, s->stream);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_solve, cudaEventDisableTiming);
   // the slots are cleared on the handle's own (non-blocking) stream and the clear is waited for: a memset on the legacy default
   // stream would not be ordered against solves on s->stream or on a caller's stream
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_state, 0, ssz, s->stream);
@@ -166,6 +119,15 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
   if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->ev_tab) cudaEventDestroy(s->ev_tab);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
+  for (f110_cycle_lane& l : s->lane) {
+    l.cyc.release();
+    cudaFree(l.stage);
+    if (l.pin_in) cudaFreeHost(l.pin_in);
+    if (l.pin_out) cudaFreeHost(l.pin_out);
+    if (l.ev_done) cudaEventDestroy(l.ev_done);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  if (s->ev_solve) cudaEventDestroy(s->ev_solve);
   delete s;
 }
 
@@ -190,9 +152,9 @@ int f110_mpc_set_packed_output(f110_mpc_solver* s, double* d_packed) {
 }  // extern "C"
 
 // Solve `count` QPs that occupy warm-start / scratch slots slot0 .. slot0 + count - 1 of the handle.
-static int solve_device_range(f110_mpc_solver* s, int slot0, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
-                              double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
-                              void* cuda_stream) {
+int f110api::solve_device_range(f110_mpc_solver* s, int slot0, int count, const double* d_recs, int rec_stride, double* d_x, double* d_y,
+                                double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
+                                void* cuda_stream) {
   if (!s || !d_recs) return fail(F110_ERR_ARG, "f110_mpc_solve_device: null solver or records");
   if (count < 0 || slot0 < 0 || slot0 + count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_device: count exceeds max_batch");
   if (rec_stride < f110_mpc_record_doubles(s->cfg.horizon)) return fail(F110_ERR_ARG, "f110_mpc_solve_device: record stride too small");
@@ -236,7 +198,7 @@ int f110_mpc_solve_device(f110_mpc_solver* s, int count, const double* d_recs, i
                           double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_rho_updates, double* d_info,
                           void* cuda_stream) {
   if (s) s->last_launches = 0;
-  return solve_device_range(s, 0, count, d_recs, rec_stride, d_x, d_y, d_u0, d_status, d_iters, d_rho_updates, d_info, cuda_stream);
+  return f110api::solve_device_range(s, 0, count, d_recs, rec_stride, d_x, d_y, d_u0, d_status, d_iters, d_rho_updates, d_info, cuda_stream);
 }
 
 int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int rec_stride, double* x, double* y, double* u0,
@@ -347,8 +309,9 @@ void f110_cycle_default_config(f110_cycle_config* c) {
 
 }  // extern "C"
 
-// Argument checks + (re)allocation of the per-scene device scratch shared by f110_cycle_device / f110_cycle_host.
-static int cycle_prepare(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, int paths, int samples, int n_wp, const double* d_table_xy) {
+// Argument checks + (re)allocation of the per-scene device scratch `c` (grown on demand; the cycle entries each own one).
+int f110api::cycle_prepare(f110_mpc_solver* s, f110_cycle_scratch& c, const f110_cycle_config* cc, int scenes, int paths, int samples, int n_wp,
+                           const double* d_table_xy) {
   if (cc->qp_mode < 0 || cc->qp_mode > 2) return fail(F110_ERR_ARG, "f110_cycle_device: bad qp_mode");
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
   if (scenes < 0 || nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_device: QP count exceeds max_batch");
@@ -360,40 +323,41 @@ static int cycle_prepare(f110_mpc_solver* s, const f110_cycle_config* cc, int sc
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (int)(cc->occ_size / cc->occ_discrete);           // occupancy_grid.cpp:9
   const int N = s->cfg.horizon, rd = (f110_mpc_record_doubles(N) + 1) & ~1;  // even stride: records stay 16-byte aligned (TMA staging)
-  auto& c = s->cyc;
-  if (c.blocks != blocks || c.paths < paths) {
+  if (c.blocks != blocks || c.paths < paths || c.cap_scenes < (size_t)scenes || c.cap_qps < (size_t)nqp) {
+    // (the buffers may still be read by queued work of an earlier call: cudaFree waits for the device)
+    const size_t S = (size_t)scenes > c.cap_scenes ? (size_t)scenes : c.cap_scenes;
+    const size_t Q = (size_t)nqp > c.cap_qps ? (size_t)nqp : c.cap_qps;
+    const int P = paths > c.paths ? paths : c.paths;
     c.release();
-    const size_t B = s->max_batch;
-    CUDA_TRY(cudaMalloc(&c.grid, B * blocks * blocks * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c.offset, B * 2 * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c.endw, B * paths * 2 * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c.rot, B * 4 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.pose_xy, B * 2 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.state3, B * 3 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.l1l2, B * 6 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.recs, B * rd * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.valid, B * paths));
-    CUDA_TRY(cudaMalloc(&c.free_cnt, B * paths * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&c.gap, B * 2 * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&c.best_global, B * sizeof(int32_t)));
-    c.blocks = blocks; c.paths = paths;
+    CUDA_TRY(cudaMalloc(&c.grid, S * blocks * blocks * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.offset, S * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.endw, S * P * 2 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.rot, S * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.pose_xy, S * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.state3, S * 3 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.l1l2, S * 6 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.recs, Q * rd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.valid, S * P));
+    CUDA_TRY(cudaMalloc(&c.free_cnt, S * P * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&c.gap, S * 2 * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&c.best_global, S * sizeof(int32_t)));
+    c.blocks = blocks; c.paths = P; c.cap_scenes = S; c.cap_qps = Q;
   }
   return F110_OK;
 }
 
 // The 5 kernels of one cycle for scenes scene0 .. scene0 + scenes - 1.  The caller's pointers are already offset to scene0; the
 // handle's per-scene scratch and the solver's warm-start slots are offset here, so ranges of one batch can run on different streams.
-static int cycle_device_range(f110_mpc_solver* s, const f110_cycle_config* cc, int scene0, int scenes, const double* d_pose7,
-                              const float* d_ranges, const double* d_prev_steer, const double* d_table_xy, int paths, int samples,
-                              const float* d_wp_xy, int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen,
-                              uint8_t* d_valid, cudaStream_t st) {
+int f110api::cycle_device_range(f110_mpc_solver* s, f110_cycle_scratch& c, const f110_cycle_config* cc, int scene0, int scenes,
+                                const double* d_pose7, const float* d_ranges, const double* d_prev_steer, const double* d_table_xy, int paths,
+                                int samples, const float* d_wp_xy, int n_wp, double* d_u0, int32_t* d_status, int32_t* d_iters,
+                                int32_t* d_chosen, uint8_t* d_valid, cudaStream_t st, cudaEvent_t wait_before_solve) {
   if (scenes == 0) return F110_OK;
   const int blocks = (int)(cc->occ_size / cc->occ_discrete);
   const int N = s->cfg.horizon, rd = (f110_mpc_record_doubles(N) + 1) & ~1;
   const size_t s0 = (size_t)scene0;
   const size_t q0 = cc->qp_mode == 0 ? s0 : s0 * paths;                 // first QP slot of the range
   const long long nqp = cc->qp_mode == 0 ? scenes : (long long)scenes * paths;
-  auto& c = s->cyc;
   float* grid = c.grid + s0 * blocks * blocks;
   float* offset = c.offset + s0 * 2;
   float* endw = c.endw + s0 * paths * 2;
@@ -413,9 +377,23 @@ static int cycle_device_range(f110_mpc_solver* s, const f110_cycle_config* cc, i
   if (e == cudaSuccess) e = f110::launch_build_records(scenes, paths, samples, N, rd, cc->qp_mode, cc->v_lin, d_pose7, rot, valid, d_chosen,
                                                        d_table_xy, d_prev_steer, l1l2, recs, st);
   if (e != cudaSuccess) return cuda_fail(e, "f110_cycle_device: kernel launch");
+  if (wait_before_solve) CUDA_TRY(cudaStreamWaitEvent(st, wait_before_solve, 0));
   const int rc = solve_device_range(s, (int)q0, (int)nqp, recs, rd, nullptr, nullptr, d_u0, d_status, d_iters, nullptr, nullptr, st);
+  if (rc == F110_OK && s->ev_solve) cudaEventRecord(s->ev_solve, st);   // the next cycle's solve (any stream of this handle) waits for this one
   s->last_launches += 4;
   return rc;
+}
+
+// FNV-1a over the constant tables (20 KB): cheaper than two more copies per cycle
+unsigned long long f110api::table_hash(const double* table_xy, size_t n_tab, const float* wp_xy, size_t n_wpb, int paths, int samples, int n_wp) {
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&h](const void* ptr, size_t n) {
+    const unsigned long long* w = static_cast<const unsigned long long*>(ptr);
+    for (size_t i = 0; i < n / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+  };
+  mix(table_xy, n_tab); mix(wp_xy, n_wpb);
+  h ^= (unsigned long long)paths * 1315423911ull + (unsigned long long)samples * 2654435761ull + (unsigned long long)n_wp;
+  return h;
 }
 
 extern "C" {
@@ -424,11 +402,11 @@ int f110_cycle_device(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                       const double* d_prev_steer, const double* d_table_xy, int paths, int samples, const float* d_wp_xy, int n_wp,
                       double* d_u0, int32_t* d_status, int32_t* d_iters, int32_t* d_chosen, uint8_t* d_valid, void* cuda_stream) {
   if (!s || !cc || !d_pose7 || !d_ranges || !d_table_xy || !d_wp_xy || !d_chosen) return fail(F110_ERR_ARG, "f110_cycle_device: null argument");
-  const int rc = cycle_prepare(s, cc, scenes, paths, samples, n_wp, d_table_xy);
+  const int rc = f110api::cycle_prepare(s, s->cyc, cc, scenes, paths, samples, n_wp, d_table_xy);
   if (rc != F110_OK) return rc;
   s->last_launches = 0;
-  return cycle_device_range(s, cc, 0, scenes, d_pose7, d_ranges, d_prev_steer, d_table_xy, paths, samples, d_wp_xy, n_wp, d_u0, d_status,
-                            d_iters, d_chosen, d_valid, (cudaStream_t)cuda_stream);
+  return f110api::cycle_device_range(s, s->cyc, cc, 0, scenes, d_pose7, d_ranges, d_prev_steer, d_table_xy, paths, samples, d_wp_xy, n_wp, d_u0, d_status,
+                            d_iters, d_chosen, d_valid, (cudaStream_t)cuda_stream, nullptr);
 }
 
 int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
@@ -475,20 +453,13 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_tab, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   }
-  // FNV-1a over the constant tables (20 KB): cheaper than two more copies per cycle
-  unsigned long long h = 1469598103934665603ull;
-  auto mix = [&h](const void* ptr, size_t n) {
-    const unsigned long long* w = static_cast<const unsigned long long*>(ptr);
-    for (size_t i = 0; i < n / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
-  };
-  mix(table_xy, n_tab); mix(wp_xy, n_wpb);
-  h ^= (unsigned long long)paths * 1315423911ull + (unsigned long long)samples * 2654435761ull + (unsigned long long)n_wp;
+  const unsigned long long h = f110api::table_hash(table_xy, n_tab, wp_xy, n_wpb, paths, samples, n_wp);
   if (h != s->cyc_tab_hash) {
     CUDA_TRY(cudaMemcpyAsync(d_tab, table_xy, n_tab, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_wp, wp_xy, n_wpb, cudaMemcpyHostToDevice, st));
     s->cyc_tab_hash = h;
   }
-  int rc = cycle_prepare(s, cc, scenes, paths, samples, n_wp, d_tab);
+  int rc = f110api::cycle_prepare(s, s->cyc, cc, scenes, paths, samples, n_wp, d_tab);
   if (rc != F110_OK) return rc;
   // Scenes are independent, so a large batch is pipelined as two halves over two streams: the copies and the small kernels of the
   // second half run under the solve of the first, and the second solve fills the first one's tail.  Measured at 205 scenes x 20
@@ -507,9 +478,9 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
     CUDA_TRY(cudaMemcpyAsync(d_rng + (size_t)a * cc->n_beams, ranges + (size_t)a * cc->n_beams, (size_t)(b - a) * cc->n_beams * sizeof(float),
                              cudaMemcpyHostToDevice, cs));
     if (prev_steer) CUDA_TRY(cudaMemcpyAsync(d_prev + a, prev_steer + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, cs));
-    rc = cycle_device_range(s, cc, a, b - a, d_pose + (size_t)a * 7, d_rng + (size_t)a * cc->n_beams, prev_steer ? d_prev + a : nullptr, d_tab,
+    rc = f110api::cycle_device_range(s, s->cyc, cc, a, b - a, d_pose + (size_t)a * 7, d_rng + (size_t)a * cc->n_beams, prev_steer ? d_prev + a : nullptr, d_tab,
                             paths, samples, d_wp, n_wp, (double*)(d_out + o_u0) + 2 * q0, (int32_t*)(d_out + o_st) + q0,
-                            (int32_t*)(d_out + o_it) + q0, (int32_t*)(d_out + o_ch) + a, d_out + o_val + (size_t)a * paths, cs);
+                            (int32_t*)(d_out + o_it) + q0, (int32_t*)(d_out + o_ch) + a, d_out + o_val + (size_t)a * paths, cs, nullptr);
     if (rc != F110_OK) { cudaStreamSynchronize(st); cudaStreamSynchronize(s->stream2); return rc; }
   }
   if (chunks > 1) {

@@ -109,7 +109,24 @@ BatchMPC::BatchMPC(const f110::Params& prm, int max_batch, int device, bool warm
   iters_.assign(max_batch, 0);
 }
 
-BatchMPC::~BatchMPC() { f110_mpc_destroy(solver_); }
+BatchMPC::BatchMPC(const f110::Params& prm, int max_batch, const std::vector<int>& devices, int shard_unit)
+    : max_batch_(max_batch), shard_unit_(shard_unit) {
+  Constraints con(prm);
+  config_ = config_from(prm, con);
+  f110_solver_default_settings(&settings_);
+  settings_.warm_start = 0;
+  const int rc = f110_mpc_create_multi(&config_, &settings_, max_batch, devices.data(), static_cast<int>(devices.size()), &multi_);
+  if (rc != F110_OK) throw std::runtime_error(std::string("BatchMPC: f110_mpc_create_multi failed: ") + f110_last_error());
+  records_.assign(static_cast<std::size_t>(max_batch) * record_doubles(), 0.0);
+  u0_.assign(2 * static_cast<std::size_t>(max_batch), 0.0);
+  status_.assign(max_batch, F110_UNSOLVED);
+  iters_.assign(max_batch, 0);
+}
+
+BatchMPC::~BatchMPC() {
+  f110_mpc_destroy(solver_);
+  f110_mpc_destroy_multi(multi_);
+}
 
 void BatchMPC::SetProblem(int b, const State& x0, const Input& in, const std::vector<State>& desired, const f110::Vector& l1,
                           const f110::Vector& l2) {
@@ -117,5 +134,7 @@ void BatchMPC::SetProblem(int b, const State& x0, const Input& in, const std::ve
 }
 
 int BatchMPC::Solve(int count) {
+  if (multi_)
+    return f110_mpc_solve_multi_host(multi_, count, shard_unit_, records_.data(), record_doubles(), u0_.data(), status_.data(), iters_.data());
   return f110_mpc_solve_host(solver_, count, records_.data(), record_doubles(), nullptr, nullptr, u0_.data(), status_.data(), iters_.data());
 }

@@ -66,7 +66,12 @@ class MPC {
 class BatchMPC {
  public:
   BatchMPC(const f110::Params& params, int max_batch, int device = 0, bool warm_start = false);
+  // Several GPUs of one box behind the same interface: Solve() cuts the batch into contiguous shards of whole `shard_unit`s (QPs
+  // that belong together, e.g. one scenario's lane x path QPs), one shard per device; the chosen controls of every device land on
+  // devices[0] through the solve kernels' own peer stores and come back in one copy.  Cold start (slots move with the sharding).
+  BatchMPC(const f110::Params& params, int max_batch, const std::vector<int>& devices, int shard_unit = 1);
   ~BatchMPC();
+  int num_devices() const { return multi_ ? f110_mpc_multi_devices(multi_) : 1; }
   BatchMPC(const BatchMPC&) = delete;
   BatchMPC& operator=(const BatchMPC&) = delete;
   int horizon() const { return config_.horizon; }
@@ -84,7 +89,8 @@ class BatchMPC {
   f110_mpc_config config_;
   f110_solver_settings settings_;
   f110_mpc_solver* solver_ = nullptr;
-  int max_batch_;
+  f110_mpc_multi* multi_ = nullptr;
+  int max_batch_, shard_unit_ = 1;
   std::vector<double> records_, u0_;
   std::vector<int32_t> status_, iters_;
 };

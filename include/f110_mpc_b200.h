@@ -30,6 +30,7 @@
 #ifndef F110_MPC_B200_H
 #define F110_MPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -196,6 +197,53 @@ int f110_cycle_host(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes,
  * Any pointer may be NULL. */
 int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, double** d_l1l2, double** d_recs,
                        int32_t** d_best_global);
+
+/* ---- asynchronous form of f110_cycle_host (the shape of the reference's own loop: OdomCallback computes cycle k+1 while
+ * DriveLoop applies cycle k's result, project.cpp:160-191, 220-238).  f110_cycle_submit queues the copies and kernels of one
+ * cycle and returns a ticket; f110_cycle_wait blocks until that cycle's results are in the caller's arrays.  At most TWO cycles
+ * may be in flight per handle: cycle k+1's host-to-device copies and perception kernels run under cycle k's solve; the solves
+ * themselves run in submission order (they share the handle's warm-start slots).  Inputs are read straight from the caller's
+ * buffers when those are pinned (cudaHostAlloc / cudaHostRegister) and must then stay untouched until the matching wait; pageable
+ * inputs are copied into the handle's own pinned staging before the call returns.  Results are identical to f110_cycle_host.
+ * `gathered` (f110_cycle_wait): NULL, or — on the root of an attached gather ring — world x rows x 4 doubles. */
+int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
+                      const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp,
+                      int* ticket);
+int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid,
+                    double* gathered);
+
+/* ---- multi-GPU: QPs are independent, shards are contiguous, the only exchange is a final gather of the
+ * packed rows (u0_v, u0_steer, status, iters) to one GPU — and that gather is the solve kernel's own store over NVLink.
+ *
+ * (1) one process, several GPUs: the reference-facing batched call (mirrors what MPC::Update does for one QP, mpc.cpp:69-143).
+ *     The batch is cut into contiguous shards of whole `unit`s (QPs that belong together, e.g. the 140 lane x path QPs of one
+ *     scenario); every GPU's kernel stores its rows into one buffer on devices[0] (peer access; one peer copy per GPU without it). */
+typedef struct f110_mpc_multi f110_mpc_multi;
+int f110_mpc_create_multi(const f110_mpc_config* cfg, const f110_solver_settings* settings, int max_batch, const int* devices,
+                          int n_devices, f110_mpc_multi** out);
+void f110_mpc_destroy_multi(f110_mpc_multi* m);
+int f110_mpc_solve_multi_host(f110_mpc_multi* m, int count, int unit, const double* recs, int rec_stride, double* u0,
+                              int32_t* status, int32_t* iters);
+int f110_mpc_multi_devices(const f110_mpc_multi* m);
+int f110_mpc_multi_uses_peer_stores(const f110_mpc_multi* m, int index);  /* 1: device `index` stores into devices[0] directly */
+int f110_mpc_multi_last_shard(const f110_mpc_multi* m, int index, int* first_qp, int* count);
+
+/* (2) one process per GPU (torchrun): a gather ring on the root rank's GPU, mapped into the other ranks through CUDA IPC.
+ *     Layout: world flags (int32), then `slots` slots of world x rows_per_rank x 4 doubles.  Rank r's cycle number c lands in
+ *     slot c % slots, block r; afterwards the rank raises flags[r] = c + 1 (f110_stream_signal) and the root's stream waits for
+ *     every flag (f110_stream_wait_flags: a stream memory operation, no kernel spins) before it reads the slot.  No rank may be
+ *     `slots` or more cycles ahead of the root's reads.  f110_gather_create zero-fills; the 64-byte handle goes to the peers by
+ *     any host channel.  f110_cycle_set_gather attaches the ring to the asynchronous cycle entry (NULL detaches);
+ *     f110_gather_slot + f110_mpc_set_packed_output do the same by hand for f110_mpc_solve_device. */
+int f110_gather_bytes(int world, int rows_per_rank, int slots, size_t* bytes);
+int f110_gather_create(int device, int world, int rows_per_rank, int slots, void** d_ring, unsigned char* ipc_handle64);
+int f110_gather_open(int device, const unsigned char* ipc_handle64, void** d_ring);
+int f110_gather_close(int device, void* d_ring, int opened);
+int f110_gather_slot(void* d_ring, int world, int rank, int rows_per_rank, int slots, long long cycle, double** d_rows,
+                     int32_t** d_flag);
+int f110_stream_signal(void* cuda_stream, int32_t* d_flag, int32_t value);
+int f110_stream_wait_flags(void* cuda_stream, const int32_t* d_flags, int n, int skip, int32_t value);
+int f110_cycle_set_gather(f110_mpc_solver* s, void* d_ring, int world, int rank, int rows_per_rank, int slots);
 
 /* ---- measurement utility (not on the solve path): FP64 FMA issue rate of `device` in TFLOP/s, the
  * roofline denominator for the ADMM kernel. */

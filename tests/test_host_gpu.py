@@ -102,3 +102,19 @@ def test_closed_loop_follows_raceline(pkg, workloads):
     progress = (nearest[-1] - nearest[0]) % len(xy)
     assert 150 < progress < 450                              # ~6 s at ~4.4 m/s on a 31.9 m lap of 500 points
     assert (traj[100:, 3] >= 3.0 - 1e-3).all() and (traj[100:, 3] <= 4.5 + 1e-3).all() and (np.abs(traj[:, 4]) <= 0.43 + 1e-3).all()
+
+
+def test_batch_mpc_over_all_visible_gpus_cpp(pkg, tmp_path):
+    # tests/host_multi_gpu.cpp: the C++ BatchMPC over every visible device (f110_mpc_create_multi) against the one-device BatchMPC
+    import os
+    import subprocess
+    pkg.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "f110-mpc_b200", "host")
+    exe = tmp_path / "host_multi_gpu"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", host, "-I", os.path.join(root, "include"), os.path.join(root, "tests", "host_multi_gpu.cpp"),
+                    "-o", str(exe), "-L", os.path.join(root, "f110-mpc_b200"), "-lf110mpc_host", "-lf110mpc_b200",
+                    "-Wl,-rpath," + os.path.join(root, "f110-mpc_b200")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "multi-GPU host checks passed" in r.stdout
