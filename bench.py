@@ -229,6 +229,15 @@ class PeerGather:
             self.ring = None
 
 
+def ring_slot_to_host(torch, dev, gather, cycle, world, rows):
+    """rank 0: the ring slot of `cycle` as a (world, rows, 4) numpy array"""
+    ptr, _ = gather.ring.slot(cycle)      # rank 0's block comes first, the other ranks' blocks follow
+
+    class _Dev:   # the raw ring pointer as a torch tensor (CUDA array interface)
+        __cuda_array_interface__ = {"shape": (world * rows * 4,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(_Dev(), device=dev).cpu().numpy().reshape(world, rows, 4)
+
+
 def main_product(args):
     import torch
     import torch.distributed as dist
@@ -334,11 +343,7 @@ def main_product(args):
         all_ok = [torch.zeros_like(ok_local) for _ in range(world)]
         dist.all_gather(all_ok, ok_local)
         if rank == 0:
-            slot0, _ = gather.ring.slot(cyc[0] - 1)   # rank 0's block comes first, the other ranks' blocks follow
-
-            class _Dev:   # the raw ring pointer as a torch tensor (CUDA array interface)
-                __cuda_array_interface__ = {"shape": (world * NQ * 4,), "typestr": "<f8", "data": (slot0, False), "version": 2}
-            host = torch.as_tensor(_Dev(), device=dev).cpu().numpy().reshape(world, NQ, 4)
+            host = ring_slot_to_host(torch, dev, gather, cyc[0] - 1, world, NQ)
             gathered_check = {"rows_solved_per_rank": [int((host[r, :B, 2] == 1).sum()) for r in range(world)],
                               "solved_per_rank_reported": [int(x.item()) for x in all_ok],
                               "rank0_rows_equal_local": bool(np.array_equal(host[0, :B, :2], d_u0.cpu().numpy()))}
@@ -527,22 +532,8 @@ def main_product(args):
 # --configs: the five BASELINE.json configurations, each measured on the GPU with the CPU oracle beside it.
 # Not the default bench line: writes a JSON report (profiles/configs_rNN.json).
 def config4_records(W, n_sc=64):
-    """BASELINE config 4: 7 lanes x 20 mini-paths x 64 scenarios = 8960 QPs.  Lanes are not implemented in the reference
-    (README:18); SURVEY 8d's synthetic definition: lane l = skirk shifted l x 0.25 m along the left normal, scenario s = station
-    s x (500/64), QP (s, l, p) = ego on lane l at that station tracking mini-path p.  Scenario-major, so a rank's shard is contiguous."""
-    xy, ori = W.skirk_waypoints()
-    head = W.reference_data()["skirk_heading"]
-    table20 = W.traj_table(steer_discrete=19)
-    recs = []
-    for sc in range(n_sc):
-        i = int(sc * (500 / 64))
-        for lane in range(7):
-            nx, ny = -np.sin(head[i]), np.cos(head[i])
-            x, y, yaw = float(xy[i, 0]) + lane * 0.25 * nx, float(xy[i, 1]) + lane * 0.25 * ny, float(ori[i])
-            for pidx in range(20):
-                ref = np.zeros((N_HORIZON, 3)); ref[:, :2] = W.path_to_world(table20[pidx, :N_HORIZON, :2], x, y, yaw)
-                recs.append(np.concatenate([[x, y, yaw], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
-    return np.array(recs)
+    """BASELINE config 4 (7 lanes x 20 mini-paths x 64 scenarios = 8960 QPs): f110-mpc_b200/workloads.py::config4_records."""
+    return W.config4_records(n_sc, N_HORIZON)
 
 
 def main_config4(args):
@@ -570,16 +561,27 @@ def main_config4(args):
     d = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
     u0 = torch.empty(b, 2, dtype=torch.float64, device=dev); st = torch.empty(b, dtype=torch.int32, device=dev)
     it = torch.empty(b, dtype=torch.int32, device=dev)
-    packed = torch.empty(b, 4, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     gathered = None
+    # the gather: every rank's solve kernel stores its packed rows into a ring on rank 0's GPU (NVLink, CUDA IPC); NCCL only as fallback
+    gather = PeerGather(M, dist, torch, dev, world, rank, local, max(sizes), 8) if world > 1 else None
+    peer = gather is not None and gather.ok
+    packed = torch.empty(b, 4, dtype=torch.float64, device=dev) if not peer else None
+    cyc = [0]
 
     def step():
+        if peer:
+            rows, _ = gather.ring.slot(cyc[0])
+            cyc[0] += 1
+            M._check(M.lib().f110_mpc_set_packed_output(sol._h, rows), "f110_mpc_set_packed_output")
+            sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream)
+            return None
         sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream, packed=packed)
         return SH.gather_results(packed, world, max_rows=max(sizes), sizes=sizes)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -596,7 +598,11 @@ def main_config4(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
     if rank == 0:
-        g = gathered.cpu().numpy()
+        if peer:   # the last step's slot: rank blocks in batch order, trimmed to each rank's shard
+            blocks = ring_slot_to_host(torch, dev, gather, cyc[0] - 1, world, max(sizes))
+            g = np.concatenate([blocks[r, :sizes[r]] for r in range(world)], axis=0)
+        else:
+            g = gathered.cpu().numpy()
         from oracle import oracle_py as O
         O.build()
         idx = np.arange(0, total, 35)           # a sample across every rank's shard, checked against the CPU oracle
@@ -606,10 +612,14 @@ def main_config4(args):
                                                         "qps_total": int(total), "qps_per_rank": sizes, "l2_policy": "256 MiB flush between steps"},
                           "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                           "ms_per_step": ms / args.steps, "scaling": "strong", "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                          "gather": "solve kernels' NVLink stores into an IPC-mapped ring on rank 0" if peer else ("NCCL all-gather" if world > 1 else None),
                           "gathered_rows": int(g.shape[0]), "solved": int((g[:, 2] == 1).sum()),
                           "parity_sample": {"n": int(len(idx)), "status_equal": bool((g[idx, 2] == o["status"]).all()),
                                             "iters_equal": bool((g[idx, 3] == o["iters"]).all()),
                                             "max_abs_du0": float(np.abs(g[idx, :2] - u0o).max())}}))
+    barrier()
+    if gather:
+        gather.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -632,6 +642,9 @@ def main_sweep(args):
     B = 4096
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    gather = PeerGather(M, dist, torch, dev, world, rank, local, B, 8) if world > 1 else None
+    peer = gather is not None and gather.ok
+    cyc = [0]
     rows = {}
     for N in (10, 20, 30, 50, 100):
         recs = W.tracking_batch(B, N, seed=20240905 + rank)
@@ -642,10 +655,17 @@ def main_sweep(args):
         it = torch.empty(B, dtype=torch.int32, device=dev); packed = torch.empty(B, 4, dtype=torch.float64, device=dev)
 
         def step():
+            if peer:   # packed rows straight into the ring on rank 0's GPU
+                rp, _ = gather.ring.slot(cyc[0])
+                cyc[0] += 1
+                M._check(M.lib().f110_mpc_set_packed_output(sol._h, rp), "f110_mpc_set_packed_output")
+                sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream)
+                return None
             sol.solve_device(d, None, None, u0, st, it, None, None, stream=stream, packed=packed)
             return SH.gather_results(packed, world, max_rows=B, sizes=[B] * world)
         for _ in range(max(args.warmup, 3)):
             g = step()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -653,19 +673,28 @@ def main_sweep(args):
         for i in range(args.steps):
             flush.fill_(i & 0xFF)
             ev[i][0].record(); g = step(); ev[i][1].record()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ms = torch.tensor([float(sum(a.elapsed_time(c) for a, c in ev))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        gg = g.cpu().numpy()
+        if peer:
+            gg = ring_slot_to_host(torch, dev, gather, cyc[0] - 1, world, B).reshape(world * B, 4) if rank == 0 else np.zeros((1, 4))
+        else:
+            gg = g.cpu().numpy()
         rows["N=%d" % N] = {"qps_total": world * B, "ms_per_step": ms.item() / args.steps, "solves_per_s": world * B * args.steps / (ms.item() * 1e-3),
                             "solved": int((gg[:, 2] == 1).sum()), "mean_iters": float(gg[:, 3].mean())}
     if rank == 0:
         print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "scaling": "weak", "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "cfg5: horizon sweep, 4096 QPs per GPU, OSQP defaults, cold start", "l2_policy": "256 MiB flush between steps"},
+                          "gather": "solve kernels' NVLink stores into an IPC-mapped ring on rank 0" if peer else ("NCCL all-gather" if world > 1 else None),
                           "horizons": rows}))
+    if world > 1:
+        dist.barrier()
+    if gather:
+        gather.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

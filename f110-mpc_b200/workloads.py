@@ -150,3 +150,62 @@ def scene_batch(S, seed=20240902):
         yaws[s] = yaw
         scans[s] = render_scan(x, y, yaw, boxes)
     return poses, yaws, scans
+
+
+# ---- BASELINE.json configurations as record batches ---------------------------------------------
+def config1_records(n=500, N=30):
+    """Config 1: one tracking QP per skirk waypoint i = 0..n-1 (pose on the raceline, free scan -> the straight-ahead mini-path is
+    valid and closest to the look-ahead point on straights; here the reference of cycle i is the mini-path whose end point is
+    nearest the raceline 2.5 m ahead), previous steering filled in by the caller (warm-started sequence)."""
+    xy, ori = skirk_waypoints()
+    table = traj_table()
+    ends = table[:, -1, :2]
+    recs = np.zeros((n, record_doubles(N)))
+    for i in range(n):
+        x, y, yaw = float(xy[i % len(xy), 0]), float(xy[i % len(xy), 1]), float(ori[i % len(xy)])
+        # look-ahead target: first raceline point at least 2.5 m ahead along the index order
+        j = i
+        while np.hypot(xy[j % len(xy), 0] - x, xy[j % len(xy), 1] - y) < 2.5 and j < i + len(xy):
+            j += 1
+        tx, ty = float(xy[j % len(xy), 0]) - x, float(xy[j % len(xy), 1]) - y
+        c, sn = np.cos(yaw), np.sin(yaw)
+        tcar = np.array([c * tx + sn * ty, -sn * tx + c * ty])
+        p = int(np.argmin(np.hypot(ends[:, 0] - tcar[0], ends[:, 1] - tcar[1])))
+        ref = np.zeros((N, 3))
+        ref[:, :2] = path_to_world(table[p, :N, :2], x, y, yaw)
+        recs[i] = np.concatenate([[x, y, yaw], [4.5, 0.0], np.zeros(6), ref.reshape(-1)])
+    return recs
+
+
+def config3_scans(B=1024, seed=20240903):
+    """Config 3: B synthetic scans — ranges U(0.5, 2.8) with 1-3 gaps (U(3.5, 10)) 8..200 beams wide inside the field of view."""
+    rng = np.random.default_rng(seed)
+    scans = np.zeros((B, SCAN_BEAMS), dtype=np.float32)
+    for b in range(B):
+        r = rng.uniform(0.5, 2.8, SCAN_BEAMS).astype(np.float32)
+        for _ in range(rng.integers(1, 4)):
+            a = rng.integers(150, 880)
+            w = rng.integers(8, 201)
+            r[a:a + w] = rng.uniform(3.5, 10.0)
+        scans[b] = r
+    return scans
+
+
+def config4_records(n_sc=64, N=30):
+    """Config 4: 7 lanes x 20 mini-paths x 64 scenarios = 8960 QPs.  Lanes are not implemented in the reference (README:18);
+    SURVEY 8d's synthetic definition: lane l = skirk shifted l x 0.25 m along the left normal, scenario s = station s x (500/64),
+    QP (s, l, p) = ego on lane l at that station tracking mini-path p.  Scenario-major, so a rank's shard is contiguous."""
+    xy, ori = skirk_waypoints()
+    head = reference_data()["skirk_heading"]
+    table20 = traj_table(steer_discrete=19)
+    recs = []
+    for sc in range(n_sc):
+        i = int(sc * (500 / 64))
+        for lane in range(7):
+            nx, ny = -np.sin(head[i]), np.cos(head[i])
+            x, y, yaw = float(xy[i, 0]) + lane * 0.25 * nx, float(xy[i, 1]) + lane * 0.25 * ny, float(ori[i])
+            for pidx in range(20):
+                ref = np.zeros((N, 3))
+                ref[:, :2] = path_to_world(table20[pidx, :N, :2], x, y, yaw)
+                recs.append(np.concatenate([[x, y, yaw], [4.5, 0.0], [0.3, -0.8, 1.5], [-0.4, 0.7, 2.0], ref.reshape(-1)]))
+    return np.array(recs)

@@ -51,7 +51,61 @@ def main():
     tab = O.traj_table()
     A, Bm, Cv = O.linearize(0.3, 4.5, -0.1, W.DT_F32)
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), traj_table=tab, lin_A=A, lin_B=Bm, lin_C=Cv)
+    make_fixed_points()
     print("wrote", sorted(os.listdir(OUT)))
+
+
+def make_fixed_points():
+    """Exact optima of sample QPs of every BASELINE.json configuration, from tests/qp_exact.py: the QP assembled in numpy straight
+    from the reference's builders (mpc.cpp:208-306, model.cpp:30-59) and solved by a dense active-set method whose answer is
+    accepted only if it passes the KKT conditions to 1e-9.  No OSQP iteration is involved, so these vectors pin the FIXED POINT
+    of the solve independently of oracle/osqp_restated.hpp and tests/osqp_numpy.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import qp_exact as E
+
+    def exact_batch(recs, N, gap_mode, want):
+        X, Y, keep = [], [], []
+        for i, r in enumerate(recs):
+            if len(keep) == want:
+                break
+            P, q, A, l, u = E.assemble(r, N, gap_mode)
+            try:
+                x, y, _ = E.solve_exact(P, q, A, l, u, max_changes=150)
+            except RuntimeError:
+                continue            # infeasible (gap mode 1 on the all-ones stage-0 pair): not a fixed-point sample
+            X.append(x); Y.append(y); keep.append(i)
+        return recs[keep], np.array(X), np.array(Y)
+
+    def n_active(Y, N):
+        return int((np.abs(Y[:, 3 * (N + 1):]) > 1e-9).sum())
+
+    samples = {
+        "cfg1_skirk_N30": (W.config1_records(500)[::16], 30, 0),
+        "cfg2_minipaths_N30": (W.tracking_batch(32, 30, seed=20240902), 30, 0),
+        "cfg3_gap0_N30": (W.tracking_batch(32, 30, seed=20240903, gaps=True), 30, 0),
+        "cfg3_gap1_N30": (W.tracking_batch(400, 30, seed=20240903, gaps=True), 30, 1),
+        "cfg3_gap2_N30": (W.tracking_batch(32, 30, seed=8, gaps=True), 30, 2),
+        "cfg4_lanes_N30": (W.config4_records(64)[::280], 30, 0),
+        "cfg5_N10": (W.tracking_batch(24, 10, seed=20240905), 10, 0),
+        "cfg5_N20": (W.tracking_batch(24, 20, seed=20240905), 20, 0),
+        "cfg5_N50": (W.tracking_batch(16, 50, seed=20240905), 50, 0),
+        "cfg5_N100": (W.tracking_batch(8, 100, seed=20240905), 100, 0),
+    }
+    # half-planes that BIND: a wall across the reference path at its 26th point (the car must brake to stay behind it) — line 2 —
+    # and a far-away line 1; gap rows on from stage 1 (gap_mode 2)
+    wall = W.tracking_batch(48, 30, seed=20240913)
+    for r in wall:
+        ref = r[11:].reshape(30, 3)
+        f = (ref[29, :2] - ref[0, :2]) / np.linalg.norm(ref[29, :2] - ref[0, :2])
+        r[5:8] = (f[0], f[1], 100.0)                       # f.p >= -100: never active
+        r[8:11] = (-f[0], -f[1], float(f @ ref[25, :2]))    # -f.p >= -f.ref_25: stay behind the wall
+    samples["cfg3_gap2_wall_N30"] = (wall, 30, 2)
+    for name, (recs, N, gap_mode) in samples.items():
+        recs, X, Y = exact_batch(recs, N, gap_mode, 32)
+        assert len(recs) >= 8, name
+        np.savez_compressed(os.path.join(OUT, "exact_%s.npz" % name), recs=recs, x=X, y=Y, N=N, gap_mode=gap_mode)
+        print("exact_%s: %d QPs, %d active inequality rows, %d of them half-plane rows" %
+              (name, len(recs), n_active(Y, N), int((np.abs(Y[:, 3 * (N + 1):5 * (N + 1)]) > 1e-9).sum())))
 
 
 if __name__ == "__main__":
