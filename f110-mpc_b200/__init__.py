@@ -54,7 +54,8 @@ EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_
            "f110_mpc_create_multi", "f110_mpc_destroy_multi", "f110_mpc_solve_multi_host", "f110_mpc_multi_devices",
            "f110_mpc_multi_uses_peer_stores", "f110_mpc_multi_last_shard", "f110_gather_bytes", "f110_gather_create",
            "f110_gather_open", "f110_gather_close", "f110_gather_slot", "f110_stream_signal", "f110_stream_wait_flags",
-           "f110_cycle_set_gather"]
+           "f110_cycle_set_gather", "f110_fleet_create", "f110_fleet_destroy", "f110_fleet_reset", "f110_fleet_run",
+           "f110_fleet_get_pose"]
 
 
 def build(force=False, verbose=False):
@@ -118,6 +119,12 @@ def lib():
         L.f110_stream_signal.argtypes = [vp, vp, C.c_int32]
         L.f110_stream_wait_flags.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int32]
         L.f110_cycle_set_gather.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.f110_fleet_create.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(vp)]
+        L.f110_fleet_destroy.argtypes = [vp]
+        L.f110_fleet_reset.argtypes = [vp, vp, vp]
+        L.f110_fleet_run.argtypes = [vp, C.c_int, vp, vp]
+        L.f110_fleet_get_pose.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -303,6 +310,50 @@ class MpcSolver:
     def close(self):
         if self._h:
             lib().f110_mpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Fleet:
+    """f110_fleet_*: `cars` simulated cars in closed loop on the device (the reference's plan / control / drive state machine against
+    the kinematic plant).  `solver` must have warm_start = 1 and max_batch >= cars."""
+    PLAN, IDLE, DROP, CONTROL = 0, 1, 2, 3
+
+    def __init__(self, solver, cc, cars, table_xy, wp_xy, drive_every=2, scan_every=4, dt_tick=0.01):
+        self.solver, self.cars = solver, cars
+        table_xy = np.ascontiguousarray(table_xy, dtype=np.float64); wp_xy = np.ascontiguousarray(wp_xy, dtype=np.float32)
+        self._h = C.c_void_p()
+        _check(lib().f110_fleet_create(solver._h, C.byref(cc), cars, C.c_void_p(table_xy.ctypes.data), table_xy.shape[0], table_xy.shape[1],
+                                       C.c_void_p(wp_xy.ctypes.data), wp_xy.shape[0], drive_every, scan_every, dt_tick, C.byref(self._h)),
+               "f110_fleet_create")
+
+    def reset(self, pose3, ranges):
+        pose3 = np.ascontiguousarray(pose3, dtype=np.float64); ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        assert pose3.shape == (self.cars, 3) and ranges.shape[0] == self.cars
+        _check(lib().f110_fleet_reset(self._h, C.c_void_p(pose3.ctypes.data), C.c_void_p(ranges.ctypes.data)), "f110_fleet_reset")
+
+    def run(self, ticks, log=True):
+        """Returns (log_i (ticks, cars, 4) int32, log_d (ticks, cars, 13) float64) or None without logging."""
+        if not log:
+            _check(lib().f110_fleet_run(self._h, ticks, None, None), "f110_fleet_run")
+            return None
+        li = np.empty((ticks, self.cars, 4), dtype=np.int32); ld = np.empty((ticks, self.cars, 13))
+        _check(lib().f110_fleet_run(self._h, ticks, C.c_void_p(li.ctypes.data), C.c_void_p(ld.ctypes.data)), "f110_fleet_run")
+        return li, ld
+
+    def poses(self):
+        p = np.empty((self.cars, 3))
+        _check(lib().f110_fleet_get_pose(self._h, C.c_void_p(p.ctypes.data)), "f110_fleet_get_pose")
+        return p
+
+    def close(self):
+        if self._h:
+            lib().f110_fleet_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

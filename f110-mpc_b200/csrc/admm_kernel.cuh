@@ -68,7 +68,8 @@ cudaError_t launch_collision(int scenes, int paths, int samples, int blocks, flo
 // perception / planning kernels (pipeline_kernels.cu, compiled with -fmad=false)
 cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
                               float angle_inc, float thresh, float divider, float buffer, const double* pose7, const float* ranges,
-                              float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st);
+                              float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st,
+                              int mode = 0);   // 0: everything, 1: no grid fill, 2: the grid fill only
 cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,
                           const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st);
 cudaError_t launch_build_records(int scenes, int paths, int samples, int N, int stride, int qp_mode, double v_lin, const double* pose7,

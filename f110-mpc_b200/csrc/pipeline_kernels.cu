@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
                                                                   const float* __restrict__ ranges, float* __restrict__ grid,
                                                                   float* __restrict__ offset, double* __restrict__ rot,
                                                                   double* __restrict__ pose_xy, double* __restrict__ l1l2,
-                                                                  int32_t* __restrict__ gap) {
+                                                                  int32_t* __restrict__ gap, int mode) {
+  // mode 0: everything;  1: no grid fill (rotation, pose, half-planes only: the grid of an earlier scan stays, as between two
+  // ScanCallbacks of the reference, project.cpp:41-59);  2: the grid fill only
   extern __shared__ unsigned char prep_sm[];   // blocks * blocks occupancy bytes, then 2 x words mask words
   const int sc = blockIdx.x;
   if (sc >= scenes) return;
@@ -186,8 +188,9 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
   const float offx = (float)(p[0] + 0.275 * cosf_cr(yaw));                      // :63
   const float offy = (float)(p[1] + 0.275 * sinf_cr(yaw));                      // :64
   const float* r = ranges + (size_t)sc * n_beams;
-  if (threadIdx.x == 0) {
-    offset[2 * sc] = offx; offset[2 * sc + 1] = offy;
+  const bool do_fill = mode != 1, do_rest = mode != 2;
+  if (threadIdx.x == 0 && do_fill) { offset[2 * sc] = offx; offset[2 * sc + 1] = offy; }
+  if (threadIdx.x == 0 && do_rest) {
     double q[4];
     quaternion_of(basis_of(p[3], p[4], p[5], p[6]), q);
     const Basis b = basis_of(q[0], q[1], q[2], q[3]);
@@ -197,10 +200,11 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
   __syncthreads();
   const bool gap_warp = (l1l2 != nullptr) && (threadIdx.x >= PREP_THREADS - 32);
   if (gap_warp) {
+    if (do_rest)
     // State(pose.x, pose.y, float yaw) of project.cpp:163-164
     find_half_spaces_warp(threadIdx.x & 31, masks, masks + (n_beams + 31) / 32, n_beams, num_scans, angle_min, angle_inc, ftg_thresh,
                           divider, buffer, p[0], p[1], yaw, r, l1l2 + 6 * (size_t)sc, gap + 2 * (size_t)sc);
-  } else {
+  } else if (do_fill) {
     const int stampers = (l1l2 != nullptr) ? PREP_THREADS - 32 : PREP_THREADS;
     const float half = (float)(blocks / 2);
     const int nb = num_scans < n_beams ? num_scans : n_beams;
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
     }
   }
   __syncthreads();
+  if (!do_fill) return;
   float* g = grid + (size_t)sc * ncell;
   for (int i = threadIdx.x; i < ncell; i += PREP_THREADS) g[i] = cells[i] ? 1.f : 0.f;
 }
@@ -380,11 +385,11 @@ __global__ void __launch_bounds__(32 * SB_WARPS) build_records_kernel(int scenes
 
 cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
                               float angle_inc, float thresh, float divider, float buffer, const double* pose7, const float* ranges,
-                              float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st) {
+                              float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st, int mode) {
   if (scenes == 0) return cudaSuccess;
   const size_t smem = (size_t)(blocks * blocks + 15) / 16 * 16 + 2 * (size_t)((n_beams + 31) / 32) * sizeof(unsigned);
   scene_prep_kernel<<<scenes, PREP_THREADS, smem, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, thresh,
-                                                        divider, buffer, pose7, ranges, grid, offset, rot, pose_xy, l1l2, gap);
+                                                        divider, buffer, pose7, ranges, grid, offset, rot, pose_xy, l1l2, gap, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,

@@ -245,6 +245,26 @@ int f110_stream_signal(void* cuda_stream, int32_t* d_flag, int32_t value);
 int f110_stream_wait_flags(void* cuda_stream, const int32_t* d_flags, int n, int skip, int32_t value);
 int f110_cycle_set_gather(f110_mpc_solver* s, void* d_ring, int world, int rank, int rows_per_rank, int slots);
 
+/* ---- batched closed loop: `cars` simulated cars, each running the reference's control loop
+ * (OdomCallback / ScanCallback / DriveLoop, project.cpp:41-238: plan a mini-path when none is held, otherwise one warm-started MPC
+ * cycle per odometry tick against the held path, path dropped within 1.98 m of its end, previous inputs kept when a solve fails)
+ * against the kinematic plant (Model::simulate_dynamics, model.cpp:61-76) — `ticks` ticks on the device with no host round trip.
+ * Car b uses warm-start slot b of `s`, which must have been created with warm_start = 1 and max_batch >= cars; cc->qp_mode must be 0.
+ * Each car keeps one scan (car frame) for the whole run.  Tick order: odometry, scan (every scan_every ticks), drive (every
+ * drive_every ticks), plant step of dt_tick seconds.
+ *   f110_fleet_reset   pose3: cars x (x, y, yaw);  ranges: cars x n_beams;  clears every car's state and the solver's warm starts
+ *   f110_fleet_run     optional logs (both or neither), one row per (tick, car):
+ *                        log_i x4: phase (0 plan, 1 idle before the first scan, 2 path dropped, 3 MPC cycle), chosen path of a planning
+ *                                  tick (-1 none valid, -2 not a planning tick), status and iterations of an MPC cycle
+ *                        log_d x13: x, y, yaw at the tick's odometry; input published (v, steer); l1, l2 of the tick; u0 of an MPC cycle */
+typedef struct f110_fleet f110_fleet;
+int f110_fleet_create(f110_mpc_solver* s, const f110_cycle_config* cc, int cars, const double* table_xy, int paths, int samples,
+                      const float* wp_xy, int n_wp, int drive_every, int scan_every, double dt_tick, f110_fleet** out);
+void f110_fleet_destroy(f110_fleet* f);
+int f110_fleet_reset(f110_fleet* f, const double* pose3, const float* ranges);
+int f110_fleet_run(f110_fleet* f, int ticks, int32_t* log_i, double* log_d);
+int f110_fleet_get_pose(f110_fleet* f, double* pose3);
+
 /* ---- measurement utility (not on the solve path): FP64 FMA issue rate of `device` in TFLOP/s, the
  * roofline denominator for the ADMM kernel. */
 int f110_bench_fp64_fma(int device, int iters, double* tflops_out);
