@@ -26,7 +26,8 @@ class MpcConfig(C.Structure):
     """f110_mpc_config"""
     _fields_ = [("horizon", C.c_int32), ("gap_mode", C.c_int32), ("dt", C.c_double), ("wheelbase", C.c_double),
                 ("q", C.c_double * 3), ("r", C.c_double * 2), ("u_des", C.c_double * 2), ("u_min", C.c_double * 2),
-                ("u_max", C.c_double * 2), ("rate_rows", C.c_int32), ("reserved", C.c_int32), ("rate_delta", C.c_double)]
+                ("u_max", C.c_double * 2), ("rate_rows", C.c_int32), ("state_rows", C.c_int32), ("rate_delta", C.c_double),
+                ("state_lim", C.c_double)]
 
 
 class SolverSettings(C.Structure):
@@ -134,14 +135,17 @@ def _check(rc, what):
         raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, lib().f110_last_error().decode()))
 
 
-def default_config(horizon=30, gap_mode=0, rate_delta=None):
-    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; None = the reference's row set."""
+def default_config(horizon=30, gap_mode=0, rate_delta=None, state_lim=None):
+    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; state_lim: d of Constraints::SetXLims ->
+    3(N+1) state-box rows appended; None = the reference's row set."""
     c = MpcConfig()
     lib().f110_mpc_default_config(C.byref(c))
     c.horizon = horizon
     c.gap_mode = gap_mode
     if rate_delta is not None:
         c.rate_rows, c.rate_delta = 1, rate_delta
+    if state_lim is not None:
+        c.state_rows, c.state_lim = 1, state_lim
     return c
 
 
@@ -190,7 +194,7 @@ class MpcSolver:
         self.settings = settings or default_settings()
         self.N = self.config.horizon
         self.n = 5 * self.N + 3
-        self.m = 7 * self.N + 5 + (self.N if self.config.rate_rows else 0)   # f110_mpc_num_rows
+        self.m = 7 * self.N + 5 + (self.N if self.config.rate_rows else 0) + (3 * (self.N + 1) if self.config.state_rows else 0)   # f110_mpc_num_rows
         self.max_batch = max_batch
         self.device = device
         self._h = C.c_void_p()

@@ -420,8 +420,17 @@ struct RateExt<true> {
   double rbase;            // centre of its bounds: steer_prev on stage 0, else 0; the row lives in [rbase - D, rbase + D]
   double wvi;              // 1 / (R_v + sigma_v + rho_box_v + b_v' R_{k+1} b_v): pivot of the speed elimination
 };
-template <bool RATE>
-struct StageT : Stage, RateExt<RATE> {};
+// What the state-box rows add to a lane (empty otherwise): three identity rows on x_k.
+template <bool SBOX>
+struct SBoxExt {};
+template <>
+struct SBoxExt<true> {
+  double zs[3], ys[3];     // row iterates
+  double rs[3], is[3];     // rho and 1/rho
+  double slo[3], shi[3];   // bounds: x_cur -+ d on x and y, -+INFTY on the orientation (Constraints::SetXLims, constraints.cpp:108-114)
+};
+template <bool RATE, bool SBOX = false>
+struct StageT : Stage, RateExt<RATE>, SBoxExt<SBOX> {};
 
 // per-QP scratch line in global memory (L2): [SCR_ROWS_ALLOC][T] doubles, element-major, one column per stage
 constexpr int SCR_DX = 0, SCR_DU = 3, SCR_ED = 5, SCR_EG = 8, SCR_EB = 10;       // scaling vectors D, E
@@ -431,7 +440,8 @@ constexpr int SCR_CG = 31, SCR_CB = 33;                 // row class codes of th
 constexpr int SCR_NQ = 35, SCR_SNQ = 36;                // ||q||_inf unscaled / scaled (termination checks only)
 constexpr int SCR_ER = 37, SCR_WR = 38, SCR_CR = 39, SCR_PYR = 40;   // steering-rate row: E, e^2/c, class, previous y
 constexpr int SCR_ZD = 41;                              // z of the dynamics rows before the first iteration
-constexpr int SCR_ROWS = 44;
+constexpr int SCR_ES = 44, SCR_WS = 47, SCR_CS = 50, SCR_PYS = 53;   // state-box rows: E, e^2/c, class, previous y
+constexpr int SCR_ROWS = 56;
 static_assert(SCR_ROWS <= SCR_ROWS_ALLOC, "scratch line too short");
 
 }  // namespace

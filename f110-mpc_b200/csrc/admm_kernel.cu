@@ -9,11 +9,16 @@ cudaError_t launch_admm_w2(const KParams& p, cudaStream_t stream);            //
 cudaError_t launch_admm_w4(const KParams& p, cudaStream_t stream);            // horizons 64..127, four warps per QP
 cudaError_t launch_admm_w1r(const KParams& p, cudaStream_t stream, int nlev); // + steering-rate rows, horizons 1..31
 cudaError_t launch_admm_w2r(const KParams& p, cudaStream_t stream);           // + steering-rate rows, horizons 32..63
+cudaError_t launch_admm_w1s(const KParams& p, cudaStream_t stream, int nlev); // + state-box rows, horizons 1..31
 
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {
   int nlev = 0;
   while ((1 << nlev) <= p.N) ++nlev;
   if (launches) *launches = 1;
+  if (p.state_rows) {   // (f110_mpc_create refuses them with steering-rate rows or above horizon 31)
+    if (p.rate_rows || nlev < 1 || nlev > 5) return cudaErrorInvalidValue;
+    return launch_admm_w1s(p, stream, nlev);
+  }
   if (p.rate_rows) {
     // the 4x4 multipliers of a 4-warp QP do not fit in one SM's shared memory: horizons above 63 are refused at create
     if (nlev >= 1 && nlev <= 5) return launch_admm_w1r(p, stream, nlev);

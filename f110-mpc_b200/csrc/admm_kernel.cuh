@@ -14,7 +14,7 @@ namespace f110 {
 
 // per-QP scratch line in global memory: scaling vectors, previous iterate, factor-step inputs (row indices SCR_* in
 // admm_kernel_impl.cuh), one column per stage
-constexpr int SCR_ROWS_ALLOC = 44;                       // rows of the per-QP scratch line (37 used, 41 with steering-rate rows)
+constexpr int SCR_ROWS_ALLOC = 56;                       // rows of the per-QP scratch line (44 used, 56 with state-box rows)
 constexpr int SCRATCH_DOUBLES = SCR_ROWS_ALLOC * 128;    // line length at 4 warps per QP (horizon 64..127); 32 / 64 columns below
 constexpr int TM_COLS = 256;                             // tensor-memory columns one persistent CTA of the TMEM variant allocates (two CTAs per SM own all 512)
 constexpr int WORK_SLOTS = 64;                           // work-counter pairs a handle cycles through (one per launch in flight) + one for the captured B = 1 graph
@@ -29,6 +29,9 @@ struct KParams {
   // steering-rate rows (f110_mpc_config.rate_rows): N extra rows  delta_k - delta_{k-1} in [-rate_delta, rate_delta]
   int rate_rows;
   double rate_delta;
+  // state-box rows (f110_mpc_config.state_rows): 3(N+1) extra rows  x_k, y_k in [x_cur -+ state_lim], ori_k free
+  int state_rows;
+  double state_lim;
   // OSQP settings (f110_solver_settings)
   double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval, warm_start;
@@ -52,10 +55,10 @@ struct KParams {
   int* work;              // tensor-memory variant: {next QP, warps run dry}, both 0 at launch; the kernel re-arms them itself
 };
 
-// constraint rows: dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N | steering rate N (optional)
-__host__ __device__ inline int num_rows(int N, int rate_rows) { return 7 * N + 5 + (rate_rows ? N : 0); }
+// constraint rows: dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N | steering rate N (optional) | state box 3(N+1) (optional)
+__host__ __device__ inline int num_rows(int N, int rate_rows, int state_rows = 0) { return 7 * N + 5 + (rate_rows ? N : 0) + (state_rows ? 3 * (N + 1) : 0); }
 // doubles per warm-start slot: x(n) + z(m) + y(m) + rho + valid flag
-__host__ __device__ inline int state_doubles(int N, int rate_rows) { return (5 * N + 3) + 2 * num_rows(N, rate_rows) + 2; }
+__host__ __device__ inline int state_doubles(int N, int rate_rows, int state_rows = 0) { return (5 * N + 3) + 2 * num_rows(N, rate_rows, state_rows) + 2; }
 
 // Launch the solve for p.B QPs on `stream`. Returns the cudaError of the launch.
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches);

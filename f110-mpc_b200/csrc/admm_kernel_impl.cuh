@@ -49,11 +49,12 @@ namespace f110 {
 // of shared memory, the per-QP scratch line lives in shared memory instead of global memory, and the caller is a persistent
 // four-warp CTA whose warps fetch QPs from a work counter (admm_kernel_tm below).  `unit` = blockIdx.x for the one-CTA-per-unit
 // kernels, the fetched index for the persistent one; `smem_all` = this unit's shared-memory region; `tid` = thread within the unit.
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM, bool SBOX = false>
 __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
                                            const int tid, [[maybe_unused]] const uint32_t rec_parity) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
   static_assert(!TM || (WPQ == 1 && QPW == 1 && !RATE), "tensor-memory variant: one warp per QP, base row set");
+  static_assert(!SBOX || (WPQ == 1 && QPW == 1 && !RATE && !TM), "state-box rows: one-warp shared-memory kernel, without steering-rate rows");
   constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
   constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
   const int k = QPW == 1 ? tid : (tid & (G - 1));                      // stage
@@ -91,7 +92,8 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   const bool actu = k < N;         // stage has an input (and box rows, and a successor)
   const bool hasp = act && k > 0;  // stage has a predecessor
   const int nvar = 5 * N + 3;
-  const int mcon = 7 * N + 5 + (RATE ? N : 0);
+  const int mcon = 7 * N + 5 + (RATE ? N : 0) + (SBOX ? 3 * (N + 1) : 0);
+  [[maybe_unused]] const int row_s0 = 7 * N + 5 + (RATE ? N : 0);    // first state-box row
   const int row_r0 = 7 * N + 5;    // first steering-rate row
 
   // ---------------- load the parameter record, linearise, stack -----------------------------------------
@@ -166,7 +168,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   }
   const double* qu = p.qu;  // -R u_des (mpc.cpp:226), precomputed on the host: lives in the constant bank
 
-  StageT<RATE> s;
+  StageT<RATE, SBOX> s;
   {
     const int kr = (k < N) ? k : (N - 1);  // terminal stage re-uses ref[N-1] (mpc.cpp:228)
 #pragma unroll
@@ -196,6 +198,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     if constexpr (RATE) {
       s.rbase = (k == 0) ? slin : 0.0;   // row 0 is measured from the steering applied last cycle
     }
+    if constexpr (SBOX) {   // Constraints::SetXLims (constraints.cpp:108-114): x, y within +-d of the current state, orientation free
+      s.slo[0] = x0[0] - p.state_lim; s.shi[0] = x0[0] + p.state_lim;
+      s.slo[1] = x0[1] - p.state_lim; s.shi[1] = x0[1] + p.state_lim;
+      s.slo[2] = -OSQP_INFTY; s.shi[2] = OSQP_INFTY;
+    }
   }
 
   // ---------------- Ruiz equilibration (OSQP scale_data) -------------------------------------------------
@@ -205,6 +212,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   {
     double dx[3] = {1, 1, 1}, du[2] = {1, 1}, ed[3] = {1, 1, 1}, eg[2] = {1, 1}, eb[2] = {1, 1};
     double er = 1.0;   // steering-rate row (RATE)
+    [[maybe_unused]] double es[3] = {1, 1, 1};   // state-box rows (SBOX)
     const double aA02 = fabs(md.a02), aA12 = fabs(md.a12);
     const double aB[6] = {fabs(md.b00), 0.0, fabs(md.b10), 0.0, fabs(md.b20), fabs(md.b21)};
     double ag[6];
@@ -242,6 +250,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         tx[j] = v;
       }
       tx[2] = dmax(tx[2], dmax(edn[0] * aA02, edn[1] * aA12) * dx[2]);
+      [[maybe_unused]] double ts[3];
+      if constexpr (SBOX) {   // identity rows on x_k: one more entry in the column of x_k[j], a one-entry row
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { ts[j] = es[j] * dx[j]; tx[j] = dmax(tx[j], ts[j]); }
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {  // KKT column of u_k[j]
         double v = c * du[j] * du[j] * p.R[j];
@@ -289,6 +302,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
       for (int j = 0; j < 2; ++j) eb[j] *= rsqrt_scaling(limit_scaling(tb[j]));
       if constexpr (RATE) er *= rsqrt_scaling(limit_scaling(tr));
+      if constexpr (SBOX) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) es[j] *= rsqrt_scaling(limit_scaling(ts[j]));
+      }
       // cost normalisation: c_temp = 1 / max(mean column norm of P, ||q||_inf)
       double psum = 0.0, qn = 0.0;
       if (act) {
@@ -324,6 +341,15 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       scr[SCR_WR * T] = er * er * cinv;
       scr[SCR_CR * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
     }
+    if constexpr (SBOX) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double lb = es[j] * s.slo[j], ub = es[j] * s.shi[j];
+        scr[(SCR_ES + j) * T] = es[j];
+        scr[(SCR_WS + j) * T] = es[j] * es[j] * cinv;
+        scr[(SCR_CS + j) * T] = (lb < -INF_THRESH && ub > INF_THRESH) ? -1.0 : ((ub - lb < RHO_TOL) ? 1.0 : 0.0);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) scr[(SCR_WD + i) * T] = ed[i] * ed[i] * cinv;
 #pragma unroll
@@ -354,8 +380,12 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
   for (int j = 0; j < 2; ++j) { s.u[j] = 0; s.zg[j] = 0; s.zb[j] = 0; s.yg[j] = 0; s.yb[j] = 0; }
   if constexpr (RATE) { s.zr = 0; s.yr = 0; }
+  if constexpr (SBOX) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s.zs[j] = 0; s.ys[j] = 0; }
+  }
   double rho_bar = dmin(dmax(p.rho0, RHO_MIN), RHO_MAX);
-  double* slot = (p.state && live) ? p.state + (size_t)qp * state_doubles(N, RATE ? 1 : 0) : nullptr;
+  double* slot = (p.state && live) ? p.state + (size_t)qp * state_doubles(N, RATE ? 1 : 0, SBOX ? 1 : 0) : nullptr;
   if (slot && p.warm_start && slot[nvar + 2 * mcon + 1] != 0.0) {
     // OSQP keeps x, z, y in SCALED coordinates across re-scalings (osqp_update_A rescales the data only):
     // x = D xbar, z = zbar / E, y = E ybar / c with the NEW D, E, c.
@@ -376,6 +406,14 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         const double e = scr[(SCR_EG + r) * T];
         s.zg[r] = sz_[3 * (N + 1) + 2 * k + r] / e;
         s.yg[r] = e * sy_[3 * (N + 1) + 2 * k + r] * cinv;
+      }
+      if constexpr (SBOX) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double e = scr[(SCR_ES + j) * T];
+          s.zs[j] = sz_[row_s0 + 3 * k + j] / e;
+          s.ys[j] = e * sy_[row_s0 + 3 * k + j] * cinv;
+        }
       }
     }
     if (actu) {
@@ -431,6 +469,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         for (int j = 0; j < 3; ++j) yo[3 * k + j] = has_sol ? s.yd[j] : qnan;
 #pragma unroll
         for (int r = 0; r < 2; ++r) yo[3 * (N + 1) + 2 * k + r] = has_sol ? s.yg[r] : qnan;
+        if constexpr (SBOX) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) yo[row_s0 + 3 * k + j] = has_sol ? s.ys[j] : qnan;
+        }
       }
       if (actu) {
 #pragma unroll
@@ -470,6 +512,14 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           const double e = scr[(SCR_EG + r) * T];
           sz_[3 * (N + 1) + 2 * k + r] = has_sol ? e * s.zg[r] : 0.0;
           sy_[3 * (N + 1) + 2 * k + r] = has_sol ? c * s.yg[r] / e : 0.0;
+        }
+        if constexpr (SBOX) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double e = scr[(SCR_ES + j) * T];
+            sz_[row_s0 + 3 * k + j] = has_sol ? e * s.zs[j] : 0.0;
+            sy_[row_s0 + 3 * k + j] = has_sol ? c * s.ys[j] / e : 0.0;
+          }
         }
       }
       if (actu) {
@@ -609,8 +659,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         double gx[3], gu[2], t3[3], t2[2];
         At_mul(md, sdn, t3);
 #pragma unroll
-        for (int j = 0; j < 3; ++j)   // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
-          gx[j] = (s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1]) + t3[j];
+        for (int j = 0; j < 3; ++j) {  // the neighbour-dependent term (t3, from sdn) is added last: the rest is ready while the shuffle flies
+          double own = s.sx[j] * s.x[j] - s.qx[j] - sd[j] + s.gm[j] * sg[0] + s.gm[3 + j] * sg[1];
+          if constexpr (SBOX) own += s.rs[j] * s.zs[j] - s.ys[j];
+          gx[j] = own + t3[j];
+        }
         Bt_mul(md, sdn, t2);
 #pragma unroll
         for (int j = 0; j < 2; ++j) gu[j] = (s.su[j] * s.u[j] - qu[j] + sb[j]) + t2[j];
@@ -724,6 +777,15 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         s.yb[r2] += s.rb[r2] * (zrb - znb);
         s.zb[r2] = znb;
       }
+      if constexpr (SBOX) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {   // z~ = x~_k[j]
+          const double zr = al * xt[j] + oma * s.zs[j];
+          const double zn = clampd(zr + s.is[j] * s.ys[j], s.slo[j], s.shi[j]);
+          s.ys[j] += s.rs[j] * (zr - zn);
+          s.zs[j] = zn;
+        }
+      }
       if constexpr (RATE) {
         const double zr = al * ztr + oma * s.zr;
         const double zn = clampd(zr + s.ir * s.yr, s.rbase - p.rate_delta, s.rbase + p.rate_delta);
@@ -746,6 +808,15 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         s.rg[r] = rg * scr[(SCR_WG + r) * T]; s.ig[r] = rcp_pos(s.rg[r]);
         s.rb[r] = actu ? rb * scr[(SCR_WB + r) * T] : 0.0;
         s.ib[r] = actu ? rcp_pos(s.rb[r]) : 0.0;
+      }
+      if constexpr (SBOX) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double cs = scr[(SCR_CS + j) * T];
+          const double rsb = cs < 0 ? RHO_MIN : (cs > 0 ? RHO_EQ_OVER_RHO_INEQ * rho_bar : rho_bar);
+          s.rs[j] = act ? rsb * scr[(SCR_WS + j) * T] : 0.0;
+          s.is[j] = act ? rcp_pos(s.rs[j]) : 0.0;
+        }
       }
       if constexpr (RATE) {
         // ---- steering-rate variant: eliminate the speed v_k only; reduced unknown s_k = (x_k, delta_k), 4x4 blocks ----
@@ -927,6 +998,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
             for (int l = 0; l < 3; ++l)
               Bm[3 * i + l] = (i == l ? p.Q[i] + s.sx[i] : 0.0) + s.rg[0] * s.gm[i] * s.gm[l] + s.rg[1] * s.gm[3 + i] * s.gm[3 + l] + Rt[3 * i + l];
+          if constexpr (SBOX) {   // identity rows: rho on the diagonal
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Bm[4 * i] += s.rs[i];
+          }
           double ARn[9];  // A' Rn
 #pragma unroll
           for (int l = 0; l < 3; ++l) {
@@ -1067,6 +1142,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
       for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
       if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
+      if constexpr (SBOX) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) scr[(SCR_PYS + j) * T] = s.ys[j];
+      }
     }
 
     if (first_iter) { iterate(std::true_type{}); first_iter = false; }
@@ -1083,6 +1162,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     const double ebv[2] = {scr[(SCR_EB + 0) * T], scr[(SCR_EB + 1) * T]};
     [[maybe_unused]] double erv = 0.0;
     if constexpr (RATE) erv = scr[SCR_ER * T];
+    [[maybe_unused]] double esv[3] = {0.0, 0.0, 0.0};
+    if constexpr (SBOX) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) esv[j] = scr[(SCR_ES + j) * T];
+    }
     {
       double ax[3], pred[3], t3[3], t2[2];
       A_mul(md, s.x, ax);
@@ -1140,7 +1224,14 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const double Atx = -s.yd[j] + t3[j] + s.gm[j] * s.yg[0] + s.gm[3 + j] * s.yg[1];
+          double Atx = -s.yd[j] + t3[j] + s.gm[j] * s.yg[0] + s.gm[3 + j] * s.yg[1];
+          if constexpr (SBOX) {   // identity row on x_k[j]
+            Atx += s.ys[j];
+            const double rr = fabs(s.x[j] - s.zs[j]), zz = fabs(s.zs[j]), aa = fabs(s.x[j]);
+            poisoned |= !(rr == rr);
+            m_pri = dmax(m_pri, rr); m_z = dmax(m_z, zz); m_Ax = dmax(m_Ax, aa);
+            q_pri = dmax(q_pri, esv[j] * rr); q_z = dmax(q_z, esv[j] * zz); q_Ax = dmax(q_Ax, esv[j] * aa);
+          }
           const double Pxx = p.Q[j] * s.x[j];
           const double dr = fabs(Pxx + s.qx[j] + Atx), ay = fabs(Atx), px = fabs(Pxx);
           poisoned |= !(dr == dr);
@@ -1218,6 +1309,21 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             mx = fabs(dyr);
             lhs = rhi * dmax(dyr, 0.0) + rlo * dmin(dyr, 0.0);
           }
+          [[maybe_unused]] double dys[3] = {0.0, 0.0, 0.0};
+          if constexpr (SBOX) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              double d = s.ys[j] - scr[(SCR_PYS + j) * T];
+              const double lbs = esv[j] * s.slo[j], ubs = esv[j] * s.shi[j];
+              if (ubs > INF_THRESH) d = (lbs < -INF_THRESH) ? 0.0 : dmin(d, 0.0);
+              else if (lbs < -INF_THRESH) d = dmax(d, 0.0);
+              d = act ? d : 0.0;
+              dys[j] = d;
+              mx = dmax(mx, fabs(d));
+              // (an infinite bound only ever meets a zero here: its side of delta_y was projected away above)
+              lhs += (d > 0.0 ? s.shi[j] * d : 0.0) + (d < 0.0 ? s.slo[j] * d : 0.0);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 3; ++i) { dyd[i] = act ? dyd[i] : 0.0; mx = dmax(mx, fabs(dyd[i])); lhs += s.bd[i] * dyd[i]; }
 #pragma unroll
@@ -1247,7 +1353,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             if constexpr (RATE) t2[1] += dyr - dyrn;
             double m2 = 0.0;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) m2 = dmax(m2, fabs(-dyd[j] + t3[j] + s.gm[j] * dyg[0] + s.gm[3 + j] * dyg[1]));
+            for (int j = 0; j < 3; ++j) m2 = dmax(m2, fabs(-dyd[j] + t3[j] + s.gm[j] * dyg[0] + s.gm[3 + j] * dyg[1] + (SBOX ? dys[j] : 0.0)));
 #pragma unroll
             for (int j = 0; j < 2; ++j) m2 = dmax(m2, fabs(t2[j] + dyb[j]));
             pinf = cm.rmax(m2) < epi * ndy;
@@ -1292,6 +1398,13 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             for (int i = 0; i < 3; ++i) {  // equality rows: both sides finite
               const double a = (hasp ? pp[i] : 0.0) - ddx[i];
               if (act && (a > th || a < -th)) bad = true;
+            }
+            if constexpr (SBOX) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double a = ddx[j];
+                if (act && ((esv[j] * s.shi[j] < INF_THRESH && a > th) || (esv[j] * s.slo[j] > -INF_THRESH && a < -th))) bad = true;
+              }
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -1342,10 +1455,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 
 // One CTA per unit: a QP on WPQ warps (horizons 32..127, steering-rate rows), or QPW short-horizon QPs in one warp.
 // (255 registers / 8 warps per SM is the measured optimum: capping at 224 for 9 warps costs 17 % in spills)
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW>
-__global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool SBOX = false>
+__global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE && !SBOX) ? ADMM_MIN_BLOCKS : 1) admm_kernel(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
-  solve_unit<NLEV, WPQ, LASTFULL, RATE, QPW, false>(p, (int)blockIdx.x, smem_all, 0u, (int)threadIdx.x, 0u);
+  solve_unit<NLEV, WPQ, LASTFULL, RATE, QPW, false, SBOX>(p, (int)blockIdx.x, smem_all, 0u, (int)threadIdx.x, 0u);
 }
 
 // Tensor-memory variant (horizons 16..31, base row set): persistent CTAs of four warps, two per SM.  Each CTA allocates TM_COLS
@@ -1385,7 +1498,7 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   if (w == 0) tmem_free(tmem_base, TM_COLS);
 }
 
-template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1, bool SBOX = false>
 static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ;
   KParams p = pin;
@@ -1404,7 +1517,7 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     smem += (size_t)(QPW - 1) * p.stride * sizeof(double) + (size_t)p.rec_bulk_bytes + 16;  // QPW records + the mbarrier
   }
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW, SBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   if (RATE && WPQ == 1) {
@@ -1413,10 +1526,10 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
     // 164 KB carve-out leave 92 KB of L1, which holds them (ncu: profiles/r1f_rate_kernel_ncu_summary.txt).
     int carve = 72;
     if (const char* ev = std::getenv("F110_RATE_CARVEOUT")) { const int v = std::atoi(ev); if (v >= 0 && v <= 100) carve = v; }   // tuning override (percent)
-    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaError_t e = cudaFuncSetAttribute(admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW, SBOX>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
   }
-  admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
+  admm_kernel<NLEV, WPQ, LASTFULL, RATE, QPW, SBOX><<<(p.B + QPW - 1) / QPW, T, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -41,7 +41,8 @@ void f110_mpc_default_config(f110_mpc_config* c) {
   c->u_des[0] = 4.5; c->u_des[1] = 0.0;
   c->u_min[0] = (double)3.0f; c->u_min[1] = (double)-0.43f;  // constraints.cpp:20-21
   c->u_max[0] = (double)4.5f; c->u_max[1] = (double)0.43f;   // constraints.cpp:18-19
-  c->rate_rows = 0; c->reserved = 0; c->rate_delta = 0.0;    // the reference has no steering-rate rows
+  c->rate_rows = 0; c->rate_delta = 0.0;    // the reference has no steering-rate rows
+  c->state_rows = 0; c->state_lim = 1.0;    // the state box is stored (params.yaml:50 state_lims = 1) but never stacked
 }
 
 void f110_solver_default_settings(f110_solver_settings* s) {
@@ -57,7 +58,7 @@ void f110_solver_default_settings(f110_solver_settings* s) {
 int f110_mpc_record_doubles(int N) { return 11 + 3 * N; }
 int f110_mpc_num_variables(int N) { return 5 * N + 3; }
 int f110_mpc_num_constraints(int N) { return 7 * N + 5; }
-int f110_mpc_num_rows(const f110_mpc_config* c) { return c ? f110::num_rows(c->horizon, c->rate_rows) : 0; }
+int f110_mpc_num_rows(const f110_mpc_config* c) { return c ? f110::num_rows(c->horizon, c->rate_rows, c->state_rows) : 0; }
 
 int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, int max_batch, int device,
                     f110_mpc_solver** out) {
@@ -66,6 +67,8 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   if (cfg->gap_mode < 0 || cfg->gap_mode > 2) return fail(F110_ERR_ARG, "f110_mpc_create: gap_mode must be 0, 1 or 2");
   if (cfg->rate_rows && cfg->horizon > 63) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: steering-rate rows need horizon <= 63");
   if (cfg->rate_rows && !(cfg->rate_delta >= 0.0)) return fail(F110_ERR_ARG, "f110_mpc_create: rate_delta must be >= 0");
+  if (cfg->state_rows && (cfg->rate_rows || cfg->horizon > 31)) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: state-box rows need horizon <= 31 and no steering-rate rows");
+  if (cfg->state_rows && !(cfg->state_lim >= 0.0)) return fail(F110_ERR_ARG, "f110_mpc_create: state_lim must be >= 0");
   if (st->scaled_termination) return fail(F110_ERR_UNSUPPORTED, "f110_mpc_create: scaled_termination = 1 is not supported");
   if (st->max_iter < 1 || st->check_termination < 0 || st->scaling < 0) return fail(F110_ERR_ARG, "f110_mpc_create: bad settings");
   int ndev = 0;
@@ -80,7 +83,7 @@ int f110_mpc_create(const f110_mpc_config* cfg, const f110_solver_settings* st, 
   s->max_batch = max_batch;
   s->device = device;
   const int N = cfg->horizon;
-  const size_t ssz = (size_t)max_batch * f110::state_doubles(N, cfg->rate_rows) * sizeof(double);
+  const size_t ssz = (size_t)max_batch * f110::state_doubles(N, cfg->rate_rows, cfg->state_rows) * sizeof(double);
   e = cudaMalloc(&s->d_state, ssz);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scratch, (size_t)(max_batch + 4) * f110::SCR_ROWS_ALLOC * (cfg->horizon < 32 ? 32 : (cfg->horizon < 64 ? 64 : 128)) * sizeof(double));
   if (e == cudaSuccess && cfg->horizon >= (ADMM_W2_GLOBAL_LEVELS > 0 ? 32 : 64) && !cfg->rate_rows)
@@ -136,7 +139,7 @@ int f110_mpc_reset(f110_mpc_solver* s) {
   CUDA_TRY(cudaSetDevice(s->device));
   // Ordered after everything already queued on the handle's stream, and complete when this returns.  Work the caller queued on
   // its OWN streams (solve_device / cycle_device) is not waited for: synchronise those before calling reset.
-  CUDA_TRY(cudaMemsetAsync(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) * sizeof(double), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_state, 0, (size_t)s->max_batch * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows) * sizeof(double), s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return F110_OK;
 }
@@ -167,6 +170,7 @@ int f110api::solve_device_range(f110_mpc_solver* s, int slot0, int count, const 
   for (int i = 0; i < 2; ++i) p.qu[i] = -1.0 * s->cfg.r[i] * s->cfg.u_des[i];
   p.one_minus_alpha = 1.0 - s->st.alpha;
   p.rate_rows = s->cfg.rate_rows ? 1 : 0; p.rate_delta = s->cfg.rate_delta;
+  p.state_rows = s->cfg.state_rows ? 1 : 0; p.state_lim = s->cfg.state_lim;
   p.rho0 = s->st.rho; p.sigma = s->st.sigma; p.alpha = s->st.alpha; p.eps_abs = s->st.eps_abs; p.eps_rel = s->st.eps_rel;
   p.eps_prim_inf = s->st.eps_prim_inf; p.eps_dual_inf = s->st.eps_dual_inf; p.adaptive_rho_tolerance = s->st.adaptive_rho_tolerance;
   p.max_iter = s->st.max_iter; p.check_termination = s->st.check_termination; p.scaling = s->st.scaling;
@@ -175,7 +179,7 @@ int f110api::solve_device_range(f110_mpc_solver* s, int slot0, int count, const 
   p.rho_updates = d_rho_updates; p.info = d_info; p.packed = s->d_packed_next;
   s->d_packed_next = nullptr;
   const int T = s->cfg.horizon < 32 ? 32 : (s->cfg.horizon < 64 ? 64 : 128);   // threads (stage slots) per QP
-  p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows) : nullptr;
+  p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows) : nullptr;
   p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
   p.scratch_dummy = s->d_scratch + (size_t)s->max_batch * f110::SCR_ROWS_ALLOC * T;
   p.mult_global = s->d_mult ? s->d_mult + (size_t)slot0 * 28 * T : nullptr;
@@ -206,7 +210,7 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
   if (!s || !recs) return fail(F110_ERR_ARG, "f110_mpc_solve_host: null solver or records");
   if (count < 0 || count > s->max_batch) return fail(F110_ERR_ARG, "f110_mpc_solve_host: count exceeds max_batch");
   if (count == 0) return F110_OK;
-  const int N = s->cfg.horizon, n = 5 * N + 3, m = f110::num_rows(N, s->cfg.rate_rows);
+  const int N = s->cfg.horizon, n = 5 * N + 3, m = f110::num_rows(N, s->cfg.rate_rows, s->cfg.state_rows);
   const int rd = f110_mpc_record_doubles(N);
   const int rdp = (rd + 1) & ~1;  // device stride: even, so every record is 16-byte aligned for the kernel's TMA staging
   if (rec_stride < rd) return fail(F110_ERR_ARG, "f110_mpc_solve_host: record stride too small");
@@ -233,7 +237,7 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
     // latency path: records staged through pinned memory (true async DMA)
     double* hp = reinterpret_cast<double*>(s->h_pin);
     for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rdp, recs + (size_t)b * rec_stride, rd * sizeof(double));
-    if (count == 1 && !s->cfg.rate_rows && N <= 31 && !s->d_packed_next) {   // (longer horizons set a function attribute at launch: not captured;
+    if (count == 1 && !s->cfg.rate_rows && !s->cfg.state_rows && N <= 31 && !s->d_packed_next) {   // (longer horizons set a function attribute at launch: not captured;
                                                                           //  a packed-output request is per call and must not be frozen into the graph)
       // one QP (the reference's own call pattern, mpc.cpp:69-143): copy-in, solve and copy-out are replayed as one captured graph,
       // one driver call instead of three.  Every address and size in it is fixed for the handle's lifetime.

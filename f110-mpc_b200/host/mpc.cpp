@@ -16,6 +16,7 @@ f110_mpc_config config_from(const f110::Params& prm, const Constraints& con) {
   c.u_des[0] = prm.des_vel; c.u_des[1] = prm.des_steer;
   for (int j = 0; j < 2; ++j) { c.u_min[j] = con.u_min()(j); c.u_max[j] = con.u_max()(j); }
   if (prm.steer_rate_max > 0.0) { c.rate_rows = 1; c.rate_delta = prm.steer_rate_max * c.dt; }
+  if (prm.state_box) { c.state_rows = 1; c.state_lim = prm.state_lims; }   // Constraints::SetXLims' d (constraints.cpp:10, 108-114)
   return c;
 }
 

@@ -82,6 +82,9 @@ struct Params {
   int gap_mode = 0;
   // steering-rate rows (not in the reference): |delta_k - delta_{k-1}| <= steer_rate_max * dt, 0 = off
   double steer_rate_max = 0.0;             // rad/s
+  // state box (stored by the reference, never stacked — constraints.cpp:14-17, 108-114): true stacks x_k, y_k within +-state_lims of
+  // the current state (Constraints::SetXLims) as 3(N+1) extra rows; horizon <= 31, not together with the steering-rate rows
+  bool state_box = false;
 
   // "key: value" lines of a params.yaml-style file override the defaults; unknown keys are ignored.
   static Params FromYaml(const std::string& path);

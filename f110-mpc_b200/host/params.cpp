@@ -43,6 +43,7 @@ Params Params::FromYaml(const std::string& path) {
     else if (key == "lookahead") p.lookahead = static_cast<float>(d);
     else if (key == "gap_mode") p.gap_mode = static_cast<int>(d);
     else if (key == "steer_rate_max") p.steer_rate_max = d;
+    else if (key == "state_box") p.state_box = d != 0.0;
   }
   return p;
 }

@@ -22,6 +22,7 @@
  * Solution layout = the reference's (mpc.cpp:26-29):
  *     x[5N+3]  = [x_0(3) ... x_N(3) | u_0(2) ... u_{N-1}(2)]
  *     y[7N+5]  = [dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N]
+ * With f110_mpc_config.state_rows = 1, 3(N+1) state-box rows follow the input box (y has 10N+8 entries): row 3k+j bounds x_k[j].
  * With f110_mpc_config.rate_rows = 1, N steering-rate rows follow the input box (y has 8N+5 entries):
  *     row k:  delta_k - delta_{k-1} in [-rate_delta, +rate_delta]  (k >= 1);   row 0:  delta_0 - u_lin[1]  likewise.
  * The reference has no such rows (its relic of an extra input constraint is the commented slip block,
@@ -71,8 +72,11 @@ typedef struct f110_mpc_config {
   double u_min[2];   /* umin, -0.43f            (constraints.cpp:20-21) */
   double u_max[2];   /* umax, +0.43f            (constraints.cpp:18-19) */
   int32_t rate_rows; /* 0 = the reference's row set; 1 = append N steering-rate rows (horizon <= 63) */
-  int32_t reserved;
+  int32_t state_rows;/* 0 = the reference's row set; 1 = append the state box the reference stores but never stacks
+                        (constraints.cpp:14-17 + Constraints::SetXLims, :108-114): 3(N+1) rows, x_k and y_k within
+                        +-state_lim of the current state, ori_k free.  Horizon <= 31, not together with rate_rows */
   double rate_delta; /* max steering change per step (rad) = steering-rate limit (rad/s) * dt */
+  double state_lim;  /* d of SetXLims (params.yaml:50 state_lims = 1) */
 } f110_mpc_config;
 
 /* The OSQP settings the reference leaves at their defaults (it only sets warm start + verbosity,
@@ -95,7 +99,7 @@ void f110_solver_default_settings(f110_solver_settings* s);
 int f110_mpc_record_doubles(int horizon); /* 11 + 3N */
 int f110_mpc_num_variables(int horizon);  /* 5N + 3  (mpc.cpp:26-28) */
 int f110_mpc_num_constraints(int horizon);/* 7N + 5  (mpc.cpp:29) */
-int f110_mpc_num_rows(const f110_mpc_config* cfg); /* 7N + 5, + N with rate_rows: length of one dual vector */
+int f110_mpc_num_rows(const f110_mpc_config* cfg); /* 7N + 5, + N with rate_rows, + 3(N+1) with state_rows: length of one dual vector */
 const char* f110_last_error(void);
 int f110_device_count(void);
 

@@ -407,6 +407,13 @@ struct MpcConfig {
   //   row 0:  delta_0                in [steer_prev - rate_delta, steer_prev + rate_delta],  steer_prev = u_lin[1]
   int rate_rows = 0;
   double rate_delta = 0.0;   // max steering change per step (rad)
+  // State-box rows.  The reference STORES x_min_ / x_max_ (constraints.cpp:14-17) and has
+  // Constraints::SetXLims (constraints.cpp:108-114: x and y within +-d of the current state, d = /state_lims; the orientation
+  // stays at +-INFTY) but never stacks them into the QP.  Stacked here the way the input box is: 3(N+1) identity rows on
+  // x_0..x_N appended after the input box (and after the steering-rate rows when both are on),
+  //   rows 3k, 3k+1:  x_k, y_k  in [x_cur - d, x_cur + d], [y_cur - d, y_cur + d]      row 3k+2:  ori_k in (-INFTY, +INFTY)
+  int state_rows = 0;
+  double state_lim = 0.0;    // d
 };
 
 struct QpData {
@@ -422,7 +429,7 @@ struct QpData {
 // Create{Lower,Upper}Bound (mpc.cpp:26-47, 208-219, 231-254, 275-291).
 inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
   const int N = cfg.N, ns = 3 * (N + 1), nu = 2 * N;
-  d->N = N; d->n = ns + nu; d->m = ns + 2 * (N + 1) + nu + (cfg.rate_rows ? N : 0);
+  d->N = N; d->n = ns + nu; d->m = ns + 2 * (N + 1) + nu + (cfg.rate_rows ? N : 0) + (cfg.state_rows ? ns : 0);
   const int n = d->n, m = d->m;
   struct T { int r, c; double v; int tag; };
   // Hessian: dense diagonal blocks (upper triangle kept, OsqpEigen passes triu to OSQP)
@@ -462,6 +469,9 @@ inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
       ta.push_back({rate0 + k, ns + 2 * k + 1, 1.0, 0});
       if (k > 0) ta.push_back({rate0 + k, ns + 2 * (k - 1) + 1, -1.0, 0});
     }
+  const int st0 = rate0 + (cfg.rate_rows ? N : 0);   // first state-box row
+  if (cfg.state_rows)
+    for (int r = 0; r < ns; ++r) ta.push_back({st0 + r, r, 1.0, 0});
   std::vector<int> where;
   to_csc(ta, m, n, &d->A, &where);
   d->posA.assign(9 * N, -1); d->posB.assign(6 * N, -1); d->posG.assign(6 * N, -1);
@@ -483,12 +493,15 @@ inline void qp_build_structure(const MpcConfig& cfg, QpData* d) {
   }
   if (cfg.rate_rows)
     for (int k = 0; k < N; ++k) { d->l[rate0 + k] = -cfg.rate_delta; d->u[rate0 + k] = cfg.rate_delta; }
+  if (cfg.state_rows)
+    for (int r = 0; r < ns; ++r) { d->l[st0 + r] = -osqp_restated::OSQP_INFTY; d->u[st0 + r] = osqp_restated::OSQP_INFTY; }   // constraints.cpp:14-17
   // KKT ordering, stage by stage: [dyn rows k | x_k | gap rows k | u_k | box rows k | rate row k]
   d->perm.clear();
   for (int k = 0; k <= N; ++k) {
     for (int r = 0; r < 3; ++r) d->perm.push_back(n + 3 * k + r);
     for (int r = 0; r < 3; ++r) d->perm.push_back(3 * k + r);
     for (int r = 0; r < 2; ++r) d->perm.push_back(n + ns + 2 * k + r);
+    if (cfg.state_rows) for (int r = 0; r < 3; ++r) d->perm.push_back(n + st0 + 3 * k + r);
     if (k < N) {
       for (int r = 0; r < 2; ++r) d->perm.push_back(ns + 2 * k + r);
       for (int r = 0; r < 2; ++r) d->perm.push_back(n + ns + 2 * (N + 1) + 2 * k + r);
@@ -527,6 +540,11 @@ inline void qp_fill_values(const MpcConfig& cfg, const double* rec, QpData* d) {
     const int rate0 = ns + 2 * (N + 1) + 2 * N;
     d->l[rate0] = ulin[1] - cfg.rate_delta;
     d->u[rate0] = ulin[1] + cfg.rate_delta;
+  }
+  if (cfg.state_rows) {  // Constraints::SetXLims(current_state), constraints.cpp:108-114
+    const int st0 = ns + 2 * (N + 1) + 2 * N + (cfg.rate_rows ? N : 0);
+    for (int k = 0; k <= N; ++k)
+      for (int r = 0; r < 2; ++r) { d->l[st0 + 3 * k + r] = x0[r] - cfg.state_lim; d->u[st0 + 3 * k + r] = x0[r] + cfg.state_lim; }
   }
 }
 

@@ -3,7 +3,7 @@
 // the CPU restatement through ctypes.  Flat double arrays carry config/settings so this library
 // shares no struct layout with the product.
 //
-//   cfg[16]      = N, dt, Q0,Q1,Q2, R0,R1, udes0,udes1, umin0,umin1, umax0,umax1, gap_mode, rate_rows, rate_delta
+//   cfg[18]      = N, dt, Q0,Q1,Q2, R0,R1, udes0,udes1, umin0,umin1, umax0,umax1, gap_mode, rate_rows, rate_delta, state_rows, state_lim
 //   settings[15] = rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, max_iter,
 //                  check_termination, scaling, adaptive_rho, adaptive_rho_interval,
 //                  adaptive_rho_tolerance, warm_start, scaled_termination
@@ -24,6 +24,7 @@ static MpcConfig cfg_from(const double* c) {
   for (int i = 0; i < 2; ++i) { k.R[i] = c[5 + i]; k.u_des[i] = c[7 + i]; k.u_min[i] = c[9 + i]; k.u_max[i] = c[11 + i]; }
   k.gap_mode = (int)c[13];
   k.rate_rows = (int)c[14]; k.rate_delta = c[15];
+  k.state_rows = (int)c[16]; k.state_lim = c[17];
   return k;
 }
 static osq::Settings settings_from(const double* s) {
@@ -56,7 +57,7 @@ void orc_default_cfg(double* c) {
   c[0] = k.N; c[1] = k.dt;
   for (int i = 0; i < 3; ++i) c[2 + i] = k.Q[i];
   for (int i = 0; i < 2; ++i) { c[5 + i] = k.R[i]; c[7 + i] = k.u_des[i]; c[9 + i] = k.u_min[i]; c[11 + i] = k.u_max[i]; }
-  c[13] = k.gap_mode; c[14] = k.rate_rows; c[15] = k.rate_delta;
+  c[13] = k.gap_mode; c[14] = k.rate_rows; c[15] = k.rate_delta; c[16] = k.state_rows; c[17] = k.state_lim;
 }
 void orc_default_settings(double* s) {
   osq::Settings t;
@@ -96,7 +97,7 @@ int orc_osqp_dense(int n, int m, const double* P, const double* q, const double*
 // ---- MPC QP: dense assembly for cross-checks ---------------------------------------------------------
 // Pd n x n, Ad m x n row-major, plus q, l, u.  Returns 0; dims via orc_mpc_dims.
 void orc_mpc_dims(int N, int* n, int* m) { *n = 5 * N + 3; *m = 7 * N + 5; }
-int orc_mpc_rows(const double* cfg) { MpcConfig k = cfg_from(cfg); return 7 * k.N + 5 + (k.rate_rows ? k.N : 0); }
+int orc_mpc_rows(const double* cfg) { MpcConfig k = cfg_from(cfg); return 7 * k.N + 5 + (k.rate_rows ? k.N : 0) + (k.state_rows ? 3 * (k.N + 1) : 0); }
 int orc_mpc_assemble_dense(const double* cfg, const double* rec, double* Pd, double* q, double* Ad, double* l, double* u) {
   MpcConfig k = cfg_from(cfg);
   QpData d;
@@ -152,7 +153,7 @@ double orc_mpc_solve(void* hv, const double* recs, int stride, int count, int wa
                      int* status, int* iters, int* rho_updates, double* extra) {
   MpcBatch* h = (MpcBatch*)hv;
   if (count > h->B) return -1.0;
-  const int n = 5 * h->cfg.N + 3, m = 7 * h->cfg.N + 5 + (h->cfg.rate_rows ? h->cfg.N : 0);
+  const int n = 5 * h->cfg.N + 3, m = 7 * h->cfg.N + 5 + (h->cfg.rate_rows ? h->cfg.N : 0) + (h->cfg.state_rows ? 3 * (h->cfg.N + 1) : 0);
   std::atomic<int> next(0);
   std::atomic<int> err(0);
   auto worker = [&](int tid) {

@@ -73,20 +73,23 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
 
 
-def default_cfg(N=30, gap_mode=0, rate_delta=None):
-    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; None = the reference's row set."""
-    c = np.zeros(16)
+def default_cfg(N=30, gap_mode=0, rate_delta=None, state_lim=None):
+    """rate_delta: max steering change per step (rad) -> N steering-rate rows appended; state_lim: d of Constraints::SetXLims ->
+    3(N+1) state-box rows appended; None = the reference's row set."""
+    c = np.zeros(18)
     lib().orc_default_cfg(_dp(c))
     c[0] = N
     c[13] = gap_mode
     if rate_delta is not None:
         c[14], c[15] = 1, rate_delta
+    if state_lim is not None:
+        c[16], c[17] = 1, state_lim
     return c
 
 
 def mpc_rows(cfg):
     N = int(cfg[0])
-    return 7 * N + 5 + (N if len(cfg) > 14 and cfg[14] else 0)
+    return 7 * N + 5 + (N if len(cfg) > 14 and cfg[14] else 0) + (3 * (N + 1) if len(cfg) > 16 and cfg[16] else 0)
 
 
 def default_settings(**kw):

@@ -63,12 +63,12 @@ def make_fixed_points():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import qp_exact as E
 
-    def exact_batch(recs, N, gap_mode, want):
+    def exact_batch(recs, N, gap_mode, want, state_lim=None):
         X, Y, keep = [], [], []
         for i, r in enumerate(recs):
             if len(keep) == want:
                 break
-            P, q, A, l, u = E.assemble(r, N, gap_mode)
+            P, q, A, l, u = E.assemble(r, N, gap_mode, state_lim)
             try:
                 x, y, _ = E.solve_exact(P, q, A, l, u, max_changes=150)
             except RuntimeError:
@@ -106,6 +106,13 @@ def make_fixed_points():
         np.savez_compressed(os.path.join(OUT, "exact_%s.npz" % name), recs=recs, x=X, y=Y, N=N, gap_mode=gap_mode)
         print("exact_%s: %d QPs, %d active inequality rows, %d of them half-plane rows" %
               (name, len(recs), n_active(Y, N), int((np.abs(Y[:, 3 * (N + 1):5 * (N + 1)]) > 1e-9).sum())))
+    # state-box rows (stored by the reference, never stacked: constraints.cpp:14-17, 108-114), d = params.yaml's state_lims = 1 —
+    # the box binds: at the 3 m/s speed floor the car travels 0.9 m over the horizon, at 4.5 m/s 1.35 m
+    for N, d in ((30, 1.0), (20, 0.7)):
+        recs, X, Y = exact_batch(W.tracking_batch(32, N, seed=20240920 + N), N, 0, 32, state_lim=d)
+        assert len(recs) >= 8
+        np.savez_compressed(os.path.join(OUT, "exactbox_N%d_d%g.npz" % (N, d)), recs=recs, x=X, y=Y, N=N, gap_mode=0, state_lim=d)
+        print("exactbox_N%d_d%g: %d QPs, %d active state-box rows" % (N, d, len(recs), int((np.abs(Y[:, 7 * N + 5:]) > 1e-9).sum())))
 
 
 if __name__ == "__main__":

@@ -39,8 +39,10 @@ def linearize(theta, v, delta, dt=DT, L=WHEELBASE):
     return A, B, C
 
 
-def assemble(rec, N, gap_mode=0):
-    """record (x0[3] | u_lin[2] | l1[3] | l2[3] | ref[3N]) -> dense P, q, A, l, u."""
+def assemble(rec, N, gap_mode=0, state_lim=None):
+    """record (x0[3] | u_lin[2] | l1[3] | l2[3] | ref[3N]) -> dense P, q, A, l, u.
+    state_lim = d: append the state box the reference stores but never stacks (constraints.cpp:14-17, SetXLims :108-114):
+    3(N+1) identity rows on x_0..x_N, x and y within +-d of the current state, the orientation rows at +-INFTY."""
     rec = np.asarray(rec, dtype=np.float64)
     x0, ulin, l1, l2, ref = rec[0:3], rec[3:5], rec[5:8], rec[8:11], rec[11:11 + 3 * N].reshape(N, 3)
     nx, nu = 3 * (N + 1), 2 * N
@@ -82,6 +84,14 @@ def assemble(rec, N, gap_mode=0):
         A[r + 1, nx + 2 * k + 1] = 1.0
         l[r:r + 2] = U_MIN
         u[r:r + 2] = U_MAX
+    if state_lim is not None:
+        As = np.zeros((nx, n))
+        As[:, :nx] = np.eye(nx)
+        ls, us = np.full(nx, -INFTY), np.full(nx, INFTY)
+        for k in range(N + 1):
+            ls[3 * k:3 * k + 2] = x0[0:2] - state_lim
+            us[3 * k:3 * k + 2] = x0[0:2] + state_lim
+        A, l, u = np.vstack([A, As]), np.concatenate([l, ls]), np.concatenate([u, us])
     return P, q, A, l, u
 
 
