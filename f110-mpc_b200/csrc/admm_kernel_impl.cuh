@@ -53,7 +53,7 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM, bool SB
 __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
                                            const int tid, [[maybe_unused]] const uint32_t rec_parity) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
-  static_assert(!TM || (WPQ == 1 && QPW == 1 && !RATE), "tensor-memory variant: one warp per QP, base row set");
+  static_assert(!TM || (WPQ == 1 && QPW == 1), "tensor-memory variant: one warp per QP");
   static_assert(!SBOX || (WPQ == 1 && QPW == 1 && !RATE && !TM), "state-box rows: one-warp shared-memory kernel, without steering-rate rows");
   constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
   constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
@@ -75,16 +75,22 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   constexpr int GTOP = GL == 2 ? 9 : 0;            // where the top level starts in it
   constexpr int SM_PAIRS = NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
   constexpr int FINAL_PAIR = SM_PAIRS - 3;
-  static_assert(!TM || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
+  static_assert(!TM || RATE || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
+  // Steering-rate rows + tensor memory: the 16 pairs of each two-sided level live in the strip (4 x 16 pairs = all 256 columns at
+  // NLEV = 5); the one-sided top level (8 pairs) and the final inverse (5 pairs) stay in shared memory, re-based to index 0.
+  // The scratch line stays in global memory for this variant: its spill traffic needs the L1 the shared memory would take.
+  static_assert(!(TM && RATE) || (NLEV - 1) * 64 <= TM_COLS, "two-sided levels exceed the warp's tensor-memory strip");
+  constexpr bool SCR_SM = TM && !RATE;                            // scratch line in shared memory
+  constexpr int RT_SM0 = (TM && RATE) ? (NLEV - 1) * 16 : 0;       // first steering-rate pair that is NOT in tensor memory
   [[maybe_unused]] double2* sm_pair = reinterpret_cast<double2*>(smem_all) + tid;
   [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)unit * (GLP * T) + tid : nullptr;
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
-  constexpr int SM_DOUBLES = TM ? 0 : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
+  constexpr int SM_DOUBLES = TM ? (RATE ? 26 : 0) : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
   Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, tid);
   // scratch line: global memory (L2), or — tensor-memory variant — the shared memory the multipliers no longer occupy
   double* scr;
-  if constexpr (TM) scr = smem_all + k;
+  if constexpr (SCR_SM) scr = smem_all + k;
   else scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(tid / G) * (SCR_ROWS_ALLOC * T)) + k;
 
   const int N = p.N;
@@ -547,7 +553,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     constexpr bool FIRST = decltype(first_c)::value;
       // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
       [[maybe_unused]] double2 mc[9];
-      if constexpr (TM) {
+      [[maybe_unused]] double2 mrow[4];   // steering-rate variant: one row (four pairs) of the current level
+      if constexpr (TM && RATE) {
+        static_assert(!(TM && RATE) || NLEV > 1, "steering-rate rows in tensor memory need a two-sided level");
+        tmem_ld_pairs<4>(tmb, mrow);
+      } else if constexpr (TM) {
         if constexpr (NLEV > 1) tmem_ld_pairs<9>(tmb, mc);
         else { tmem_ld_pairs<8>(tmb, mc); mc[8] = make_double2(0.0, 0.0); }
       }
@@ -597,10 +607,20 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           const int h = 1 << lev;
           double lo[4], hi[4];
           cm.template both<4>(r, lo, hi, h);
-          const double2* cf = sm_pair + (lev * 16) * T;
+          [[maybe_unused]] const double2* cf = sm_pair + (lev * 16) * T;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const double2 c0 = cf[(4 * i + 0) * T], c1 = cf[(4 * i + 1) * T], c2 = cf[(4 * i + 2) * T], c3 = cf[(4 * i + 3) * T];
+            double2 c0, c1, c2, c3;
+            if constexpr (TM) {
+              // the row's four pairs were fetched from tensor memory while the previous row was applied; fetch the next row now
+              tmem_wait_ld();
+              tmem_tie<4>(mrow);
+              c0 = mrow[0]; c1 = mrow[1]; c2 = mrow[2]; c3 = mrow[3];
+              if (i < 3) tmem_ld_pairs<4>(tmb + 4 * (lev * 16 + 4 * (i + 1)), mrow);
+              else if (lev + 1 < NLEV - 1) tmem_ld_pairs<4>(tmb + 4 * ((lev + 1) * 16), mrow);
+            } else {
+              c0 = cf[(4 * i + 0) * T]; c1 = cf[(4 * i + 1) * T]; c2 = cf[(4 * i + 2) * T]; c3 = cf[(4 * i + 3) * T];
+            }
             double a = fma(c0.x, lo[0], r[i]);
             a = fma(c2.x, hi[0], a);
             a = fma(c0.y, lo[1], a);
@@ -615,7 +635,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           constexpr int h = 1 << (NLEV - 1);
           double nb[4];
           cm.template xr<4>(r, nb, h);
-          const double2* cf = sm_pair + ((NLEV - 1) * 16) * T;
+          const double2* cf = sm_pair + ((NLEV - 1) * 16 - RT_SM0) * T;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const double2 c0 = cf[(2 * i) * T], c1 = cf[(2 * i + 1) * T];
@@ -624,7 +644,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         }
         double st[4];
         {
-          const double2* cf = sm_pair + ((NLEV - 1) * 16 + 8) * T;
+          const double2* cf = sm_pair + ((NLEV - 1) * 16 + 8 - RT_SM0) * T;
           const double2 q0 = cf[0 * T], q1 = cf[1 * T], q2 = cf[2 * T], q3 = cf[3 * T], q4 = cf[4 * T];
           const double b00 = q0.x, b01 = q0.y, b02 = q1.x, b03 = q1.y, b11 = q2.x, b12 = q2.y, b13 = q3.x, b22 = q3.y, b23 = q4.x, b33 = q4.y;
           st[0] = fma(b03, r[3], fma(b02, r[2], fma(b01, r[1], b00 * r[0])));
@@ -938,22 +958,30 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           if (lev < NLEV - 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              sm_pair[(lev * 16 + 4 * i + 0) * T] = make_double2(alp[4 * i], alp[4 * i + 1]);
-              sm_pair[(lev * 16 + 4 * i + 1) * T] = make_double2(alp[4 * i + 2], alp[4 * i + 3]);
-              sm_pair[(lev * 16 + 4 * i + 2) * T] = make_double2(gam[4 * i], gam[4 * i + 1]);
-              sm_pair[(lev * 16 + 4 * i + 3) * T] = make_double2(gam[4 * i + 2], gam[4 * i + 3]);
+              if constexpr (TM) {
+                const uint32_t dst = tmb + 4 * (lev * 16 + 4 * i);
+                tmem_st_pair(dst, alp[4 * i], alp[4 * i + 1]);
+                tmem_st_pair(dst + 4, alp[4 * i + 2], alp[4 * i + 3]);
+                tmem_st_pair(dst + 8, gam[4 * i], gam[4 * i + 1]);
+                tmem_st_pair(dst + 12, gam[4 * i + 2], gam[4 * i + 3]);
+              } else {
+                sm_pair[(lev * 16 + 4 * i + 0) * T] = make_double2(alp[4 * i], alp[4 * i + 1]);
+                sm_pair[(lev * 16 + 4 * i + 1) * T] = make_double2(alp[4 * i + 2], alp[4 * i + 3]);
+                sm_pair[(lev * 16 + 4 * i + 2) * T] = make_double2(gam[4 * i], gam[4 * i + 1]);
+                sm_pair[(lev * 16 + 4 * i + 3) * T] = make_double2(gam[4 * i + 2], gam[4 * i + 3]);
+              }
             }
           } else {
             // top level: the stage has its k-h or its k+h neighbour, never both (stage k ^ h): one 4x4 block
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              sm_pair[(lev * 16 + q) * T] = make_double2(alp[2 * q] + gam[2 * q], alp[2 * q + 1] + gam[2 * q + 1]);
+              sm_pair[(lev * 16 + q - RT_SM0) * T] = make_double2(alp[2 * q] + gam[2 * q], alp[2 * q + 1] + gam[2 * q + 1]);
           }
         }
         {
           double Bi[16];
           inv_spdD<4>(Bm, Bi);
-          constexpr int FB = (NLEV - 1) * 16 + 8;   // symmetric: 10 distinct entries
+          constexpr int FB = (NLEV - 1) * 16 + 8 - RT_SM0;   // symmetric: 10 distinct entries
           sm_pair[(FB + 0) * T] = make_double2(Bi[0], Bi[1]);
           sm_pair[(FB + 1) * T] = make_double2(Bi[2], Bi[3]);
           sm_pair[(FB + 2) * T] = make_double2(Bi[5], Bi[6]);
@@ -1465,7 +1493,11 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE && !SBOX) ? ADMM_
 // columns of tensor memory once; each warp owns a 32-row strip of it for its multipliers and fetches QPs from a work counter until
 // the batch is exhausted, so warps whose QPs stop after 25 iterations take up the slack of those that need 75.  Per-warp shared
 // memory: the QP's scratch line and the TMA landing zone of its parameter record.
-template <int NLEV, bool LASTFULL>
+// RATE = true: the steering-rate variant (4x4 blocks).  Its two-sided levels fill the strip, the rest of its multipliers (13 pairs) sit
+// in the warp's shared memory where the base variant keeps its scratch line; its scratch line stays in global memory.
+template <int RATE>
+__host__ __device__ constexpr int tm_warp_head() { return RATE ? 26 * 32 : SCR_ROWS_ALLOC * 32; }   // doubles at the head of a warp's shared-memory region
+template <int NLEV, bool LASTFULL, bool RATE = false>
 __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
   __shared__ uint32_t tmem_base;
@@ -1475,7 +1507,7 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
-  double* const smem_w = smem_all + (size_t)w * (SCR_ROWS_ALLOC * 32 + p.rec_bulk_bytes / 8 + 2);
+  double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2);
   if (p.rec_bulk_bytes && lane == 0) mbar_init(smem_u32(smem_w + p.rec_smem_offset + p.rec_bulk_bytes / 8), 1);
   __syncwarp();
   uint32_t parity = 0;
@@ -1484,7 +1516,7 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
     if (lane == 0) unit = atomicAdd(p.work, 1);
     unit = __shfl_sync(FULL, unit, 0);
     if (unit >= p.B) break;
-    solve_unit<NLEV, 1, LASTFULL, false, 1, true>(p, unit, smem_w, tmb, lane, parity);
+    solve_unit<NLEV, 1, LASTFULL, RATE, 1, true>(p, unit, smem_w, tmb, lane, parity);
     if (p.rec_bulk_bytes) parity ^= 1u;
     __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
   }
@@ -1535,7 +1567,7 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
 
 // Launch of the tensor-memory variant: at most two CTAs per SM (they own the SM's 512 tensor-memory columns between them),
 // fewer when the batch has fewer than 8 QPs per SM.
-template <int NLEV, bool LASTFULL>
+template <int NLEV, bool LASTFULL, bool RATE = false>
 static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   KParams p = pin;
   if (!p.work) return cudaErrorInvalidValue;
@@ -1552,18 +1584,18 @@ static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   }
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
   p.rec_bulk_bytes = 0;
-  p.rec_smem_offset = SCR_ROWS_ALLOC * 32;
+  p.rec_smem_offset = tm_warp_head<RATE>();
   if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) p.rec_bulk_bytes = rec_even * (int)sizeof(double);
-  const size_t smem = 4 * (size_t)(SCR_ROWS_ALLOC * 32 + p.rec_bulk_bytes / 8 + 2) * sizeof(double);
-  static bool attr_set[64] = {false};
+  const size_t smem = 4 * (size_t)(tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2) * sizeof(double);
+  static bool attr_set[64] = {false};   // (one flag array per instantiation of this template)
   if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   int grid = (p.B + 3) / 4;
   if (grid > 2 * sms_of[dev]) grid = 2 * sms_of[dev];
-  admm_kernel_tm<NLEV, LASTFULL><<<grid, 128, smem, stream>>>(p);
+  admm_kernel_tm<NLEV, LASTFULL, RATE><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
