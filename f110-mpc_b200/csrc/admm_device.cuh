@@ -187,7 +187,7 @@ struct Comm;
 template <int G>
 struct Comm<1, G> {
   unsigned gmask;   // lanes of this lane's group
-  __device__ __forceinline__ Comm(double*, int tid)
+  __device__ __forceinline__ Comm(double*, int tid, int = 0)
       : gmask(G == 32 ? FULL : (((1u << (G & 31)) - 1u) << ((unsigned)tid & ~(unsigned)(G - 1) & 31u))) {}
   __device__ __forceinline__ unsigned m() const { return G == 32 ? FULL : gmask; }
   template <int K> __device__ __forceinline__ void up(const double* v, double* o, int h) {
@@ -219,7 +219,13 @@ struct Comm {
   double* xb;   // [2][KMAX][T] exchange buffers
   double* rb;   // [2][WPQ] reduction slots
   int tid, xph = 0, rph = 0;
-  __device__ __forceinline__ Comm(double* smem, int t) : xb(smem), rb(smem + 2 * KMAX * T), tid(t) {}
+  int bar;      // hardware barrier of this QP's T threads: 0 when the QP is the whole CTA, 1 + q when several QPs share a CTA
+  __device__ __forceinline__ Comm(double* smem, int t, int bar_id = 0) : xb(smem), rb(smem + 2 * KMAX * T), tid(t), bar(bar_id) {}
+  __device__ __forceinline__ void barrier() const {   // immediate barrier numbers: a register operand would make ptxas reserve all 16
+    if (bar == 0) asm volatile("bar.sync 0, %0;" ::"n"(T) : "memory");
+    else if (bar == 1) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
+  }
   static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ; }
   template <int K> __device__ __forceinline__ double* put(const double* v) {
     static_assert(K <= KMAX, "exchange wider than the buffer");
@@ -227,7 +233,7 @@ struct Comm {
     xph ^= 1;
 #pragma unroll
     for (int i = 0; i < K; ++i) b[i * T + tid] = v[i];
-    __syncthreads();
+    barrier();
     return b;
   }
   // out-of-range sources return the caller's own value, like a shuffle; callers mask them
@@ -271,7 +277,7 @@ struct Comm {
     double* r = rb + rph * WPQ;
     rph ^= 1;
     if ((tid & 31) == 0) r[tid >> 5] = v;
-    __syncthreads();
+    barrier();
     return r;
   }
   __device__ __forceinline__ double rmax(double v) {
@@ -288,8 +294,14 @@ struct Comm {
     for (int w = 1; w < WPQ; ++w) m += r[w];
     return m;
   }
-  __device__ __forceinline__ bool any(bool b) { return __syncthreads_or(b) != 0; }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ bool any(bool b) {
+    const double* r = rslot(__any_sync(FULL, b) ? 1.0 : 0.0);
+    bool a = false;
+#pragma unroll
+    for (int w = 0; w < WPQ; ++w) a |= r[w] != 0.0;
+    return a;
+  }
+  __device__ __forceinline__ void sync() { barrier(); }
 };
 
 // ---- 3x3 helpers (row-major double[9]) ------------------------------------------------------------

@@ -51,9 +51,10 @@ namespace f110 {
 // kernels, the fetched index for the persistent one; `smem_all` = this unit's shared-memory region; `tid` = thread within the unit.
 template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM, bool SBOX = false>
 __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
-                                           const int tid, [[maybe_unused]] const uint32_t rec_parity) {
+                                           const int tid, [[maybe_unused]] const uint32_t rec_parity, [[maybe_unused]] const int bar_id = 0) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
-  static_assert(!TM || (WPQ == 1 && QPW == 1), "tensor-memory variant: one warp per QP");
+  static_assert(!TM || QPW == 1, "tensor-memory variant: one QP per unit");
+  static_assert(!(TM && RATE) || WPQ == 1, "steering-rate rows in tensor memory: one warp per QP");
   static_assert(!SBOX || (WPQ == 1 && QPW == 1 && !RATE && !TM), "state-box rows: one-warp shared-memory kernel, without steering-rate rows");
   constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
   constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
@@ -69,7 +70,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   // that wrote them; the shared memory saved buys residency.  Four warps (N 64..127): the two top levels (9 + 5 pairs) -> two QPs
   // per SM instead of one (N = 100: 2.75 -> 2.24 ms per 4096 QPs).  Two warps (N 32..63): only the one-sided top level (5 pairs)
   // -> four QPs per SM instead of three (2-4 % faster; moving both levels loses 5 %).  GL = number of levels kept there.
-  constexpr int GL = RATE ? 0 : (WPQ == 4 ? 2 : (WPQ == 2 ? ADMM_W2_GLOBAL_LEVELS : 0));
+  constexpr int GL = (RATE || TM) ? 0 : (WPQ == 4 ? 2 : (WPQ == 2 ? ADMM_W2_GLOBAL_LEVELS : 0));
   constexpr bool TOPG = GL > 0;
   constexpr int GLP = GL == 2 ? 14 : 5;            // pairs per stage in the global line
   constexpr int GTOP = GL == 2 ? 9 : 0;            // where the top level starts in it
@@ -87,7 +88,8 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
   constexpr int SM_DOUBLES = TM ? (RATE ? 26 : 0) : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
-  Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + SM_DOUBLES * T, tid);
+  // (tensor-memory variant: the scratch line, when it lives in shared memory, comes first; the exchange buffers of a multi-warp QP follow)
+  Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + ((TM && !RATE) ? SCR_ROWS_ALLOC * T : 0) + SM_DOUBLES * T, tid, bar_id);
   // scratch line: global memory (L2), or — tensor-memory variant — the shared memory the multipliers no longer occupy
   double* scr;
   if constexpr (SCR_SM) scr = smem_all + k;
@@ -108,7 +110,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
     // is a shared-memory read
     double* rec_sm = smem_all + p.rec_smem_offset;
-    if constexpr (TM) {
+    if constexpr (TM && WPQ == 1) {
       // persistent warp: the mbarrier was initialised once by the caller, its phase alternates from QP to QP
       uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
       if (k == 0) bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
@@ -1528,6 +1530,50 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   tmem_fence_before_sync();
   __syncthreads();
   if (w == 0) tmem_free(tmem_base, TM_COLS);
+}
+
+// Tensor-memory variant for multi-warp QPs (horizons 32..127, base row set): a CTA of four warps holds 4 / WPQ QPs (two two-warp QPs
+// side by side, or one four-warp QP), allocates 256 tensor-memory columns and keeps every PCR multiplier of its QPs there — the
+// shared-memory kernels of these horizons were bound by the multiplier loads (LSU data pipe 73-78 % busy).  Two QPs of one CTA
+// synchronise on their own hardware barriers (bar.sync 1 + q, 64).  The scratch line lives in shared memory.
+template <int NLEV, int WPQ, bool LASTFULL>
+__global__ void __launch_bounds__(128, 2) admm_kernel_tmw(const KParams p) {
+  extern __shared__ __align__(16) double smem_all[];
+  __shared__ uint32_t tmem_base;
+  constexpr int T = 32 * WPQ, QPC = 4 / WPQ;
+  const int w = (int)threadIdx.x >> 5;
+  if (w == 0) tmem_alloc(&tmem_base, TM_COLS);
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
+  const int q = (int)threadIdx.x / T, unit = (int)blockIdx.x * QPC + q;
+  if (unit < p.B)
+    solve_unit<NLEV, WPQ, LASTFULL, false, 1, true>(p, unit, smem_all + (size_t)q * p.tm_unit_doubles, tmb, (int)threadIdx.x % T, 0u, QPC == 1 ? 0 : 1 + q);
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (w == 0) tmem_free(tmem_base, TM_COLS);
+}
+
+template <int NLEV, int WPQ, bool LASTFULL>
+static cudaError_t launch_tmw(const KParams& pin, cudaStream_t stream) {
+  constexpr int T = 32 * WPQ, QPC = 4 / WPQ;
+  KParams p = pin;
+  size_t unit = (size_t)SCR_ROWS_ALLOC * T + Comm<WPQ, 32>::doubles();
+  const int rec_even = (11 + 3 * p.N + 1) & ~1;
+  p.rec_bulk_bytes = 0;
+  unit = (unit + 1) & ~(size_t)1;
+  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) {
+    p.rec_smem_offset = (int)unit;
+    p.rec_bulk_bytes = rec_even * (int)sizeof(double);
+    unit += (size_t)rec_even + 2;   // the record + its mbarrier
+  }
+  p.tm_unit_doubles = (int)unit;
+  const size_t smem = unit * QPC * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(admm_kernel_tmw<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  admm_kernel_tmw<NLEV, WPQ, LASTFULL><<<(p.B + QPC - 1) / QPC, 128, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false, int QPW = 1, bool SBOX = false>
