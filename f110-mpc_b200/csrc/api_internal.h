@@ -35,6 +35,8 @@ struct f110_cycle_scratch {
 struct f110_cycle_lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_done = nullptr;
+  cudaEvent_t ev_own = nullptr, ev_gather = nullptr;   // gather root: this rank's rows are in the slot / the slot is on the host
+  bool gather_pending = false;
   unsigned char* stage = nullptr;      // device: [table | waypoints | inputs | outputs]
   size_t stage_bytes = 0;
   unsigned char* pin_in = nullptr;     // pinned staging of pageable caller inputs
@@ -85,6 +87,7 @@ struct f110_mpc_solver {
   // slots and the per-QP scratch lines, and one solve fills the GPU anyway), everything before a solve overlaps the previous one
   f110_cycle_lane lane[2];
   cudaEvent_t ev_solve = nullptr;
+  cudaStream_t gather_stream = nullptr;   // gather root: waits for the other ranks' flags and copies the slot out
   int next_ticket = 0;
   // gather of the packed rows across GPUs (f110_cycle_set_gather): where this rank's rows go, the flag it raises, and — on the
   // root — the flags it waits for and the rows it copies out

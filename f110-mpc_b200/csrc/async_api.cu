@@ -247,10 +247,21 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
     CUDA_TRY(f110api::launch_signal(st, d_flag, delivered));
     s->last_launches += 1;
     if (g.rank == 0) {
-      rc = f110_stream_wait_flags(st, g.flags, g.world, 0, delivered);
+      // the root waits for the other ranks and copies the slot out on its own gather stream: a rank that lags must not hold up the
+      // lane (the next cycle on this lane queues behind everything on its stream)
+      if (!s->gather_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->gather_stream, cudaStreamNonBlocking));
+      if (!L.ev_gather) {
+        CUDA_TRY(cudaEventCreateWithFlags(&L.ev_gather, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&L.ev_own, cudaEventDisableTiming));
+      }
+      CUDA_TRY(cudaEventRecord(L.ev_own, st));                                  // this rank's rows are in the slot
+      CUDA_TRY(cudaStreamWaitEvent(s->gather_stream, L.ev_own, 0));
+      rc = f110_stream_wait_flags(s->gather_stream, g.flags, g.world, 0, delivered);
       if (rc != F110_OK) return rc;
       const double* slot = g.ring + (size_t)(g.seq % g.slots) * g.world * g.rows * 4;
-      CUDA_TRY(cudaMemcpyAsync(L.pin_out + L.b_out, slot, L.gather_bytes, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(L.pin_out + L.b_out, slot, L.gather_bytes, cudaMemcpyDeviceToHost, s->gather_stream));
+      CUDA_TRY(cudaEventRecord(L.ev_gather, s->gather_stream));
+      L.gather_pending = true;
     }
     ++g.seq;
   }
@@ -268,7 +279,9 @@ int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status,
   f110_cycle_lane& L = s->lane[ticket & 1];
   if (!L.busy || L.ticket != ticket) return fail(F110_ERR_ARG, "f110_cycle_wait: no such cycle in flight");
   CUDA_TRY(cudaSetDevice(s->device));
-  const cudaError_t e = cudaEventSynchronize(L.ev_done);
+  cudaError_t e = cudaEventSynchronize(L.ev_done);
+  if (e == cudaSuccess && L.gather_pending) e = cudaEventSynchronize(L.ev_gather);
+  L.gather_pending = false;
   L.busy = false;
   if (e != cudaSuccess) return cuda_fail(e, "f110_cycle_wait");
   const unsigned char* ho = L.pin_out;

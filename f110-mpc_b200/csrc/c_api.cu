@@ -128,9 +128,12 @@ void f110_mpc_destroy(f110_mpc_solver* s) {
     if (l.pin_in) cudaFreeHost(l.pin_in);
     if (l.pin_out) cudaFreeHost(l.pin_out);
     if (l.ev_done) cudaEventDestroy(l.ev_done);
+    if (l.ev_own) cudaEventDestroy(l.ev_own);
+    if (l.ev_gather) cudaEventDestroy(l.ev_gather);
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   if (s->ev_solve) cudaEventDestroy(s->ev_solve);
+  if (s->gather_stream) cudaStreamDestroy(s->gather_stream);
   delete s;
 }
 
