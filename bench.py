@@ -372,11 +372,17 @@ def main_product(args):
     h_tab, h_wp = np.ascontiguousarray(wl["table_xy"]), np.ascontiguousarray(W.skirk_waypoints()[0], dtype=np.float32)
     out = {"u0": pin(np.empty((NQ, 2))), "status": pin(np.empty(NQ, dtype=np.int32)), "iters": pin(np.empty(NQ, dtype=np.int32)),
            "chosen": pin(np.empty(S, dtype=np.int32)), "valid": pin(np.empty((S, PATHS), dtype=np.uint8))}
-    h_gathered = pin(np.empty((world, NQ, 4))) if (peer and rank == 0) else None
+    h_gathered = None          # rank 0 reads the gathered rows in place (f110_cycle_gathered_view): no second host copy
+    last_view = [None]
     e2e_gather = peer
     if e2e_gather:
         barrier()
         sol_e.set_gather(gather.ring.ptr, world, rank, NQ, SLOTS)
+
+    def finish(tk):
+        sol_e.cycle_wait(tk, out=out)
+        if e2e_gather and rank == 0:     # every rank's rows of this cycle, in rank 0's (pinned) host memory
+            last_view[0] = sol_e.gathered_view(tk, world, NQ)
 
     def e2e_loop(n):
         """n cycles, two in flight; ranks re-align every SLOTS cycles so that nobody laps the ring"""
@@ -384,15 +390,15 @@ def main_product(args):
         for i in range(n):
             if e2e_gather and i and i % SLOTS == 0:
                 if pending is not None:
-                    sol_e.cycle_wait(pending, out=out, gathered=h_gathered)
+                    finish(pending)
                     pending = None
                 dist.barrier()
             tk = sol_e.cycle_submit(cc, h_pose, h_scan, None, h_tab, h_wp)
             if pending is not None:
-                sol_e.cycle_wait(pending, out=out, gathered=h_gathered)
+                finish(pending)
             pending = tk
         if pending is not None:
-            sol_e.cycle_wait(pending, out=out, gathered=h_gathered)
+            finish(pending)
 
     e2e_loop(warmup + (SLOTS - warmup % SLOTS) % SLOTS if e2e_gather else warmup)   # (keeps the ring's cycle counter aligned to a slot 0)
     barrier()
@@ -411,12 +417,13 @@ def main_product(args):
     # bytes that really move each step: poses + scans in; the output block (and, on rank 0, every rank's gathered rows) out.
     # The mini-path table and the raceline are start-up constants (project.cpp:34-37): uploaded once, not per step.
     h2d = int(h_pose.nbytes + h_scan.nbytes)
-    d2h = int(sum(v.nbytes for v in out.values())) + (int(h_gathered.nbytes) if h_gathered is not None else 0)
+    d2h = int(sum(v.nbytes for v in out.values())) + (int(last_view[0].nbytes) if last_view[0] is not None else 0)
     e2e_launches = sol_e.last_launches
     assert (out["status"] == 1).mean() > 0.95
     e2e_gather_ok = None
-    if h_gathered is not None:
-        e2e_gather_ok = bool(np.array_equal(h_gathered[0, :, :2], out["u0"]) and all((h_gathered[r, :, 2] == 1).mean() > 0.95 for r in range(world)))
+    if last_view[0] is not None:
+        hg = last_view[0]
+        e2e_gather_ok = bool(np.array_equal(hg[0, :, :2], out["u0"]) and all((hg[r, :, 2] == 1).mean() > 0.95 for r in range(world)))
     if e2e_gather:
         barrier()
         sol_e.set_gather(None, 0, 0, 0, 0)

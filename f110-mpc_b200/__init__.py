@@ -55,7 +55,7 @@ EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_
            "f110_mpc_create_multi", "f110_mpc_destroy_multi", "f110_mpc_solve_multi_host", "f110_mpc_multi_devices",
            "f110_mpc_multi_uses_peer_stores", "f110_mpc_multi_last_shard", "f110_gather_bytes", "f110_gather_create",
            "f110_gather_open", "f110_gather_close", "f110_gather_slot", "f110_stream_signal", "f110_stream_wait_flags",
-           "f110_cycle_set_gather", "f110_fleet_create", "f110_fleet_destroy", "f110_fleet_reset", "f110_fleet_run",
+           "f110_cycle_set_gather", "f110_cycle_gathered_view", "f110_fleet_create", "f110_fleet_destroy", "f110_fleet_reset", "f110_fleet_run",
            "f110_fleet_get_pose"]
 
 
@@ -120,6 +120,7 @@ def lib():
         L.f110_stream_signal.argtypes = [vp, vp, C.c_int32]
         L.f110_stream_wait_flags.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int32]
         L.f110_cycle_set_gather.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.f110_cycle_gathered_view.argtypes = [vp, C.c_int, C.POINTER(dp), C.POINTER(C.c_size_t)]
         L.f110_fleet_create.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.POINTER(vp)]
         L.f110_fleet_destroy.argtypes = [vp]
@@ -279,6 +280,14 @@ class MpcSolver:
         vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
         _check(lib().f110_cycle_wait(self._h, ticket, vp(u0), vp(status), vp(iters), vp(chosen), vp(valid), vp(gathered)), "f110_cycle_wait")
         return dict(u0=u0, status=status, iters=iters, chosen=chosen, valid=valid)
+
+    def gathered_view(self, ticket, world, rows):
+        """Gather root, after cycle_wait(ticket): the cycle's gathered rows as a (world, rows, 4) numpy VIEW of the handle's pinned
+        host buffer (no copy; valid until the second-next cycle_submit)."""
+        ptr, n = C.POINTER(C.c_double)(), C.c_size_t()
+        _check(lib().f110_cycle_gathered_view(self._h, ticket, C.byref(ptr), C.byref(n)), "f110_cycle_gathered_view")
+        assert n.value == world * rows * 4
+        return np.ctypeslib.as_array(ptr, shape=(world, rows, 4))
 
     def set_gather(self, ring_ptr, world, rank, rows_per_rank, slots):
         """Attach (or, with ring_ptr None, detach) a gather ring to the asynchronous cycle entry."""

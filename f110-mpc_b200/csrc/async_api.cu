@@ -297,4 +297,14 @@ int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status,
   return F110_OK;
 }
 
+int f110_cycle_gathered_view(f110_mpc_solver* s, int ticket, const double** rows, size_t* doubles) {
+  if (!s || ticket < 0 || !rows) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: bad argument");
+  f110_cycle_lane& L = s->lane[ticket & 1];
+  if (L.busy || L.ticket != ticket) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: call f110_cycle_wait on this ticket first (and before the second-next submit)");
+  if (!L.gather_bytes) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: gathered rows exist on the gather root (rank 0) only");
+  *rows = reinterpret_cast<const double*>(L.pin_out + L.b_out);
+  if (doubles) *doubles = L.gather_bytes / sizeof(double);
+  return F110_OK;
+}
+
 }  // extern "C"

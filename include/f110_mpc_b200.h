@@ -215,6 +215,9 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
                       int* ticket);
 int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid,
                     double* gathered);
+/* Zero-copy alternative to `gathered` on the gather root: after f110_cycle_wait(ticket) the gathered rows of that cycle stay in
+ * the handle's pinned host buffer until the second-next f110_cycle_submit; *rows points at world x rows x 4 doubles there. */
+int f110_cycle_gathered_view(f110_mpc_solver* s, int ticket, const double** rows, size_t* doubles);
 
 /* ---- multi-GPU: QPs are independent, shards are contiguous, the only exchange is a final gather of the
  * packed rows (u0_v, u0_steer, status, iters) to one GPU — and that gather is the solve kernel's own store over NVLink.

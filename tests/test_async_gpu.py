@@ -139,6 +139,7 @@ def test_gather_ring_two_ranks_on_one_device(pkg, workloads):
         got1 = sols[1].cycle_wait(tick[1])
         got0 = sols[0].cycle_wait(tick[0], gathered=gathered)
         _same(got0, want[0]); _same(got1, want[1])
+        np.testing.assert_array_equal(sols[0].gathered_view(tick[0], world, S), gathered)    # zero-copy view of the same rows
         for r in range(world):
             np.testing.assert_array_equal(gathered[r, :, :2], want[r]["u0"])
             np.testing.assert_array_equal(gathered[r, :, 2].astype(np.int32), want[r]["status"])
