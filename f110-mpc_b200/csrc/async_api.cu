@@ -241,7 +241,7 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   rc = f110api::cycle_device_range(s, L.cyc, cc, 0, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp,
                                    (double*)(d_out + L.o_u0), (int32_t*)(d_out + L.o_st), (int32_t*)(d_out + L.o_it), (int32_t*)(d_out + L.o_ch),
                                    d_out + L.o_val, st, s->ev_solve);
-  if (rc != F110_OK) { cudaStreamSynchronize(st); return rc; }
+  if (rc != F110_OK) { s->d_packed_next = nullptr; cudaStreamSynchronize(st); return rc; }
   if (g.ring) {
     const int32_t delivered = (int32_t)(g.seq + 1);
     CUDA_TRY(f110api::launch_signal(st, d_flag, delivered));

@@ -80,3 +80,32 @@ def test_header_is_plain_c_and_struct_layouts_match_bindings(pkg, tmp_path):
         assert int(out[name]) == C.sizeof(cls), name
         for fname, _ in cls._fields_:
             assert int(out["%s.%s" % (name, fname)]) == getattr(cls, fname).offset, (name, fname)
+
+
+def test_new_entry_points_check_their_arguments_without_a_gpu(pkg):
+    # argument errors are reported before any CUDA call: they must come back as F110_ERR_ARG (1) on a box without a GPU too
+    import ctypes as C
+    L = pkg.lib()
+    n = C.c_size_t()
+    assert L.f110_gather_bytes(8, 4100, 64, C.byref(n)) == 0 and n.value == 256 + 64 * 8 * 4100 * 32
+    assert L.f110_gather_bytes(0, 4100, 64, C.byref(n)) == 1 and L.f110_gather_bytes(8, 0, 64, C.byref(n)) == 1
+    assert L.f110_gather_slot(None, 2, 0, 8, 4, 0, None, None) == 1
+    assert L.f110_stream_signal(None, None, 1) == 1 and L.f110_stream_wait_flags(None, None, 2, 0, 1) == 1
+    cfg, st = pkg.default_config(), pkg.default_settings()
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 0)
+    assert L.f110_mpc_create_multi(C.byref(cfg), C.byref(st), 64, devs, 2, C.byref(h)) == 1          # a device listed twice
+    assert b"twice" in L.f110_last_error()
+    assert L.f110_mpc_create_multi(C.byref(cfg), C.byref(st), 0, devs, 1, C.byref(h)) == 1
+    t = C.c_int()
+    assert L.f110_cycle_submit(None, None, 1, None, None, None, None, 1, 1, None, 1, C.byref(t)) == 1
+    assert L.f110_cycle_wait(None, 0, None, None, None, None, None, None) == 1
+    assert L.f110_cycle_gathered_view(None, 0, None, None) == 1
+    assert L.f110_fleet_create(None, None, 1, None, 1, 1, None, 1, 2, 4, 0.01, C.byref(h)) == 1
+    assert L.f110_fleet_run(None, 1, None, None) == 1 and L.f110_fleet_reset(None, None, None) == 1
+    assert L.f110_mpc_multi_devices(None) == 0
+    # the state-box option is part of the config struct and of the row count
+    c = pkg.default_config(30, 0, state_lim=1.0)
+    assert L.f110_mpc_num_rows(C.byref(c)) == 7 * 30 + 5 + 3 * 31
+    c = pkg.default_config(30, 0, rate_delta=0.03)
+    assert L.f110_mpc_num_rows(C.byref(c)) == 8 * 30 + 5
