@@ -14,18 +14,26 @@
 //    eliminated per stage (2x2), leaving a symmetric block-tridiagonal system in x_0..x_N with 3x3 blocks.
 //  * That system is solved by parallel cyclic reduction across the lanes of the warp: log2(N+1) levels,
 //    every lane busy at every level.  The PCR multipliers are computed once per rho (factor step) and kept
-//    in shared memory (negated, in 16-byte pairs); each iteration only applies them to the right-hand side
-//    as FMA chains.  The top level is one-sided (partner = stage k XOR h) and stores a single 3x3 block.
+//    on chip (negated, in 16-byte pairs); each iteration only applies them to the right-hand side as FMA
+//    chains.  The top level is one-sided (partner = stage k XOR h) and stores a single 3x3 block.
+//  * Where the multipliers live: in TENSOR MEMORY for horizons 16..127 of the base row set and 16..31 with
+//    steering-rate rows (TM = true: tcgen05.st in the factor step, tcgen05.ld one PCR level ahead of its use in
+//    the iteration; each lane reads back exactly what it wrote, so the warp's 32-row strip is private storage
+//    with its own datapath), in shared memory otherwise.  The round-1 kernel was bound by the shared-memory /
+//    shuffle data pipe; see admm_device.cuh and DESIGN.md section 3.1.
 //  * The parameter record is staged into shared memory by one bulk asynchronous copy (TMA, cp.async.bulk +
 //    mbarrier) when it is 16-byte aligned; the Ruiz passes do not wait for anything but that one transfer.
 //  * x/z/y update, projection onto [l,u], residual norms and the termination test are fused in the same
-//    kernel; all reductions are warp shuffles.  Nothing but the parameter record is read from HBM and
-//    nothing but the solution is written (a per-QP scratch line in L2 holds the scaling vectors and the
-//    previous iterate, touched once per termination check).
+//    kernel; all reductions are warp shuffles / REDUX.  Nothing but the parameter record is read from HBM and
+//    nothing but the solution is written (a per-QP scratch line — shared memory for the tensor-memory
+//    kernels, L2 otherwise — holds the scaling vectors and the previous iterate, touched once per
+//    termination check).
 //
 //  * RATE = true adds N steering-rate rows  delta_k - delta_{k-1} in [-D, D]  (row 0: delta_0 - steer_prev).  They couple
 //    consecutive inputs, so only the speed v_k is eliminated per stage (a scalar pivot) and the steering angle joins
-//    the reduced unknown: s_k = (x_k, delta_k), 4x4 blocks, same cyclic reduction and shared-memory layout.
+//    the reduced unknown: s_k = (x_k, delta_k), 4x4 blocks, same cyclic reduction and pair layout.
+//  * SBOX = true adds 3(N+1) identity rows on x_0..x_N (the state box the reference stores but never stacks,
+//    constraints.cpp:14-17, 108-114): rho on the diagonal of T_kk, three more (z, y) pairs per stage.
 //
 // Lane k owns stage k: x_k(3), u_k(2) (k<N), dynamics rows k (3), gap rows k (2), input-box rows k (2), rate row k (1).
 // Lanes above N hold all-zero state and never feed an active lane (every cross-lane read is masked or
