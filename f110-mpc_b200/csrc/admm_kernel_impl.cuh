@@ -256,44 +256,41 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         for (int j = 0; j < 2; ++j) dup[j] = hasp ? rcv[3 + j] : 0.0;
       }
       double tx[3], tu[2], td[3], tg[2], tb[2];
+      // Column / row infinity norms of the scaled KKT matrix.  Every entry of a column carries the column's own scale as a positive
+      // factor, and rounding is monotone, so  max_i fl(a_i d) = fl((max_i a_i) d):  the factor is applied once, after the max.
+      // Structural zeros of B (b01 = b11 = 0) are left out of the maxima.
+      const double cQ[3] = {c * p.Q[0], c * p.Q[1], c * p.Q[2]}, cR[2] = {c * p.R[0], c * p.R[1]};
       // KKT column of x_k[j]: P, the -1 of dyn row k, column j of A in dyn rows k+1 (A = I + a02/a12 in col 2), gap rows k
+      [[maybe_unused]] double ts[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        double v = c * dx[j] * dx[j] * p.Q[j];
-        v = dmax(v, ed[j] * dx[j]);
-        v = dmax(v, edn[j] * dx[j]);
-        v = dmax(v, dmax(eg[0] * ag[j], eg[1] * ag[3 + j]) * dx[j]);
-        tx[j] = v;
+        double v = cQ[j] * dx[j];
+        v = dmax(v, ed[j]);
+        v = dmax(v, edn[j]);
+        v = dmax(v, dmax(eg[0] * ag[j], eg[1] * ag[3 + j]));
+        if (j == 2) v = dmax(v, dmax(edn[0] * aA02, edn[1] * aA12));
+        if constexpr (SBOX) {   // identity rows on x_k: one more entry in the column of x_k[j], a one-entry row
+          v = dmax(v, es[j]);
+          ts[j] = es[j] * dx[j];
+        }
+        tx[j] = v * dx[j];
       }
-      tx[2] = dmax(tx[2], dmax(edn[0] * aA02, edn[1] * aA12) * dx[2]);
-      [[maybe_unused]] double ts[3];
-      if constexpr (SBOX) {   // identity rows on x_k: one more entry in the column of x_k[j], a one-entry row
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { ts[j] = es[j] * dx[j]; tx[j] = dmax(tx[j], ts[j]); }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {  // KKT column of u_k[j]
-        double v = c * du[j] * du[j] * p.R[j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) v = dmax(v, edn[i] * aB[2 * i + j] * du[j]);
-        v = dmax(v, eb[j] * du[j]);
-        tu[j] = v;
+      {  // KKT columns of u_k = (v_k, delta_k): B has b00, b10, b20 in its first column, b21 in its second
+        double v = cR[0] * du[0];
+        v = dmax(v, dmax(edn[0] * aB[0], edn[1] * aB[2]));
+        v = dmax(v, dmax(edn[2] * aB[4], eb[0]));
+        tu[0] = v * du[0];
+        v = dmax(cR[1] * du[1], dmax(edn[2] * aB[5], eb[1]));
+        // steering-rate rows: column of delta_k has +1 in rate row k, -1 in rate row k+1
+        if constexpr (RATE) v = dmax(v, dmax(er, ern));
+        tu[1] = v * du[1];
       }
       double tr = 0.0;
-      if constexpr (RATE) {
-        // column of delta_k: +1 in rate row k, -1 in rate row k+1; rate row k: +1 on delta_k, -1 on delta_{k-1}
-        tu[1] = dmax(tu[1], dmax(er, ern) * du[1]);
-        tr = er * dmax(du[1], dup[1]);
-      }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {  // KKT column (= A row) of dyn row (k, i)
-        double v = dmax(dx[i], dxp[i]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) v = dmax(v, aB[2 * i + j] * dup[j]);
-        td[i] = v;
-      }
-      td[0] = dmax(td[0], aA02 * dxp[2]);
-      td[1] = dmax(td[1], aA12 * dxp[2]);
+      if constexpr (RATE) tr = er * dmax(du[1], dup[1]);   // rate row k: +1 on delta_k, -1 on delta_{k-1}
+      // KKT column (= A row) of dyn row (k, i): -1 on x_k[i], row i of [A B] on stage k-1
+      td[0] = dmax(dmax(dx[0], dxp[0]), dmax(aB[0] * dup[0], aA02 * dxp[2]));
+      td[1] = dmax(dmax(dx[1], dxp[1]), dmax(aB[2] * dup[0], aA12 * dxp[2]));
+      td[2] = dmax(dmax(dx[2], dxp[2]), dmax(aB[4] * dup[0], aB[5] * dup[1]));
 #pragma unroll
       for (int i = 0; i < 3; ++i) td[i] *= ed[i];
 #pragma unroll
@@ -326,11 +323,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       double psum = 0.0, qn = 0.0;
       if (act) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { psum += c * dx[j] * dx[j] * p.Q[j]; qn = dmax(qn, fabs(dx[j] * s.qx[j])); }
+        for (int j = 0; j < 3; ++j) { psum = fma(cQ[j] * dx[j], dx[j], psum); qn = dmax(qn, fabs(dx[j] * s.qx[j])); }
       }
       if (actu) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { psum += c * du[j] * du[j] * p.R[j]; qn = dmax(qn, fabs(du[j] * qu[j])); }
+        for (int j = 0; j < 2; ++j) { psum = fma(cR[j] * du[j], du[j], psum); qn = dmax(qn, fabs(du[j] * qu[j])); }
       }
       const double mean = cm.rsum(psum) / (double)nvar;
       const double qinf = limit_scaling(c * cm.rmax(qn));
@@ -1164,32 +1161,33 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       cm.sync();
     }
 
-    // Plain iterations run in their own inner loop (its back edge touches none of the rare blocks around it), up to and including
-    // the next iteration that needs residuals.
-    bool last, chk, adp;
-    for (;;) {
-    last = (iter == p.max_iter);
-    chk = (--ct_left == 0);
-    adp = (--ar_left == 0);
+    // Plain iterations run in their own counted inner loop (its back edge touches none of the rare blocks around it and carries one
+    // counter), up to and including the next iteration that needs residuals: a termination check, a rho adaptation or the last one.
+    int togo = p.max_iter - iter + 1;
+    if (ct_left > 0 && ct_left < togo) togo = ct_left;
+    if (ar_left > 0 && ar_left < togo) togo = ar_left;
+    iter += togo - 1;
+    ct_left -= togo;   // (a disabled countdown is negative and stays negative)
+    ar_left -= togo;
+    const bool last = (iter == p.max_iter), chk = (ct_left == 0), adp = (ar_left == 0);
     if (chk) ct_left = p.check_termination;
     if (adp) ar_left = ari;
-    const bool info_iter = chk || adp || last;
-    if (info_iter) {  // the infeasibility tests need delta x, delta y of this iteration
+    for (;;) {
+      --togo;
+      if (togo == 0) {  // the infeasibility tests need delta x, delta y of this iteration
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
+        for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
-      if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
-      if constexpr (SBOX) {
+        for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
+        if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
+        if constexpr (SBOX) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) scr[(SCR_PYS + j) * T] = s.ys[j];
+          for (int j = 0; j < 3; ++j) scr[(SCR_PYS + j) * T] = s.ys[j];
+        }
       }
-    }
-
-    if (first_iter) { iterate(std::true_type{}); first_iter = false; }
-    else iterate(std::false_type{});
-    if (info_iter) break;
-    ++iter;
+      if (first_iter) { iterate(std::true_type{}); first_iter = false; }
+      else iterate(std::false_type{});
+      if (togo == 0) break;
     }
 
     // ---------- residuals & norms (OSQP update_info + the norms of compute_rho_estimate) -----------------------
