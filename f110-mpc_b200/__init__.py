@@ -55,7 +55,7 @@ EXPORTS = ["f110_mpc_default_config", "f110_solver_default_settings", "f110_mpc_
            "f110_mpc_create_multi", "f110_mpc_destroy_multi", "f110_mpc_solve_multi_host", "f110_mpc_multi_devices",
            "f110_mpc_multi_uses_peer_stores", "f110_mpc_multi_last_shard", "f110_gather_bytes", "f110_gather_create",
            "f110_gather_open", "f110_gather_close", "f110_gather_slot", "f110_stream_signal", "f110_stream_wait_flags",
-           "f110_cycle_set_gather", "f110_cycle_gathered_view", "f110_fleet_create", "f110_fleet_destroy", "f110_fleet_reset", "f110_fleet_run",
+           "f110_cycle_set_gather", "f110_cycle_gathered_view", "f110_cycle_set_depth", "f110_fleet_create", "f110_fleet_destroy", "f110_fleet_reset", "f110_fleet_run",
            "f110_fleet_get_pose"]
 
 
@@ -121,6 +121,7 @@ def lib():
         L.f110_stream_wait_flags.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int32]
         L.f110_cycle_set_gather.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.f110_cycle_gathered_view.argtypes = [vp, C.c_int, C.POINTER(dp), C.POINTER(C.c_size_t)]
+        L.f110_cycle_set_depth.argtypes = [vp, C.c_int]
         L.f110_fleet_create.argtypes = [vp, C.POINTER(CycleConfig), C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.POINTER(vp)]
         L.f110_fleet_destroy.argtypes = [vp]
@@ -288,6 +289,10 @@ class MpcSolver:
         _check(lib().f110_cycle_gathered_view(self._h, ticket, C.byref(ptr), C.byref(n)), "f110_cycle_gathered_view")
         assert n.value == world * rows * 4
         return np.ctypeslib.as_array(ptr, shape=(world, rows, 4))
+
+    def set_cycle_depth(self, depth):
+        """f110_cycle_set_depth: cycles that may be in flight on this handle (1..4, default 2); only while none is in flight."""
+        _check(lib().f110_cycle_set_depth(self._h, depth), "f110_cycle_set_depth")
 
     def set_gather(self, ring_ptr, world, rank, rows_per_rank, slots):
         """Attach (or, with ring_ptr None, detach) a gather ring to the asynchronous cycle entry."""

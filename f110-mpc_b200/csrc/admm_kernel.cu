@@ -1,5 +1,7 @@
 // Launch dispatch of the batched ADMM solve.  The kernel template lives in admm_kernel_impl.cuh and is instantiated in
 // one translation unit per warps-per-QP class (and per row set) so the instantiations compile in parallel.
+#include <cstdlib>
+
 #include "admm_kernel.cuh"
 
 namespace f110 {
@@ -10,6 +12,11 @@ cudaError_t launch_admm_w4(const KParams& p, cudaStream_t stream);            //
 cudaError_t launch_admm_w1r(const KParams& p, cudaStream_t stream, int nlev); // + steering-rate rows, horizons 1..31
 cudaError_t launch_admm_w2r(const KParams& p, cudaStream_t stream);           // + steering-rate rows, horizons 32..63
 cudaError_t launch_admm_w1s(const KParams& p, cudaStream_t stream, int nlev); // + state-box rows, horizons 1..31
+
+bool admm_state_on_chip(int N, int rate_rows, int state_rows) {
+  static const bool no_tmem = [] { const char* e = std::getenv("F110_NO_TMEM"); return e && e[0] == '1'; }();
+  return !no_tmem && !rate_rows && !state_rows && N >= 16 && N <= 127;
+}
 
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {
   int nlev = 0;

@@ -63,6 +63,9 @@ __host__ __device__ inline int state_doubles(int N, int rate_rows, int state_row
 
 // Launch the solve for p.B QPs on `stream`. Returns the cudaError of the launch.
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches);
+// True when the kernel launch_admm picks for this problem family keeps all per-QP working state on chip (tensor memory + shared
+// memory: horizons 16..127 of the base row set): two launches of one handle may then overlap without sharing scratch lines.
+bool admm_state_on_chip(int N, int rate_rows, int state_rows);
 
 cudaError_t launch_collision(int scenes, int paths, int samples, int blocks, float discrete, const float* grid,
                              const float* offset, const double* rot, const double* pose_xy,

@@ -83,9 +83,13 @@ struct f110_mpc_solver {
   cudaGraphExec_t lat_graph[3] = {nullptr, nullptr, nullptr};
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
-  // asynchronous cycles: two lanes; the solves of consecutive cycles are serialised through ev_solve (they share the warm-start
-  // slots and the per-QP scratch lines, and one solve fills the GPU anyway), everything before a solve overlaps the previous one
-  f110_cycle_lane lane[2];
+  // asynchronous cycles: `depth` lanes (2 by default, f110_cycle_set_depth).  Everything before a solve overlaps the previous
+  // cycle's solve.  The solves themselves are serialised through ev_solve when consecutive cycles share state (warm-start slots,
+  // per-QP scratch lines in global memory, the gather ring's per-rank flag); cold-started solves of a kernel that keeps its
+  // working state on chip share nothing and overlap too — the next cycle's CTAs fill the SMs the previous solve's tail leaves idle.
+  static constexpr int kMaxLanes = 4;
+  f110_cycle_lane lane[kMaxLanes];
+  int depth = 2;
   cudaEvent_t ev_solve = nullptr;
   cudaStream_t gather_stream = nullptr;   // gather root: waits for the other ranks' flags and copies the slot out
   int next_ticket = 0;

@@ -3,9 +3,10 @@
 //
 // Why: f110_cycle_host copies in, runs five kernels, copies out and synchronises — 96 us of every 410 us call was exposed copy
 // and synchronisation (round-1 measurement).  The reference's own control loop has the same shape: OdomCallback runs a cycle
-// while DriveLoop applies the previous cycle's result (project.cpp:160-191, 220-238).  Here two cycles may be in flight per
-// handle: cycle k+1's host-to-device copies and its small perception kernels run under cycle k's solve, and the host only blocks
-// in f110_cycle_wait.
+// while DriveLoop applies the previous cycle's result (project.cpp:160-191, 220-238).  Here two cycles (up to four,
+// f110_cycle_set_depth) may be in flight per handle: cycle k+1's host-to-device copies and its small perception kernels run under
+// cycle k's solve, cold-started solves of consecutive cycles overlap as well (the next cycle's CTAs take the SMs the previous
+// solve's tail leaves idle), and the host only blocks in f110_cycle_wait.
 //
 // Gather: QPs are independent, so a multi-GPU batch needs nothing but a final gather of (u0, status, iters) to one GPU
 // (SURVEY.md section 8e).  The solve kernel writes that packed row itself; with a gather ring attached, the row's destination is
@@ -13,6 +14,7 @@
 // NVLink — no collective launch on the step.  A rank raises a per-rank flag on the root after its solve; the root's stream waits for
 // all flags with a stream memory operation before it copies the gathered rows out.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda.h>
 
@@ -159,6 +161,16 @@ int f110_cycle_set_gather(f110_mpc_solver* s, void* d_ring, int world, int rank,
   return F110_OK;
 }
 
+int f110_cycle_set_depth(f110_mpc_solver* s, int depth) {
+  if (!s || depth < 1 || depth > f110_mpc_solver::kMaxLanes) return fail(F110_ERR_ARG, "f110_cycle_set_depth: depth must be 1.." + std::to_string(f110_mpc_solver::kMaxLanes));
+  for (const f110_cycle_lane& l : s->lane)
+    if (l.busy) return fail(F110_ERR_ARG, "f110_cycle_set_depth: cycles are in flight (wait for them first)");
+  // tickets map to lanes by ticket % depth: restart the numbering on a multiple of every depth so lane 0 comes next
+  s->next_ticket = (s->next_ticket + 11) / 12 * 12;
+  s->depth = depth;
+  return F110_OK;
+}
+
 int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scenes, const double* pose7, const float* ranges,
                       const double* prev_steer, const double* table_xy, int paths, int samples, const float* wp_xy, int n_wp, int* ticket) {
   if (!s || !cc || !pose7 || !ranges || !table_xy || !wp_xy || !ticket) return fail(F110_ERR_ARG, "f110_cycle_submit: null argument");
@@ -167,8 +179,9 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   if (nqp > s->max_batch) return fail(F110_ERR_ARG, "f110_cycle_submit: QP count exceeds max_batch");
   auto& g = s->gather;
   if (g.ring && nqp > g.rows) return fail(F110_ERR_ARG, "f110_cycle_submit: QP count exceeds the gather ring's rows per rank");
-  f110_cycle_lane& L = s->lane[s->next_ticket & 1];
-  if (L.busy) return fail(F110_ERR_ARG, "f110_cycle_submit: two cycles are already in flight (call f110_cycle_wait on the older ticket)");
+  f110_cycle_lane& L = s->lane[s->next_ticket % s->depth];
+  if (L.busy)
+    return fail(F110_ERR_ARG, "f110_cycle_submit: " + std::to_string(s->depth) + " cycles are already in flight (call f110_cycle_wait on the oldest ticket)");
   CUDA_TRY(cudaSetDevice(s->device));
   if (!L.stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -238,9 +251,13 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
     s->d_packed_next = d_rows;   // the solve kernel stores this rank's rows on the root GPU
   }
   s->last_launches = 0;
+  // Consecutive solves must run in submission order when they share state: the warm-start slots, scratch lines in global memory, or
+  // the gather ring's per-rank flag (a counter of delivered cycles).  Otherwise they may overlap.
+  static const bool force_ordered = [] { const char* e = std::getenv("F110_CYCLE_ORDERED"); return e && e[0] == '1'; }();   // A/B measurements
+  const bool ordered = force_ordered || s->st.warm_start || g.ring || !f110::admm_state_on_chip(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows);
   rc = f110api::cycle_device_range(s, L.cyc, cc, 0, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp,
                                    (double*)(d_out + L.o_u0), (int32_t*)(d_out + L.o_st), (int32_t*)(d_out + L.o_it), (int32_t*)(d_out + L.o_ch),
-                                   d_out + L.o_val, st, s->ev_solve);
+                                   d_out + L.o_val, st, ordered ? s->ev_solve : nullptr);
   if (rc != F110_OK) { s->d_packed_next = nullptr; cudaStreamSynchronize(st); return rc; }
   if (g.ring) {
     const int32_t delivered = (int32_t)(g.seq + 1);
@@ -276,7 +293,7 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
 int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid,
                     double* gathered) {
   if (!s || ticket < 0) return fail(F110_ERR_ARG, "f110_cycle_wait: bad argument");
-  f110_cycle_lane& L = s->lane[ticket & 1];
+  f110_cycle_lane& L = s->lane[ticket % s->depth];
   if (!L.busy || L.ticket != ticket) return fail(F110_ERR_ARG, "f110_cycle_wait: no such cycle in flight");
   CUDA_TRY(cudaSetDevice(s->device));
   cudaError_t e = cudaEventSynchronize(L.ev_done);
@@ -299,8 +316,8 @@ int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status,
 
 int f110_cycle_gathered_view(f110_mpc_solver* s, int ticket, const double** rows, size_t* doubles) {
   if (!s || ticket < 0 || !rows) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: bad argument");
-  f110_cycle_lane& L = s->lane[ticket & 1];
-  if (L.busy || L.ticket != ticket) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: call f110_cycle_wait on this ticket first (and before the second-next submit)");
+  f110_cycle_lane& L = s->lane[ticket % s->depth];
+  if (L.busy || L.ticket != ticket) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: call f110_cycle_wait on this ticket first (and before the lane's next submit)");
   if (!L.gather_bytes) return fail(F110_ERR_ARG, "f110_cycle_gathered_view: gathered rows exist on the gather root (rank 0) only");
   *rows = reinterpret_cast<const double*>(L.pin_out + L.b_out);
   if (doubles) *doubles = L.gather_bytes / sizeof(double);

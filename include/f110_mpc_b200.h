@@ -205,8 +205,10 @@ int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, dou
 /* ---- asynchronous form of f110_cycle_host (the shape of the reference's own loop: OdomCallback computes cycle k+1 while
  * DriveLoop applies cycle k's result, project.cpp:160-191, 220-238).  f110_cycle_submit queues the copies and kernels of one
  * cycle and returns a ticket; f110_cycle_wait blocks until that cycle's results are in the caller's arrays.  At most TWO cycles
- * may be in flight per handle: cycle k+1's host-to-device copies and perception kernels run under cycle k's solve; the solves
- * themselves run in submission order (they share the handle's warm-start slots).  Inputs are read straight from the caller's
+ * may be in flight per handle (f110_cycle_set_depth: 1..4): cycle k+1's host-to-device copies and perception kernels run under
+ * cycle k's solve.  The solves themselves run in submission order when they share state — warm_start = 1 (the handle's warm-start
+ * slots), an attached gather ring, or a problem family whose kernel keeps scratch lines in global memory (steering-rate / state-box
+ * rows, horizons below 16); cold-started solves of the base row set overlap, which changes no result.  Inputs are read straight from the caller's
  * buffers when those are pinned (cudaHostAlloc / cudaHostRegister) and must then stay untouched until the matching wait; pageable
  * inputs are copied into the handle's own pinned staging before the call returns.  Results are identical to f110_cycle_host.
  * `gathered` (f110_cycle_wait): NULL, or — on the root of an attached gather ring — world x rows x 4 doubles. */
@@ -216,8 +218,11 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
 int f110_cycle_wait(f110_mpc_solver* s, int ticket, double* u0, int32_t* status, int32_t* iters, int32_t* chosen, uint8_t* valid,
                     double* gathered);
 /* Zero-copy alternative to `gathered` on the gather root: after f110_cycle_wait(ticket) the gathered rows of that cycle stay in
- * the handle's pinned host buffer until the second-next f110_cycle_submit; *rows points at world x rows x 4 doubles there. */
+ * the handle's pinned host buffer until the `depth`-th next f110_cycle_submit; *rows points at world x rows x 4 doubles there. */
 int f110_cycle_gathered_view(f110_mpc_solver* s, int ticket, const double** rows, size_t* doubles);
+/* Number of cycles that may be in flight per handle (1..4, default 2).  Only while no cycle is in flight.  Deeper pipelines pay when
+ * one QP of a batch runs far longer than the rest (a max_iter straggler): later cycles stream past it. */
+int f110_cycle_set_depth(f110_mpc_solver* s, int depth);
 
 /* ---- multi-GPU: QPs are independent, shards are contiguous, the only exchange is a final gather of the
  * packed rows (u0_v, u0_steer, status, iters) to one GPU — and that gather is the solve kernel's own store over NVLink.

@@ -101,6 +101,7 @@ def test_new_entry_points_check_their_arguments_without_a_gpu(pkg):
     assert L.f110_cycle_submit(None, None, 1, None, None, None, None, 1, 1, None, 1, C.byref(t)) == 1
     assert L.f110_cycle_wait(None, 0, None, None, None, None, None, None) == 1
     assert L.f110_cycle_gathered_view(None, 0, None, None) == 1
+    assert L.f110_cycle_set_depth(None, 2) == 1
     assert L.f110_fleet_create(None, None, 1, None, 1, 1, None, 1, 2, 4, 0.01, C.byref(h)) == 1
     assert L.f110_fleet_run(None, 1, None, None) == 1 and L.f110_fleet_reset(None, None, None) == 1
     assert L.f110_mpc_multi_devices(None) == 0

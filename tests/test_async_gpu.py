@@ -171,3 +171,50 @@ def test_multi_gpu_handle_matches_single_gpu(pkg, workloads, unit):
     with pytest.raises(RuntimeError, match="multiple of the shard unit"):
         m.solve_host(recs[:unit * 3 + 1], unit=3 if unit == 1 else unit)
     m.close()
+
+
+def test_four_cycles_in_flight_with_overlapping_solves(pkg, workloads):
+    # cold-started solves of the base row set share nothing on the device, so consecutive cycles' solves are not ordered against
+    # each other (f110_cycle_set_depth up to 4): same bits as one synchronous call per cycle, in any completion order
+    S, P = 80, 20
+    cc = pkg.default_cycle_config(qp_mode=2)
+    scenes = [_scene(workloads, S, 540 + i) for i in range(7)]
+    ref = pkg.MpcSolver(pkg.default_config(30), pkg.default_settings(warm_start=0), max_batch=S * P)
+    want = [ref.cycle_host(cc, s[0], s[1], None, s[2], s[3]) for s in scenes]
+    sol = pkg.MpcSolver(pkg.default_config(30), pkg.default_settings(warm_start=0), max_batch=S * P)
+    sol.set_cycle_depth(4)
+    pending, got = [], []
+    for s in scenes:
+        if len(pending) == 4:
+            got.append(sol.cycle_wait(pending.pop(0)))
+        pending.append(sol.cycle_submit(cc, s[0], s[1], None, s[2], s[3]))
+    with pytest.raises(RuntimeError, match="in flight"):
+        sol.set_cycle_depth(2)                      # only between cycles
+    got += [sol.cycle_wait(t) for t in pending]
+    for g, w in zip(got, want):
+        _same(g, w)
+    with pytest.raises(RuntimeError, match="depth must be"):
+        sol.set_cycle_depth(5)
+    sol.set_cycle_depth(1)                          # strictly one at a time
+    t0 = sol.cycle_submit(cc, *scenes[0][:2], None, *scenes[0][2:])
+    with pytest.raises(RuntimeError, match="already in flight"):
+        sol.cycle_submit(cc, *scenes[1][:2], None, *scenes[1][2:])
+    _same(sol.cycle_wait(t0), want[0])
+
+
+def test_depth_four_keeps_warm_started_solves_in_order(pkg, workloads):
+    S = 40
+    cc = pkg.default_cycle_config(qp_mode=0)
+    scenes = [_scene(workloads, S, 560 + i) for i in range(6)]
+    ref = pkg.MpcSolver(pkg.default_config(30), pkg.default_settings(warm_start=1), max_batch=S)
+    want = [ref.cycle_host(cc, s[0], s[1], None, s[2], s[3]) for s in scenes]
+    sol = pkg.MpcSolver(pkg.default_config(30), pkg.default_settings(warm_start=1), max_batch=S)
+    sol.set_cycle_depth(4)
+    pending, got = [], []
+    for s in scenes:
+        if len(pending) == 4:
+            got.append(sol.cycle_wait(pending.pop(0)))
+        pending.append(sol.cycle_submit(cc, s[0], s[1], None, s[2], s[3]))
+    got += [sol.cycle_wait(t) for t in pending]
+    for g, w in zip(got, want):
+        _same(g, w)
