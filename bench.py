@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 
 N_HORIZON = 30
 QPS_PER_GPU = 4096
-PIPELINE_DEPTH = 4     # streams the steps of the timed region alternate over / cycles in flight of the e2e leg
+E2E_MIN_CYCLES = 200   # the e2e leg is timed by the host clock: at least this many cycles (45 ms), so that one scheduling hiccup is not the number
+PIPELINE_DEPTH = int(os.environ.get("F110_BENCH_DEPTH", "4"))     # streams the steps of the timed region alternate over / cycles in flight of the e2e leg
 PATHS = 20            # README.md:12 count (steer_discrete = 19)
 SAMPLES = 50
 METRIC = "batched MPC QP solves/sec"
@@ -93,6 +94,22 @@ def build_workload(M, W, rank):
             r[11:] = ref.reshape(-1)
     return dict(recs=recs[:QPS_PER_GPU], grids=grids, offs=offs, rots=rots, pose_xy=poses[:, :2].copy(),
                 table_xy=np.ascontiguousarray(table[:, :, :2]), scenes=S, poses=poses, scans=scans)
+
+
+def init_nccl(dist, torch, dev):
+    """init_process_group + a first collective with file descriptor 1 pointed at stderr: NCCL prints its version banner on
+    stdout when the communicator comes up, and stdout carries exactly one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 class ClockSampler:
@@ -255,7 +272,7 @@ def main_product(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dist, torch, dev)
     M.build()
     wl = build_workload(M, W, rank)
     B, S = QPS_PER_GPU, wl["scenes"]
@@ -286,8 +303,8 @@ def main_product(args):
     streams = [torch.cuda.Stream(device=dev) for _ in range(DEPTH)]
     # ---- the gather: a ring on rank 0's GPU that every rank's solve kernel stores into (no collective on the step)
     # ring depth: a rank may run ahead of rank 0's reads by fewer than SLOTS cycles, so the ranks re-align (one host barrier) every
-    # SLOTS e2e cycles; deep enough that a default run never needs to (64 slots x 8 ranks x 4100 rows x 32 B = 67 MB on rank 0)
-    SLOTS = min(1024, max(64, 8 * ((2 * args.steps + max(args.warmup, 3) + 15) // 8)))
+    # SLOTS e2e cycles; deep enough that a default run never needs to (224 slots x 8 ranks x 4100 rows x 32 B = 235 MB on rank 0)
+    SLOTS = min(1024, max(64, 8 * ((max(2 * args.steps, E2E_MIN_CYCLES) + max(args.warmup, 3) + 2 * PIPELINE_DEPTH + 15) // 8)))
     gather = PeerGather(M, dist, torch, dev, world, rank, local, NQ, SLOTS) if world > 1 else None
     peer = gather is not None and gather.ok
     d_packed = torch.empty(B, 4, dtype=torch.float64, device=dev) if (world > 1 and not peer) else None   # NCCL fallback
@@ -443,7 +460,8 @@ def main_product(args):
     import gc
     gc.collect(); gc.disable()          # a collector pause inside a 0.3 ms host loop would be measured as GPU time
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
+    e2e_cycles = max(args.steps, E2E_MIN_CYCLES)
+    e2e_loop(e2e_cycles)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     gc.enable()
@@ -451,7 +469,7 @@ def main_product(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = te.item()
-    e2e_value = world * NQ * args.steps / e2e_s
+    e2e_value = world * NQ * e2e_cycles / e2e_s
     # bytes that really move each step: poses + scans in; the output block (and, on rank 0, every rank's gathered rows) out.
     # The mini-path table and the raceline are start-up constants (project.cpp:34-37): uploaded once, not per step.
     h2d = int(h_pose.nbytes + h_scan.nbytes)
@@ -554,7 +572,7 @@ def main_product(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(wl),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "cycles": e2e_cycles,
                     "call": "f110_cycle_submit / f110_cycle_wait (qp_mode 2), %d cycles in flight: scans + poses in, %d kernels, controls out; "
                             "%d QPs per step per GPU%s" % (DEPTH, e2e_launches, NQ, "; every rank's rows gathered to rank 0's host buffer each step" if peer else ""),
                     "gathered_to_rank0_host": e2e_gather_ok},
@@ -595,7 +613,7 @@ def main_config4(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dist, torch, dev)
     M.build()
     recs = config4_records(W)
     total, per_sc = recs.shape[0], 7 * 20
@@ -684,7 +702,7 @@ def main_sweep(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dist, torch, dev)
     M.build()
     B = 4096
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

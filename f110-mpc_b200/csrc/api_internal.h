@@ -85,7 +85,7 @@ struct f110_mpc_solver {
   cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
   // asynchronous cycles: `depth` lanes (2 by default, f110_cycle_set_depth).  Everything before a solve overlaps the previous
   // cycle's solve.  The solves themselves are serialised through ev_solve when consecutive cycles share state (warm-start slots,
-  // per-QP scratch lines in global memory, the gather ring's per-rank flag); cold-started solves of a kernel that keeps its
+  // per-QP scratch lines in global memory); cold-started solves of a kernel that keeps its
   // working state on chip share nothing and overlap too — the next cycle's CTAs fill the SMs the previous solve's tail leaves idle.
   static constexpr int kMaxLanes = 4;
   f110_cycle_lane lane[kMaxLanes];
@@ -97,7 +97,7 @@ struct f110_mpc_solver {
   // root — the flags it waits for and the rows it copies out
   struct Gather {
     double* ring = nullptr;      // [slots][world][rows][4] doubles on the root GPU (peer-mapped on the others)
-    int32_t* flags = nullptr;    // [world] on the root GPU: flags[r] = number of cycles rank r has delivered
+    int32_t* flags = nullptr;    // [slots][world] on the root GPU: flags[c % slots][r] = c + 1 once rank r has delivered cycle c
     int slots = 0, world = 0, rank = 0, rows = 0;
     long long seq = 0;           // cycles submitted with the gather on
   } gather;

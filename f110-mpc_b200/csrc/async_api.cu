@@ -54,6 +54,22 @@ wait_value_fn wait_value_entry() {
   return fn;
 }
 
+// cuStreamWriteValue32: the flag is raised by the stream itself once everything before it (the solve kernel's peer stores
+// included) is complete.  Unlike a one-thread kernel it needs no SM slot — with overlapping solves every slot is held by a
+// persistent CTA of the next cycle, and a signal kernel would queue behind them.
+typedef CUresult (*write_value_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+write_value_fn write_value_entry() {
+  static write_value_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    const char* e = std::getenv("F110_SIGNAL_KERNEL");   // A/B measurements: force the one-thread kernel
+    if (e && e[0] == '1') p = nullptr;
+    return reinterpret_cast<write_value_fn>(p);
+  }();
+  return fn;
+}
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -61,11 +77,15 @@ bool is_pinned(const void* p) {
 }
 
 size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-constexpr size_t kFlagBytes = 256;   // flags[world] at the head of the ring allocation
+// flags[slots][world] at the head of the ring allocation: one flag per (slot, rank), so cycles may complete in any order
+size_t flag_bytes(int world, int slots) { return up256((size_t)slots * world * sizeof(int32_t)); }
 
 }  // namespace
 
 cudaError_t f110api::launch_signal(cudaStream_t st, int32_t* flag, int32_t value) {
+  if (write_value_fn fn = write_value_entry()) {
+    if (fn((CUstream)st, (CUdeviceptr)(uintptr_t)flag, (cuuint32_t)value, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return cudaSuccess;
+  }
   signal_kernel<<<1, 1, 0, st>>>(flag, value);
   return cudaGetLastError();
 }
@@ -74,7 +94,7 @@ extern "C" {
 
 int f110_gather_bytes(int world, int rows_per_rank, int slots, size_t* bytes) {
   if (world < 1 || world > 64 || rows_per_rank < 1 || slots < 1 || !bytes) return fail(F110_ERR_ARG, "f110_gather_bytes: bad argument");
-  *bytes = kFlagBytes + (size_t)slots * world * rows_per_rank * 4 * sizeof(double);
+  *bytes = flag_bytes(world, slots) + (size_t)slots * world * rows_per_rank * 4 * sizeof(double);
   return F110_OK;
 }
 
@@ -121,8 +141,8 @@ int f110_gather_close(int device, void* d_ring, int opened) {
 int f110_gather_slot(void* d_ring, int world, int rank, int rows_per_rank, int slots, long long seq, double** d_rows, int32_t** d_flag) {
   if (!d_ring || rank < 0 || rank >= world || slots < 1) return fail(F110_ERR_ARG, "f110_gather_slot: bad argument");
   unsigned char* base = static_cast<unsigned char*>(d_ring);
-  if (d_rows) *d_rows = reinterpret_cast<double*>(base + kFlagBytes) + ((size_t)(seq % slots) * world + rank) * rows_per_rank * 4;
-  if (d_flag) *d_flag = reinterpret_cast<int32_t*>(base) + rank;
+  if (d_rows) *d_rows = reinterpret_cast<double*>(base + flag_bytes(world, slots)) + ((size_t)(seq % slots) * world + rank) * rows_per_rank * 4;
+  if (d_flag) *d_flag = reinterpret_cast<int32_t*>(base) + (size_t)(seq % slots) * world + rank;
   return F110_OK;
 }
 
@@ -156,7 +176,7 @@ int f110_cycle_set_gather(f110_mpc_solver* s, void* d_ring, int world, int rank,
   if (world < 1 || rank < 0 || rank >= world || rows_per_rank < 1 || slots < 1) return fail(F110_ERR_ARG, "f110_cycle_set_gather: bad argument");
   unsigned char* base = static_cast<unsigned char*>(d_ring);
   s->gather.flags = reinterpret_cast<int32_t*>(base);
-  s->gather.ring = reinterpret_cast<double*>(base + kFlagBytes);
+  s->gather.ring = reinterpret_cast<double*>(base + flag_bytes(world, slots));
   s->gather.world = world; s->gather.rank = rank; s->gather.rows = rows_per_rank; s->gather.slots = slots; s->gather.seq = 0;
   return F110_OK;
 }
@@ -247,14 +267,14 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
   int32_t* d_flag = nullptr;
   if (g.ring) {
     d_rows = g.ring + ((size_t)(g.seq % g.slots) * g.world + g.rank) * g.rows * 4;
-    d_flag = g.flags + g.rank;
+    d_flag = g.flags + (size_t)(g.seq % g.slots) * g.world + g.rank;
     s->d_packed_next = d_rows;   // the solve kernel stores this rank's rows on the root GPU
   }
   s->last_launches = 0;
-  // Consecutive solves must run in submission order when they share state: the warm-start slots, scratch lines in global memory, or
-  // the gather ring's per-rank flag (a counter of delivered cycles).  Otherwise they may overlap.
+  // Consecutive solves must run in submission order when they share state: the warm-start slots or scratch lines in global memory.
+  // Otherwise they may overlap (the gather ring has one flag per slot and rank, so cycles may complete in any order).
   static const bool force_ordered = [] { const char* e = std::getenv("F110_CYCLE_ORDERED"); return e && e[0] == '1'; }();   // A/B measurements
-  const bool ordered = force_ordered || s->st.warm_start || g.ring || !f110::admm_state_on_chip(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows);
+  const bool ordered = force_ordered || s->st.warm_start || !f110::admm_state_on_chip(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows);
   rc = f110api::cycle_device_range(s, L.cyc, cc, 0, scenes, d_pose, d_rng, prev_steer ? d_prev : nullptr, d_tab, paths, samples, d_wp, n_wp,
                                    (double*)(d_out + L.o_u0), (int32_t*)(d_out + L.o_st), (int32_t*)(d_out + L.o_it), (int32_t*)(d_out + L.o_ch),
                                    d_out + L.o_val, st, ordered ? s->ev_solve : nullptr);
@@ -273,7 +293,7 @@ int f110_cycle_submit(f110_mpc_solver* s, const f110_cycle_config* cc, int scene
       }
       CUDA_TRY(cudaEventRecord(L.ev_own, st));                                  // this rank's rows are in the slot
       CUDA_TRY(cudaStreamWaitEvent(s->gather_stream, L.ev_own, 0));
-      rc = f110_stream_wait_flags(s->gather_stream, g.flags, g.world, 0, delivered);
+      rc = f110_stream_wait_flags(s->gather_stream, g.flags + (size_t)(g.seq % g.slots) * g.world, g.world, 0, delivered);
       if (rc != F110_OK) return rc;
       const double* slot = g.ring + (size_t)(g.seq % g.slots) * g.world * g.rows * 4;
       CUDA_TRY(cudaMemcpyAsync(L.pin_out + L.b_out, slot, L.gather_bytes, cudaMemcpyDeviceToHost, s->gather_stream));

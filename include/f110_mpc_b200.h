@@ -207,8 +207,8 @@ int f110_cycle_buffers(f110_mpc_solver* s, float** d_grid, float** d_offset, dou
  * cycle and returns a ticket; f110_cycle_wait blocks until that cycle's results are in the caller's arrays.  At most TWO cycles
  * may be in flight per handle (f110_cycle_set_depth: 1..4): cycle k+1's host-to-device copies and perception kernels run under
  * cycle k's solve.  The solves themselves run in submission order when they share state — warm_start = 1 (the handle's warm-start
- * slots), an attached gather ring, or a problem family whose kernel keeps scratch lines in global memory (steering-rate / state-box
- * rows, horizons below 16); cold-started solves of the base row set overlap, which changes no result.  Inputs are read straight from the caller's
+ * slots) or a problem family whose kernel keeps scratch lines in global memory (steering-rate / state-box rows, horizons below
+ * 16); cold-started solves of the base row set overlap, which changes no result.  Inputs are read straight from the caller's
  * buffers when those are pinned (cudaHostAlloc / cudaHostRegister) and must then stay untouched until the matching wait; pageable
  * inputs are copied into the handle's own pinned staging before the call returns.  Results are identical to f110_cycle_host.
  * `gathered` (f110_cycle_wait): NULL, or — on the root of an attached gather ring — world x rows x 4 doubles. */
@@ -241,9 +241,10 @@ int f110_mpc_multi_uses_peer_stores(const f110_mpc_multi* m, int index);  /* 1: 
 int f110_mpc_multi_last_shard(const f110_mpc_multi* m, int index, int* first_qp, int* count);
 
 /* (2) one process per GPU (torchrun): a gather ring on the root rank's GPU, mapped into the other ranks through CUDA IPC.
- *     Layout: world flags (int32), then `slots` slots of world x rows_per_rank x 4 doubles.  Rank r's cycle number c lands in
- *     slot c % slots, block r; afterwards the rank raises flags[r] = c + 1 (f110_stream_signal) and the root's stream waits for
- *     every flag (f110_stream_wait_flags: a stream memory operation, no kernel spins) before it reads the slot.  No rank may be
+ *     Layout: slots x world flags (int32, padded to 256 bytes), then `slots` slots of world x rows_per_rank x 4 doubles.  Rank r's
+ *     cycle number c lands in slot c % slots, block r; afterwards the rank raises flags[c % slots][r] = c + 1 (f110_stream_signal)
+ *     and the root's stream waits for the slot's flags (f110_stream_wait_flags: a stream memory operation, no kernel spins) before
+ *     it reads the slot — cycles of one rank may therefore complete in any order.  No rank may be
  *     `slots` or more cycles ahead of the root's reads.  f110_gather_create zero-fills; the 64-byte handle goes to the peers by
  *     any host channel.  f110_cycle_set_gather attaches the ring to the asynchronous cycle entry (NULL detaches);
  *     f110_gather_slot + f110_mpc_set_packed_output do the same by hand for f110_mpc_solve_device. */
