@@ -777,7 +777,11 @@ def run_configs(args):
     report = {"gpu": torch.cuda.get_device_name(0), "host_threads": os.cpu_count(),
               "note": "CPU numbers: oracle/ (OSQP-algorithm restatement, not the OSQP binary). Parity UNPINNED by the reference."}
 
+    pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(PIPELINE_DEPTH)]
+
     def gpu_batch_time(N, recs, gap_mode=0, reps=10, rate_delta=None, **st):
+        """One batch per launch: median of `reps` launches timed alone (ms, solves_per_s), and the same batch launched 4 x reps times
+        over PIPELINE_DEPTH streams (pipelined_*: independent batches in flight, a batch's stragglers do not hold up the next)."""
         B = recs.shape[0]
         sol = M.MpcSolver(M.default_config(N, gap_mode, rate_delta), M.default_settings(warm_start=0, **st), max_batch=B)
         r = torch.from_numpy(np.ascontiguousarray(recs)).to(dev)
@@ -792,8 +796,40 @@ def run_configs(args):
             a.record(); sol.solve_device(r, None, None, u0, stt, it, ru, None, stream=stream); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         ms = float(np.median(ts))
-        return dict(ms=ms, solves_per_s=B / (ms * 1e-3), status=stt.cpu().numpy(), iters=it.cpu().numpy(), rho_updates=ru.cpu().numpy(),
-                    u0=u0.cpu().numpy())
+        res = dict(ms=ms, solves_per_s=B / (ms * 1e-3), status=stt.cpu().numpy(), iters=it.cpu().numpy(), rho_updates=ru.cpu().numpy(),
+                   u0=u0.cpu().numpy())
+        # pipelined: only for kernels that keep their working state on chip (launches of one handle then share nothing)
+        if rate_delta is None and 16 <= N <= 127:
+            po = [(torch.empty(B, 2, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                   torch.empty(B, dtype=torch.int32, device=dev)) for _ in pipe_streams]
+            n = 4 * reps
+            main = torch.cuda.current_stream()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(main)
+            for ps in pipe_streams:
+                ps.wait_event(a)
+            for i in range(n):
+                j = i % len(pipe_streams)
+                sol.solve_device(r, None, None, po[j][0], po[j][1], po[j][2], None, None, stream=pipe_streams[j].cuda_stream)
+            for ps in pipe_streams:
+                e = torch.cuda.Event(); e.record(ps); main.wait_event(e)
+            b.record(main); torch.cuda.synchronize()
+            res["pipelined_ms"] = a.elapsed_time(b) / n
+            res["pipelined_solves_per_s"] = B / (res["pipelined_ms"] * 1e-3)
+            res["pipelined_equal"] = bool((po[0][1].cpu().numpy() == res["status"]).all() and (po[0][2].cpu().numpy() == res["iters"]).all()
+                                          and np.array_equal(po[0][0].cpu().numpy(), res["u0"], equal_nan=True))
+        return res
+
+    def pipe(g):
+        return ({"gpu_ms_pipelined": g["pipelined_ms"], "gpu_solves_per_s_pipelined": g["pipelined_solves_per_s"],
+                 "pipelined_results_equal": g["pipelined_equal"]} if "pipelined_ms" in g else {})
+
+    def iter_hist(it):
+        edges = [0, 25, 50, 75, 100, 200, 400, 1000, 2000, 3999, 4000]
+        h = {}
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            h["%d..%d" % (lo + 1, hi)] = int(((it > lo) & (it <= hi)).sum())
+        return h
 
     def cpu_batch(N, recs, gap_mode=0, rate_delta=None, **st):
         mb = O.MpcBatch(O.default_cfg(N, gap_mode, rate_delta), O.default_settings(warm_start=0, **st), recs.shape[0])
@@ -883,7 +919,7 @@ def run_configs(args):
             recs = np.array(recs)
             g = gpu_batch_time(N_HORIZON, recs)
             o, thr = cpu_batch(N_HORIZON, recs)
-            c2[name]["qp_per_surviving_path"] = {"qps": len(recs), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"],
+            c2[name]["qp_per_surviving_path"] = {"qps": len(recs), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], **pipe(g),
                                                  "cpu_solves_per_s": len(recs) / o["seconds"], "cpu_threads": thr, "parity": parity(g, o, N_HORIZON)}
     report["config2_minipaths_grid_check"] = c2
 
@@ -905,15 +941,15 @@ def run_configs(args):
                         (2, "gap_enabled_k>=1 (stage-0 pair loose)")):
         g = gpu_batch_time(N_HORIZON, recs3, gap_mode=mode)
         o, thr = cpu_batch(N_HORIZON, recs3, gap_mode=mode)
-        c3[label] = {"gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B3 / o["seconds"], "cpu_threads": thr,
-                     "parity": parity(g, o, N_HORIZON), "status_hist": {str(k): int(v) for k, v in zip(*np.unique(g["status"], return_counts=True))}}
+        c3[label] = {"gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], **pipe(g), "cpu_solves_per_s": B3 / o["seconds"], "cpu_threads": thr,
+                     "parity": parity(g, o, N_HORIZON), "iters_hist": iter_hist(g["iters"]), "max_iters": int(g["iters"].max()), "status_hist": {str(k): int(v) for k, v in zip(*np.unique(g["status"], return_counts=True))}}
     report["config3_gap_constrained"] = c3
 
     # ---- config 4: 7 lanes x 20 paths x 64 scenarios = 8960 QPs (1 GPU here; bench.py --gpus N shards) ------------
     recs4 = config4_records(W, 64 if not args.quick else 8)
     g = gpu_batch_time(N_HORIZON, recs4)
     o, thr = cpu_batch(N_HORIZON, recs4)
-    report["config4_7lanes_20paths_64scenarios"] = {"qps": len(recs4), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"],
+    report["config4_7lanes_20paths_64scenarios"] = {"qps": len(recs4), "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], **pipe(g),
                                                     "cpu_solves_per_s": len(recs4) / o["seconds"], "cpu_threads": thr, "parity": parity(g, o, N_HORIZON)}
 
     # ---- config 5: horizon sweep, 4096 QPs per GPU ----------------------------------------------------------------------
@@ -925,7 +961,7 @@ def run_configs(args):
         g = gpu_batch_time(N, recs5)
         o, thr = cpu_batch(N, recs5)
         fl = float(flops_per_qp(N, g["iters"], g["rho_updates"]).sum())
-        c5["N=%d" % N] = {"qps": B5, "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], "cpu_solves_per_s": B5 / o["seconds"],
+        c5["N=%d" % N] = {"qps": B5, "gpu_ms": g["ms"], "gpu_solves_per_s": g["solves_per_s"], **pipe(g), "cpu_solves_per_s": B5 / o["seconds"],
                           "cpu_threads": thr, "speedup_vs_host": g["solves_per_s"] / (B5 / o["seconds"]), "mean_iters": float(g["iters"].mean()),
                           "algorithmic_tflops": fl / (g["ms"] * 1e-3) / 1e12, "fp64_roofline_frac": fl / (g["ms"] * 1e-3) / 1e12 / peak,
                           "parity": parity(g, o, N)}
@@ -975,6 +1011,30 @@ def run_configs(args):
     report["device_cycle"] = {"scenes": Sc, "kernels_per_cycle": sol.last_launches, "solved": n_solved, "device_ms": ms_dev,
                               "cars_per_s_device": Sc / (ms_dev * 1e-3), "e2e_ms (scan+pose H2D, u0 D2H)": ms_e2e,
                               "cars_per_s_e2e": Sc / (ms_e2e * 1e-3), "h2d_bytes": int(poses.nbytes + scans.nbytes)}
+    # ---- batched closed loop: cars x ticks of the reference's plan / control / drive state machine on the device,
+    # warm-started MPC cycle per car and tick, no host round trip inside the run ------------------------------------------------
+    fl = {}
+    for cars in ((12, 4096) if not args.quick else (12, 256)):
+        fsol = M.MpcSolver(M.default_config(N_HORIZON), M.default_settings(warm_start=1), max_batch=cars)
+        fleet = M.Fleet(fsol, M.default_cycle_config(qp_mode=0), cars, table, xy, drive_every=2, scan_every=4, dt_tick=0.01)
+        fp, fy, fs = W.scene_batch(cars, seed=20240908)
+        pose3 = np.stack([fp[:, 0], fp[:, 1], fy], axis=1)
+        ticks = 200 if not args.quick else 40
+        fleet.reset(pose3, fs)
+        fleet.run(20, log=False)
+        fleet.reset(pose3, fs)
+        t0 = time.perf_counter()
+        li, ld = fleet.run(ticks, log=True)
+        dt_run = time.perf_counter() - t0
+        ctrl = li[:, :, 0] == M.Fleet.CONTROL
+        fl["cars=%d" % cars] = {"ticks": ticks, "seconds": dt_run, "us_per_tick": dt_run / ticks * 1e6, "car_ticks_per_s": cars * ticks / dt_run,
+                                "mpc_cycles": int(ctrl.sum()), "mpc_cycles_per_s": float(ctrl.sum() / dt_run),
+                                "solved_fraction_of_mpc_cycles": float((li[:, :, 2][ctrl] == 1).mean()) if ctrl.any() else None,
+                                "mean_iters_of_mpc_cycles": float(li[:, :, 3][ctrl].mean()) if ctrl.any() else None,
+                                "launches_per_tick": fsol.last_launches / ticks if fsol.last_launches else None,
+                                "note": "host clock around f110_fleet_run incl. the device-to-host copy of the per-tick log"}
+        fleet.close()
+    report["fleet_closed_loop"] = fl
     out = args.configs_out or os.path.join(ROOT, "gpurun_out", "configs.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     json.dump(report, open(out, "w"), indent=1)

@@ -305,6 +305,7 @@ int f110_fleet_run(f110_fleet* f, int ticks, int32_t* log_i, double* log_d) {
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "f110_fleet_run: fleet kernels");
+    s->last_launches += 7 + scan_tick;   // begin, scene prep, collision, select, apply plan, records, end (+ the solve, counted above) + grid fill
   }
   if (log_i) {
     CUDA_TRY(cudaMemcpyAsync(log_i, f->d_log_i, (size_t)ticks * C * LOG_I * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
