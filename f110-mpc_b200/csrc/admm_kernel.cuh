@@ -70,7 +70,7 @@ bool admm_state_on_chip(int N, int rate_rows, int state_rows);
 cudaError_t launch_collision(int scenes, int paths, int samples, int blocks, float discrete, const float* grid,
                              const float* offset, const double* rot, const double* pose_xy,
                              const double* table_xy, uint8_t* valid, int32_t* free_count, float* end_world,
-                             cudaStream_t stream);
+                             cudaStream_t stream, const int32_t* scene_gate = nullptr, int gate_value = 0);   // gate: scenes with scene_gate[s] != gate_value are skipped
 
 // perception / planning kernels (pipeline_kernels.cu, compiled with -fmad=false)
 cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dilation, int n_beams, int num_scans, float angle_min,
@@ -78,7 +78,8 @@ cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dila
                               float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st,
                               int mode = 0);   // 0: everything, 1: no grid fill, 2: the grid fill only
 cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,
-                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st);
+                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st,
+                          const int32_t* scene_gate = nullptr, int gate_value = 0);
 cudaError_t launch_build_records(int scenes, int paths, int samples, int N, int stride, int qp_mode, double v_lin, const double* pose7,
                                  const double* rot, const uint8_t* valid, const int32_t* chosen, const double* table_xy,
                                  const double* prev_steer, const double* l1l2, double* recs, cudaStream_t st);

@@ -24,11 +24,14 @@ __global__ void __launch_bounds__(128) collision_kernel(int scenes, int paths, i
                                                         const float* __restrict__ grid, const float* __restrict__ offset,
                                                         const double* __restrict__ rot, const double* __restrict__ pose_xy,
                                                         const double* __restrict__ table_xy, uint8_t* __restrict__ valid,
-                                                        int32_t* __restrict__ free_count, float* __restrict__ end_world) {
+                                                        int32_t* __restrict__ free_count, float* __restrict__ end_world,
+                                                        const int32_t* __restrict__ scene_gate, int gate_value) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)scenes * paths) return;
   const int sc = (int)(wid / paths), pa = (int)(wid % paths);
+  // fleet loop: only the cars that plan on this tick need the check (project.cpp:73: OdomCallback plans when no path is held)
+  if (scene_gate && scene_gate[sc] != gate_value) return;
   const float* g = grid + (size_t)sc * blocks * blocks;
   const float offx = offset[2 * sc], offy = offset[2 * sc + 1];
   const double r00 = rot[4 * sc], r01 = rot[4 * sc + 1], r10 = rot[4 * sc + 2], r11 = rot[4 * sc + 3];
@@ -71,13 +74,14 @@ __global__ void __launch_bounds__(128) collision_kernel(int scenes, int paths, i
 
 cudaError_t launch_collision(int scenes, int paths, int samples, int blocks, float discrete, const float* grid,
                              const float* offset, const double* rot, const double* pose_xy, const double* table_xy,
-                             uint8_t* valid, int32_t* free_count, float* end_world, cudaStream_t stream) {
+                             uint8_t* valid, int32_t* free_count, float* end_world, cudaStream_t stream,
+                             const int32_t* scene_gate, int gate_value) {
   const long long warps = (long long)scenes * paths;
   if (warps == 0) return cudaSuccess;
   const int wpb = 4;
   const int grid_dim = (int)((warps + wpb - 1) / wpb);
   collision_kernel<<<grid_dim, 32 * wpb, 0, stream>>>(scenes, paths, samples, blocks, discrete, grid, offset, rot, pose_xy,
-                                                      table_xy, valid, free_count, end_world);
+                                                      table_xy, valid, free_count, end_world, scene_gate, gate_value);
   return cudaGetLastError();
 }
 

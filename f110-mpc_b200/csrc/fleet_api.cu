@@ -285,9 +285,9 @@ int f110_fleet_run(f110_fleet* f, int ticks, int32_t* log_i, double* log_d) {
                                             cc->angle_increment, cc->follow_gap_thresh, cc->fov_divider, cc->buffer, t.pose7, f->d_ranges,
                                             c.grid, c.offset, c.rot, c.pose_xy, c.l1l2, c.gap, st, 1);
     if (e == cudaSuccess) e = f110::launch_collision(C, f->paths, f->samples, blocks, cc->occ_discrete, c.grid, c.offset, c.rot, c.pose_xy,
-                                                     f->d_table, f->d_valid, c.free_cnt, c.endw, st);
+                                                     f->d_table, f->d_valid, c.free_cnt, c.endw, st, t.phase, PH_PLAN);
     if (e == cudaSuccess) e = f110::launch_select(C, f->paths, f->n_wp, cc->lookahead, t.pose7, f->d_wp, f->d_valid, c.endw, f->d_chosen,
-                                                  c.best_global, st);
+                                                  c.best_global, st, t.phase, PH_PLAN);
     if (e != cudaSuccess) return cuda_fail(e, "f110_fleet_run: planning kernels");
     fleet_apply_plan_kernel<<<(C + wpb - 1) / wpb, 32 * wpb, 0, st>>>(t, f->d_chosen, c.rot, f->d_table);
     fleet_records_kernel<<<(C + wpb - 1) / wpb, 32 * wpb, 0, st>>>(t, c.l1l2, c.recs);

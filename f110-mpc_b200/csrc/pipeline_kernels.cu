@@ -175,20 +175,23 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
                                                                   int32_t* __restrict__ gap, int mode) {
   // mode 0: everything;  1: no grid fill (rotation, pose, half-planes only: the grid of an earlier scan stays, as between two
   // ScanCallbacks of the reference, project.cpp:41-59);  2: the grid fill only
-  extern __shared__ unsigned char prep_sm[];   // blocks * blocks occupancy bytes, then 2 x words mask words
+  extern __shared__ __align__(16) unsigned char prep_sm[];   // blocks * blocks occupancy bytes, then 2 x words mask words
   const int sc = blockIdx.x;
   if (sc >= scenes) return;
   const int ncell = blocks * blocks;
   unsigned char* cells = prep_sm;
-  unsigned* masks = reinterpret_cast<unsigned*>(prep_sm + (ncell + 15) / 16 * 16);
-  for (int i = threadIdx.x; i < ncell; i += PREP_THREADS) cells[i] = 0;         // grid_ = Zero (occupancy_grid.cpp:57)
+  const int nthr = (int)blockDim.x;   // PREP_THREADS, or 32 when there is no grid to fill (mode 1: one warp per scene, all scenes resident at once)
+  const bool do_fill = mode != 1, do_rest = mode != 2;
+  unsigned* masks = reinterpret_cast<unsigned*>(prep_sm + (do_fill ? (ncell + 15) / 16 * 16 : 0));   // (no byte image without a fill)
+  // grid_ = Zero (occupancy_grid.cpp:57): the byte image is cleared a 32-bit word at a time (its allocation is rounded up to 16 bytes)
+  if (do_fill)
+    for (int i = threadIdx.x; i < (ncell + 3) / 4; i += nthr) reinterpret_cast<unsigned*>(cells)[i] = 0u;
   const double* p = pose7 + 7 * (size_t)sc;
   const double qz = p[5], qw = p[6];
   const float yaw = (float)atan2(2 * qw * qz, 1 - 2 * qz * qz);                 // :60, also Transforms::GetCarOrientation
   const float offx = (float)(p[0] + 0.275 * cosf_cr(yaw));                      // :63
   const float offy = (float)(p[1] + 0.275 * sinf_cr(yaw));                      // :64
   const float* r = ranges + (size_t)sc * n_beams;
-  const bool do_fill = mode != 1, do_rest = mode != 2;
   if (threadIdx.x == 0 && do_fill) { offset[2 * sc] = offx; offset[2 * sc + 1] = offy; }
   if (threadIdx.x == 0 && do_rest) {
     double q[4];
@@ -198,14 +201,14 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
     pose_xy[2 * sc] = p[0]; pose_xy[2 * sc + 1] = p[1];
   }
   __syncthreads();
-  const bool gap_warp = (l1l2 != nullptr) && (threadIdx.x >= PREP_THREADS - 32);
+  const bool gap_warp = (l1l2 != nullptr) && ((int)threadIdx.x >= nthr - 32);
   if (gap_warp) {
     if (do_rest)
     // State(pose.x, pose.y, float yaw) of project.cpp:163-164
     find_half_spaces_warp(threadIdx.x & 31, masks, masks + (n_beams + 31) / 32, n_beams, num_scans, angle_min, angle_inc, ftg_thresh,
                           divider, buffer, p[0], p[1], yaw, r, l1l2 + 6 * (size_t)sc, gap + 2 * (size_t)sc);
   } else if (do_fill) {
-    const int stampers = (l1l2 != nullptr) ? PREP_THREADS - 32 : PREP_THREADS;
+    const int stampers = (l1l2 != nullptr) ? nthr - 32 : nthr;
     const float half = (float)(blocks / 2);
     const int nb = num_scans < n_beams ? num_scans : n_beams;
     for (int ii = threadIdx.x; ii < nb; ii += stampers) {
@@ -222,7 +225,8 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
       float y_off = -dilation;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {                                             // :78
-        rows[t] = (y_off <= dilation) ? trunc_x86(((cy + y_off) - offy) / discrete + half) : -1;   // :31
+        rows[t] = -1;
+        if (y_off <= dilation) rows[t] = trunc_x86(((cy + y_off) - offy) / discrete + half);   // :31 (uniform branch: the offsets are launch constants)
         y_off += discrete;
       }
       for (float x_off = -dilation; x_off <= dilation; x_off += discrete) {     // :76
@@ -236,8 +240,19 @@ __global__ void __launch_bounds__(PREP_THREADS) scene_prep_kernel(int scenes, in
   }
   __syncthreads();
   if (!do_fill) return;
+  // write-out: HBM-bound (4 bytes per cell, 40 KB per scene).  Four cells per thread and store: one 32-bit read of the byte image,
+  // one 16-byte store, coalesced to 512 B per warp instruction.
   float* g = grid + (size_t)sc * ncell;
-  for (int i = threadIdx.x; i < ncell; i += PREP_THREADS) g[i] = cells[i] ? 1.f : 0.f;
+  if ((ncell & 3) == 0) {
+    float4* g4 = reinterpret_cast<float4*>(g);   // (cudaMalloc base, 4 * ncell bytes per scene: 16-byte aligned)
+    const unsigned* c4 = reinterpret_cast<const unsigned*>(cells);
+    for (int i = threadIdx.x; i < ncell / 4; i += nthr) {
+      const unsigned w = c4[i];
+      g4[i] = make_float4((w & 0xffu) ? 1.f : 0.f, (w & 0xff00u) ? 1.f : 0.f, (w & 0xff0000u) ? 1.f : 0.f, (w & 0xff000000u) ? 1.f : 0.f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < ncell; i += nthr) g[i] = cells[i] ? 1.f : 0.f;
+  }
 }
 
 // ---- look-ahead point and best surviving path: one warp per scene.  The lanes evaluate the per-waypoint
@@ -247,11 +262,13 @@ constexpr int SB_WARPS = 4;
 __global__ void __launch_bounds__(32 * SB_WARPS) select_kernel(int scenes, int paths, int n_wp, float lookahead,
                                                               const double* __restrict__ pose7, const float* __restrict__ wp_xy,
                                                               const uint8_t* __restrict__ valid, const float* __restrict__ end_world,
-                                                              int32_t* __restrict__ chosen, int32_t* __restrict__ best_global) {
+                                                              int32_t* __restrict__ chosen, int32_t* __restrict__ best_global,
+                                                              const int32_t* __restrict__ scene_gate, int gate_value) {
   extern __shared__ double off_sm[];  // SB_WARPS x n_wp look-ahead offsets (negative = waypoint behind the car)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sc = blockIdx.x * SB_WARPS + warp;
   if (sc >= scenes) return;
+  if (scene_gate && scene_gate[sc] != gate_value) return;   // fleet loop: only the cars that plan on this tick
   double* offs = off_sm + (size_t)warp * n_wp;
   const double* p = pose7 + 7 * (size_t)sc;
   // any valid path? (project.cpp:115-119)
@@ -387,16 +404,19 @@ cudaError_t launch_scene_prep(int scenes, int blocks, float discrete, float dila
                               float angle_inc, float thresh, float divider, float buffer, const double* pose7, const float* ranges,
                               float* grid, float* offset, double* rot, double* pose_xy, double* l1l2, int32_t* gap, cudaStream_t st, int mode) {
   if (scenes == 0) return cudaSuccess;
-  const size_t smem = (size_t)(blocks * blocks + 15) / 16 * 16 + 2 * (size_t)((n_beams + 31) / 32) * sizeof(unsigned);
-  scene_prep_kernel<<<scenes, PREP_THREADS, smem, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, thresh,
+  const size_t smem = (mode == 1 ? 0 : (size_t)(blocks * blocks + 15) / 16 * 16) + 2 * (size_t)((n_beams + 31) / 32) * sizeof(unsigned);
+  // without a grid to fill the only parallel work is the gap finder's warp: one-warp CTAs keep every scene resident at once (the
+  // run-length scan of a scene is one lane's serial work) and need no shared memory for the byte image
+  scene_prep_kernel<<<scenes, (mode == 1 && l1l2) ? 32 : PREP_THREADS, smem, st>>>(scenes, blocks, discrete, dilation, n_beams, num_scans, angle_min, angle_inc, thresh,
                                                         divider, buffer, pose7, ranges, grid, offset, rot, pose_xy, l1l2, gap, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_select(int scenes, int paths, int n_wp, float lookahead, const double* pose7, const float* wp_xy, const uint8_t* valid,
-                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st) {
+                          const float* end_world, int32_t* chosen, int32_t* best_global, cudaStream_t st, const int32_t* scene_gate,
+                          int gate_value) {
   if (scenes == 0) return cudaSuccess;
   select_kernel<<<(scenes + SB_WARPS - 1) / SB_WARPS, 32 * SB_WARPS, (size_t)SB_WARPS * n_wp * sizeof(double), st>>>(
-      scenes, paths, n_wp, lookahead, pose7, wp_xy, valid, end_world, chosen, best_global);
+      scenes, paths, n_wp, lookahead, pose7, wp_xy, valid, end_world, chosen, best_global, scene_gate, gate_value);
   return cudaGetLastError();
 }
 cudaError_t launch_build_records(int scenes, int paths, int samples, int N, int stride, int qp_mode, double v_lin, const double* pose7,
