@@ -87,7 +87,7 @@ def test_new_entry_points_check_their_arguments_without_a_gpu(pkg):
     import ctypes as C
     L = pkg.lib()
     n = C.c_size_t()
-    assert L.f110_gather_bytes(8, 4100, 64, C.byref(n)) == 0 and n.value == 256 + 64 * 8 * 4100 * 32
+    assert L.f110_gather_bytes(8, 4100, 64, C.byref(n)) == 0 and n.value == 64 * 8 * 4 + 64 * 8 * 4100 * 32   # slots x world flags (a multiple of 256 bytes here), then the rows
     assert L.f110_gather_bytes(0, 4100, 64, C.byref(n)) == 1 and L.f110_gather_bytes(8, 0, 64, C.byref(n)) == 1
     assert L.f110_gather_slot(None, 2, 0, 8, 4, 0, None, None) == 1
     assert L.f110_stream_signal(None, None, 1) == 1 and L.f110_stream_wait_flags(None, None, 2, 0, 1) == 1
