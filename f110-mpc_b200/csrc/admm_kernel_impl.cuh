@@ -47,6 +47,16 @@
 
 namespace f110 {
 
+// Persistent tensor-memory kernel: start the TMA bulk copy of one unit's records (QPW consecutive rows of the batch, fewer at the
+// batch's end) into a landing zone of p.tm_unit_doubles doubles whose last 16 bytes hold the zone's mbarrier.  One lane calls it.
+template <int QPW>
+__device__ __forceinline__ void tm_fetch_records(const KParams& p, double* dst, int unit) {
+  const int first = unit * QPW;
+  const int nq = (p.B - first < QPW) ? p.B - first : QPW;
+  bulk_copy_g2s(smem_u32(dst), p.recs + (size_t)first * p.stride, (uint32_t)((nq - 1) * p.stride * 8 + p.rec_bulk_bytes),
+                smem_u32(dst + p.tm_unit_doubles - 2));
+}
+
 // One unit of work = one QP on WPQ warps, one horizon stage per thread (stage k = tid) — or QPW short-horizon QPs side by side in one warp.
 // NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == lanes of the QP): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
@@ -61,8 +71,8 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM, bool SB
 __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
                                            const int tid, [[maybe_unused]] const uint32_t rec_parity, [[maybe_unused]] const int bar_id = 0) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
-  static_assert(!TM || QPW == 1, "tensor-memory variant: one QP per unit");
-  static_assert(!(TM && RATE) || WPQ == 1, "steering-rate rows in tensor memory: one warp per QP");
+  static_assert(!TM || QPW == 1 || (WPQ == 1 && !RATE), "tensor-memory variant with several QPs per warp: base row set only");
+  static_assert(!(TM && RATE) || WPQ <= 2, "steering-rate rows in tensor memory: one or two warps per QP");
   static_assert(!SBOX || (WPQ == 1 && QPW == 1 && !RATE && !TM), "state-box rows: one-warp shared-memory kernel, without steering-rate rows");
   constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
   constexpr int G = QPW == 1 ? T : 32 / QPW;   // lanes per QP
@@ -85,22 +95,23 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   constexpr int SM_PAIRS = NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
   constexpr int FINAL_PAIR = SM_PAIRS - 3;
   static_assert(!TM || RATE || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
-  // Steering-rate rows + tensor memory: the 16 pairs of each two-sided level live in the strip (4 x 16 pairs = all 256 columns at
-  // NLEV = 5); the one-sided top level (8 pairs) and the final inverse (5 pairs) stay in shared memory, re-based to index 0.
+  // Steering-rate rows + tensor memory: the 16 pairs of each of the first TML two-sided levels live in the strip (4 x 16 pairs = all
+  // 256 columns; NLEV = 5 has four such levels, NLEV = 6 five); what is left — a fifth two-sided level, the one-sided top level
+  // (8 pairs) and the final inverse (5 pairs) — stays in shared memory, re-based to index 0.
   // The scratch line stays in global memory for this variant: its spill traffic needs the L1 the shared memory would take.
-  static_assert(!(TM && RATE) || (NLEV - 1) * 64 <= TM_COLS, "two-sided levels exceed the warp's tensor-memory strip");
+  constexpr int TML = (TM && RATE) ? ((NLEV - 1) * 64 <= TM_COLS ? NLEV - 1 : TM_COLS / 64) : 0;   // two-sided levels in tensor memory
   constexpr bool SCR_SM = TM && !RATE;                            // scratch line in shared memory
-  constexpr int RT_SM0 = (TM && RATE) ? (NLEV - 1) * 16 : 0;       // first steering-rate pair that is NOT in tensor memory
+  constexpr int RT_SM0 = TML * 16;                                 // first steering-rate pair that is NOT in tensor memory
   [[maybe_unused]] double2* sm_pair = reinterpret_cast<double2*>(smem_all) + tid;
   [[maybe_unused]] double2* gl_pair = TOPG ? reinterpret_cast<double2*>(p.mult_global) + (size_t)unit * (GLP * T) + tid : nullptr;
   // steering-rate variant (4x4 blocks), same pair-major layout: 16 pairs per two-sided level, 8 for the one-sided top level,
   // 5 for the symmetric final inverse
-  constexpr int SM_DOUBLES = TM ? (RATE ? 26 : 0) : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
+  constexpr int SM_DOUBLES = TM ? (RATE ? (NLEV - 1 - TML) * 32 + 26 : 0) : (RATE ? (NLEV - 1) * 32 + 26 : 2 * SM_PAIRS);
   // (tensor-memory variant: the scratch line, when it lives in shared memory, comes first; the exchange buffers of a multi-warp QP follow)
   Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + ((TM && !RATE) ? SCR_ROWS_ALLOC * T : 0) + SM_DOUBLES * T, tid, bar_id);
   // scratch line: global memory (L2), or — tensor-memory variant — the shared memory the multipliers no longer occupy
   double* scr;
-  if constexpr (SCR_SM) scr = smem_all + k;
+  if constexpr (SCR_SM) scr = smem_all + tid;   // (one column per lane, whichever QP of the warp the lane works for)
   else scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(tid / G) * (SCR_ROWS_ALLOC * T)) + k;
 
   const int N = p.N;
@@ -114,16 +125,38 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 
   // ---------------- load the parameter record, linearise, stack -----------------------------------------
   const double* rec = p.recs + (size_t)qp * p.stride;
+  // persistent warp (tensor-memory variant, one warp per unit): the index of the warp's NEXT unit is fetched now and used by
+  // post_next() below, by which time the atomic has long returned (a plain atom: the compiler's warp-aggregated atomicAdd would
+  // read the result at once)
+  [[maybe_unused]] int next_unit = 0;
+  if constexpr (TM && WPQ == 1) {
+    // (increment written as 1 - tid, a per-thread operand: with a constant one ptxas rewrites the atomic into its warp-aggregated
+    //  form, whose leader-to-lanes shuffle reads the result at once)
+    int inc = 1 - tid;
+    asm volatile("" : "+r"(inc));
+    if (tid == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(next_unit) : "l"(p.work), "r"(inc) : "memory");
+  }
+  auto post_next = [&]() {
+    if constexpr (TM && WPQ == 1) {
+      if (tid == 0) {
+        double* const rec0 = smem_all + p.rec_smem_offset;
+        if (next_unit < (p.B + QPW - 1) / QPW && p.rec_bulk_bytes)
+          tm_fetch_records<QPW>(p, rec0 + ((rec_parity >> 1) ^ 1u) * p.tm_unit_doubles, next_unit);   // into the landing zone this unit does not use
+        *reinterpret_cast<volatile int*>(rec0 + 2 * p.tm_unit_doubles) = next_unit;
+      }
+    }
+  };
   if (p.rec_bulk_bytes) {
     // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
     // is a shared-memory read
     double* rec_sm = smem_all + p.rec_smem_offset;
     if constexpr (TM && WPQ == 1) {
-      // persistent warp: the mbarrier was initialised once by the caller, its phase alternates from QP to QP
-      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
-      if (k == 0) bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
-      mbar_wait(smem_u32(bar), rec_parity);
-      rec = rec_sm;
+      // persistent warp: two landing zones, each with its own mbarrier (initialised once by the caller).  The caller issued this
+      // record's copy while the previous QP was being solved; rec_parity = (zone << 1) | phase of the zone's barrier.
+      rec_sm += (rec_parity >> 1) * p.tm_unit_doubles;
+      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.tm_unit_doubles - 2);
+      mbar_wait(smem_u32(bar), rec_parity & 1u);
+      rec = rec_sm + (size_t)(qp - unit * QPW) * p.stride;   // (the unit's records are consecutive rows of the batch)
     } else if constexpr (QPW == 1) {
       uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
       if (k == 0) {
@@ -160,7 +193,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       if (p.rho_updates) p.rho_updates[qp] = 0;
       if (p.packed) { double* po = p.packed + 4 * (size_t)qp; po[0] = qn; po[1] = qn; po[2] = (double)ST_UNSOLVED; po[3] = 0.0; }
     }
-    if constexpr (QPW == 1) return;
+    if constexpr (QPW == 1) { post_next(); return; }
     done = true;   // the group idles (on NaN data, inside its own lanes) while its neighbours solve
   }
   Model md;
@@ -234,6 +267,11 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     double ag[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) ag[e] = fabs(s.gm[e]);
+    const double inv_nvar = 1.0 / (double)nvar;   // (one division per QP instead of one per pass: within an ulp of sum / nvar)
+    // Two passes per trip of the loop: the tail of a pass (the warp-wide sum and max behind the cost scale c) and the head of the next
+    // (neighbour exchange, every maximum that does not contain c) are independent, and only inside one basic block can the
+    // scheduler interleave them.  c enters each column norm last for the same reason (a maximum does not care about the order).
+#pragma unroll 2
     for (int it = 0; it < p.scaling; ++it) {
       double edn[3], dxp[3], dup[2];
       double ern = 0.0;   // scale of the next stage's rate row (RATE)
@@ -264,25 +302,24 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       [[maybe_unused]] double ts[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        double v = cQ[j] * dx[j];
-        v = dmax(v, ed[j]);
-        v = dmax(v, edn[j]);
+        double v = dmax(ed[j], edn[j]);
         v = dmax(v, dmax(eg[0] * ag[j], eg[1] * ag[3 + j]));
         if (j == 2) v = dmax(v, dmax(edn[0] * aA02, edn[1] * aA12));
         if constexpr (SBOX) {   // identity rows on x_k: one more entry in the column of x_k[j], a one-entry row
           v = dmax(v, es[j]);
           ts[j] = es[j] * dx[j];
         }
+        v = dmax(v, cQ[j] * dx[j]);
         tx[j] = v * dx[j];
       }
       {  // KKT columns of u_k = (v_k, delta_k): B has b00, b10, b20 in its first column, b21 in its second
-        double v = cR[0] * du[0];
-        v = dmax(v, dmax(edn[0] * aB[0], edn[1] * aB[2]));
-        v = dmax(v, dmax(edn[2] * aB[4], eb[0]));
+        double v = dmax(dmax(edn[0] * aB[0], edn[1] * aB[2]), dmax(edn[2] * aB[4], eb[0]));
+        v = dmax(v, cR[0] * du[0]);
         tu[0] = v * du[0];
-        v = dmax(cR[1] * du[1], dmax(edn[2] * aB[5], eb[1]));
+        v = dmax(edn[2] * aB[5], eb[1]);
         // steering-rate rows: column of delta_k has +1 in rate row k, -1 in rate row k+1
         if constexpr (RATE) v = dmax(v, dmax(er, ern));
+        v = dmax(v, cR[1] * du[1]);
         tu[1] = v * du[1];
       }
       double tr = 0.0;
@@ -320,16 +357,18 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         for (int j = 0; j < 3; ++j) es[j] *= rsqrt_scaling(limit_scaling(ts[j]));
       }
       // cost normalisation: c_temp = 1 / max(mean column norm of P, ||q||_inf)
-      double psum = 0.0, qn = 0.0;
-      if (act) {
+      double psum = 0.0, qn = 0.0;   // (selects, not branches: the pass stays one basic block)
+      {
+        double ps = 0.0, pu, qs = 0.0, qv = 0.0;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { psum = fma(cQ[j] * dx[j], dx[j], psum); qn = dmax(qn, fabs(dx[j] * s.qx[j])); }
-      }
-      if (actu) {
+        for (int j = 0; j < 3; ++j) { ps = fma(cQ[j] * dx[j], dx[j], ps); qs = dmax(qs, fabs(dx[j] * s.qx[j])); }
+        pu = ps;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { psum = fma(cR[j] * du[j], du[j], psum); qn = dmax(qn, fabs(du[j] * qu[j])); }
+        for (int j = 0; j < 2; ++j) { pu = fma(cR[j] * du[j], du[j], pu); qv = dmax(qv, fabs(du[j] * qu[j])); }
+        psum = actu ? pu : (act ? ps : 0.0);
+        qn = actu ? dmax(qs, qv) : (act ? qs : 0.0);
       }
-      const double mean = cm.rsum(psum) / (double)nvar;
+      const double mean = cm.rsum(psum) * inv_nvar;
       const double qinf = limit_scaling(c * cm.rmax(qn));
       const double ct = limit_scaling(dmax(mean, qinf));
       c *= rcp_pos(ct);
@@ -383,6 +422,8 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     scr[SCR_NQ * T] = cm.rmax(a);
     scr[SCR_SNQ * T] = c * cm.rmax(b);
   }
+
+  post_next();
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
 #pragma unroll
@@ -614,17 +655,17 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           const int h = 1 << lev;
           double lo[4], hi[4];
           cm.template both<4>(r, lo, hi, h);
-          [[maybe_unused]] const double2* cf = sm_pair + (lev * 16) * T;
+          [[maybe_unused]] const double2* cf = sm_pair + (lev * 16 - RT_SM0) * T;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             double2 c0, c1, c2, c3;
-            if constexpr (TM) {
+            if (TM && lev < TML) {   // (lev is a constant once the level loop is unrolled)
               // the row's four pairs were fetched from tensor memory while the previous row was applied; fetch the next row now
               tmem_wait_ld();
               tmem_tie<4>(mrow);
               c0 = mrow[0]; c1 = mrow[1]; c2 = mrow[2]; c3 = mrow[3];
               if (i < 3) tmem_ld_pairs<4>(tmb + 4 * (lev * 16 + 4 * (i + 1)), mrow);
-              else if (lev + 1 < NLEV - 1) tmem_ld_pairs<4>(tmb + 4 * ((lev + 1) * 16), mrow);
+              else if (lev + 1 < TML) tmem_ld_pairs<4>(tmb + 4 * ((lev + 1) * 16), mrow);
             } else {
               c0 = cf[(4 * i + 0) * T]; c1 = cf[(4 * i + 1) * T]; c2 = cf[(4 * i + 2) * T]; c3 = cf[(4 * i + 3) * T];
             }
@@ -734,28 +775,26 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             for (int j = 0; j < 9; ++j) mc[j] = nx[j];
           }
         }
-        {  // top level: single neighbour k ^ h
+        {  // top level (single neighbour k ^ h) and the final block inverse, fused:  x~ = B^-1 (r + C nb) = B^-1 r + (B^-1 C) nb.
+           // The factor step stores B^-1 C in the top level's slot, so B^-1 r is formed while the exchange is in flight and only a
+           // three-FMA chain per row follows it.
           constexpr int h = 1 << (NLEV - 1);
           double nb[3];
           cm.template xr<3>(r, nb, h);
-          double2 c0, c1, c2, c3, c4;
-          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; }
+          double2 c0, c1, c2, c3, c4, q0, q1, q2;
+          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
           else {
             const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
             c0 = cf[0 * T]; c1 = cf[1 * T]; c2 = cf[2 * T]; c3 = cf[3 * T]; c4 = cf[4 * T];
+            q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T];
           }
-          r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
-          r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
-          r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
-        }
-        {
-          double2 q0, q1, q2;
-          if constexpr (TM) { q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
-          else { q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T]; }
           const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
-          xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
-          xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
-          xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+          const double t0 = b0 * r[0] + b1 * r[1] + b2 * r[2];
+          const double t1 = b1 * r[0] + b4 * r[1] + b5 * r[2];
+          const double t2f = b2 * r[0] + b5 * r[1] + b8 * r[2];
+          xt[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], t0)));
+          xt[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], t1)));
+          xt[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], t2f)));
         }
         // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
         double axt[3], v[3], xn[3];
@@ -781,7 +820,6 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       for (int j = 0; j < 3; ++j) s.x[j] = al * xt[j] + oma * s.x[j];
 #pragma unroll
       for (int j = 0; j < 2; ++j) s.u[j] = al * ut[j] + oma * s.u[j];
-#pragma unroll
       if constexpr (FIRST) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {  // equality rows: the projection onto [l, u] = {b} is b itself
@@ -861,7 +899,6 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         }
         const double bv[3] = {md.b00, md.b10, md.b20};   // column of B that multiplies the speed
         double wv = p.R[0] + s.su[0] + s.rb[0];
-#pragma unroll
         double mv[3];   // R_{k+1} b_v
 #pragma unroll
         for (int i = 0; i < 3; ++i) { mv[i] = s.rdn[i] * bv[i]; wv += mv[i] * bv[i]; }
@@ -965,17 +1002,17 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           if (lev < NLEV - 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if constexpr (TM) {
+              if (TM && lev < TML) {
                 const uint32_t dst = tmb + 4 * (lev * 16 + 4 * i);
                 tmem_st_pair(dst, alp[4 * i], alp[4 * i + 1]);
                 tmem_st_pair(dst + 4, alp[4 * i + 2], alp[4 * i + 3]);
                 tmem_st_pair(dst + 8, gam[4 * i], gam[4 * i + 1]);
                 tmem_st_pair(dst + 12, gam[4 * i + 2], gam[4 * i + 3]);
-              } else {
-                sm_pair[(lev * 16 + 4 * i + 0) * T] = make_double2(alp[4 * i], alp[4 * i + 1]);
-                sm_pair[(lev * 16 + 4 * i + 1) * T] = make_double2(alp[4 * i + 2], alp[4 * i + 3]);
-                sm_pair[(lev * 16 + 4 * i + 2) * T] = make_double2(gam[4 * i], gam[4 * i + 1]);
-                sm_pair[(lev * 16 + 4 * i + 3) * T] = make_double2(gam[4 * i + 2], gam[4 * i + 3]);
+              } else if constexpr (!TM || TML < NLEV - 1) {
+                sm_pair[(lev * 16 + 4 * i + 0 - RT_SM0) * T] = make_double2(alp[4 * i], alp[4 * i + 1]);
+                sm_pair[(lev * 16 + 4 * i + 1 - RT_SM0) * T] = make_double2(alp[4 * i + 2], alp[4 * i + 3]);
+                sm_pair[(lev * 16 + 4 * i + 2 - RT_SM0) * T] = make_double2(gam[4 * i], gam[4 * i + 1]);
+                sm_pair[(lev * 16 + 4 * i + 3 - RT_SM0) * T] = make_double2(gam[4 * i + 2], gam[4 * i + 3]);
               }
             }
           } else {
@@ -1064,7 +1101,8 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             for (int e = 0; e < 9; ++e) { Bm[e] = (e % 4 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
           }
         }
-        // parallel cyclic reduction; multipliers alpha, gamma go to shared memory
+        // parallel cyclic reduction; multipliers alpha, gamma go to tensor memory / shared memory
+        double topc[9];   // the one-sided top level's block
 #pragma unroll 1
         for (int lev = 0; lev < NLEV; ++lev) {
           const int h = 1 << lev;
@@ -1131,21 +1169,24 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             }
           } else {
             // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
-            // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
-            double one[10];
+            // neighbour is stage k ^ h.  One 3x3 block (the non-zero one), kept until the final inverse is known.
 #pragma unroll
-            for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
-            one[9] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-              if constexpr (TM) tmem_st_pair(tmb + 4 * (lev * 9 + q), one[2 * q], one[2 * q + 1]);
-              else (TOPG ? gl_pair + GTOP * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
-            }
+            for (int e = 0; e < 9; ++e) topc[e] = alp[e] + gam[e];   // exactly one of them is non-zero
           }
         }
         {
           double Bi[9];
           inv_spd3(Bm, Bi);
+          {  // the iteration applies the top level and the final inverse in one step: store B^-1 C (5 pairs: 9 values + padding)
+            double one[10];
+            mm3(Bi, topc, one);
+            one[9] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              if constexpr (TM) tmem_st_pair(tmb + 4 * ((NLEV - 1) * 9 + q), one[2 * q], one[2 * q + 1]);
+              else (TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            }
+          }
           if constexpr (TM) {
             tmem_st_pair(tmb + 4 * (FINAL_PAIR + 0), Bi[0], Bi[1]);
             tmem_st_pair(tmb + 4 * (FINAL_PAIR + 1), Bi[2], Bi[4]);
@@ -1505,7 +1546,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE && !SBOX) ? ADMM_
 // in the warp's shared memory where the base variant keeps its scratch line; its scratch line stays in global memory.
 template <int RATE>
 __host__ __device__ constexpr int tm_warp_head() { return RATE ? 26 * 32 : SCR_ROWS_ALLOC * 32; }   // doubles at the head of a warp's shared-memory region
-template <int NLEV, bool LASTFULL, bool RATE = false>
+template <int NLEV, bool LASTFULL, bool RATE = false, int QPW = 1>
 __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
   __shared__ uint32_t tmem_base;
@@ -1515,18 +1556,35 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
-  double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2);
-  if (p.rec_bulk_bytes && lane == 0) mbar_init(smem_u32(smem_w + p.rec_smem_offset + p.rec_bulk_bytes / 8), 1);
+  const int zone = p.tm_unit_doubles;   // doubles per landing zone: the unit's records + the zone's mbarrier
+  const int nunits = (p.B + QPW - 1) / QPW;
+  double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + 2 * zone + 2);
+  double* const rec0 = smem_w + p.rec_smem_offset;
+  if (p.rec_bulk_bytes && lane == 0) {
+    mbar_init(smem_u32(rec0 + zone - 2), 1);
+    mbar_init(smem_u32(rec0 + 2 * zone - 2), 1);
+  }
   __syncwarp();
-  uint32_t parity = 0;
-  for (;;) {
-    int unit = 0;
-    if (lane == 0) unit = atomicAdd(p.work, 1);
-    unit = __shfl_sync(FULL, unit, 0);
-    if (unit >= p.B) break;
-    solve_unit<NLEV, 1, LASTFULL, RATE, 1, true>(p, unit, smem_w, tmb, lane, parity);
-    if (p.rec_bulk_bytes) parity ^= 1u;
-    __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
+  // The work queue runs one unit ahead of the solve (inside solve_unit): at the start of unit i lane 0 fetches the index of the
+  // warp's next unit from the counter, and once the Ruiz passes are done — the atomic's round trip long over — it starts the TMA
+  // bulk copy of that unit's records into the other landing zone and posts the index in the warp's shared-memory slot.  Neither
+  // the atomic nor the record's HBM latency sits between two solves.  A warp stops at its first index >= the number of units:
+  // exactly one such fetch per warp, which is what the re-arm below counts on.
+  int cur = 0;
+  if (lane == 0) {
+    cur = atomicAdd(p.work, 1);
+    if (cur < nunits && p.rec_bulk_bytes) tm_fetch_records<QPW>(p, rec0, cur);
+  }
+  cur = __shfl_sync(FULL, cur, 0);
+  const volatile int* next_slot = reinterpret_cast<const volatile int*>(rec0 + 2 * zone);
+  uint32_t z = 0, phase = 0;   // bit z of phase = parity of zone z's barrier
+  while (cur < nunits) {
+    solve_unit<NLEV, 1, LASTFULL, RATE, QPW, true>(p, cur, smem_w, tmb, lane, (z << 1) | ((phase >> z) & 1u));
+    phase ^= 1u << z;
+    z ^= 1u;
+    __syncwarp();   // every lane is done with the records and the scratch line before the next unit overwrites them; the slot is posted
+    cur = *next_slot;
+    __syncwarp();
   }
   // the last warp to run dry re-arms the counter pair for the next launch that uses it
   if (lane == 0) {
@@ -1542,7 +1600,7 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
 // side by side, or one four-warp QP), allocates 256 tensor-memory columns and keeps every PCR multiplier of its QPs there — the
 // shared-memory kernels of these horizons were bound by the multiplier loads (LSU data pipe 73-78 % busy).  Two QPs of one CTA
 // synchronise on their own hardware barriers (bar.sync 1 + q, 64).  The scratch line lives in shared memory.
-template <int NLEV, int WPQ, bool LASTFULL>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false>
 __global__ void __launch_bounds__(128, 2) admm_kernel_tmw(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
   __shared__ uint32_t tmem_base;
@@ -1555,17 +1613,20 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tmw(const KParams p) {
   const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
   const int q = (int)threadIdx.x / T, unit = (int)blockIdx.x * QPC + q;
   if (unit < p.B)
-    solve_unit<NLEV, WPQ, LASTFULL, false, 1, true>(p, unit, smem_all + (size_t)q * p.tm_unit_doubles, tmb, (int)threadIdx.x % T, 0u, QPC == 1 ? 0 : 1 + q);
+    solve_unit<NLEV, WPQ, LASTFULL, RATE, 1, true>(p, unit, smem_all + (size_t)q * p.tm_unit_doubles, tmb, (int)threadIdx.x % T, 0u, QPC == 1 ? 0 : 1 + q);
   tmem_fence_before_sync();
   __syncthreads();
   if (w == 0) tmem_free(tmem_base, TM_COLS);
 }
 
-template <int NLEV, int WPQ, bool LASTFULL>
+template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false>
 static cudaError_t launch_tmw(const KParams& pin, cudaStream_t stream) {
   constexpr int T = 32 * WPQ, QPC = 4 / WPQ;
   KParams p = pin;
-  size_t unit = (size_t)SCR_ROWS_ALLOC * T + Comm<WPQ, 32>::doubles();
+  // per QP: the scratch line — or, with steering-rate rows (scratch line in global memory), the multipliers that do not fit the
+  // tensor-memory strip: the two-sided levels beyond the fourth, the top level and the final inverse — then the exchange buffers
+  constexpr int RATE_SM_DOUBLES = ((NLEV - 1) * 64 <= TM_COLS ? 0 : NLEV - 1 - TM_COLS / 64) * 32 + 26;
+  size_t unit = (size_t)(RATE ? RATE_SM_DOUBLES : SCR_ROWS_ALLOC) * T + Comm<WPQ, 32>::doubles();
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
   p.rec_bulk_bytes = 0;
   unit = (unit + 1) & ~(size_t)1;
@@ -1576,9 +1637,9 @@ static cudaError_t launch_tmw(const KParams& pin, cudaStream_t stream) {
   }
   p.tm_unit_doubles = (int)unit;
   const size_t smem = unit * QPC * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(admm_kernel_tmw<NLEV, WPQ, LASTFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(admm_kernel_tmw<NLEV, WPQ, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  admm_kernel_tmw<NLEV, WPQ, LASTFULL><<<(p.B + QPC - 1) / QPC, 128, smem, stream>>>(p);
+  admm_kernel_tmw<NLEV, WPQ, LASTFULL, RATE><<<(p.B + QPC - 1) / QPC, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -1619,7 +1680,7 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
 
 // Launch of the tensor-memory variant: at most two CTAs per SM (they own the SM's 512 tensor-memory columns between them),
 // fewer when the batch has fewer than 8 QPs per SM.
-template <int NLEV, bool LASTFULL, bool RATE = false>
+template <int NLEV, bool LASTFULL, bool RATE = false, int QPW = 1>
 static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   KParams p = pin;
   if (!p.work) return cudaErrorInvalidValue;
@@ -1637,17 +1698,23 @@ static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
   p.rec_bulk_bytes = 0;
   p.rec_smem_offset = tm_warp_head<RATE>();
-  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) p.rec_bulk_bytes = rec_even * (int)sizeof(double);
-  const size_t smem = 4 * (size_t)(tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2) * sizeof(double);
-  static bool attr_set[64] = {false};   // (one flag array per instantiation of this template)
-  if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
+  p.tm_unit_doubles = 2;   // landing zone: the unit's QPW records (when they are staged by TMA) + the zone's mbarrier
+  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) {
+    p.rec_bulk_bytes = rec_even * (int)sizeof(double);
+    p.tm_unit_doubles = (QPW - 1) * p.stride + rec_even + 2;
   }
-  int grid = (p.B + 3) / 4;
+  const size_t smem = 4 * (size_t)(tm_warp_head<RATE>() + 2 * p.tm_unit_doubles + 2) * sizeof(double);   // per warp: head + two landing zones + the next-unit slot
+  static size_t attr_smem[64] = {0};   // (one array per instantiation of this template)
+  if (smem > attr_smem[dev]) {
+    const size_t want = smem > 64 * 1024 ? smem : 64 * 1024;
+    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL, RATE, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) return e;
+    attr_smem[dev] = want;
+  }
+  const int nunits = (p.B + QPW - 1) / QPW;
+  int grid = (nunits + 3) / 4;
   if (grid > 2 * sms_of[dev]) grid = 2 * sms_of[dev];
-  admm_kernel_tm<NLEV, LASTFULL, RATE><<<grid, 128, smem, stream>>>(p);
+  admm_kernel_tm<NLEV, LASTFULL, RATE, QPW><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
