@@ -15,7 +15,7 @@ cudaError_t launch_admm_w1s(const KParams& p, cudaStream_t stream, int nlev); //
 
 bool admm_state_on_chip(int N, int rate_rows, int state_rows) {
   static const bool no_tmem = [] { const char* e = std::getenv("F110_NO_TMEM"); return e && e[0] == '1'; }();
-  return !no_tmem && !rate_rows && !state_rows && N >= 1 && N <= 127;
+  return !no_tmem && !rate_rows && !state_rows && N >= 16 && N <= 127;
 }
 
 cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {

@@ -38,7 +38,7 @@ struct KParams {
   // TMA staging of the parameter record (set by the launcher): bytes of one bulk copy (0 = plain loads) and where the
   // record lands in dynamic shared memory (in doubles)
   int rec_bulk_bytes, rec_smem_offset;
-  int tm_unit_doubles;   // tensor-memory variants (set by the launcher): multi-warp QPs — shared-memory doubles per QP of a CTA; persistent one-warp kernel — doubles per record landing zone
+  int tm_unit_doubles;   // multi-warp tensor-memory variant: shared-memory doubles per QP of a CTA (set by the launcher)
   // buffers (device)
   const double* recs;
   double* x_out;      // [B][5N+3] or null

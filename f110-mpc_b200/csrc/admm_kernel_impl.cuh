@@ -47,16 +47,6 @@
 
 namespace f110 {
 
-// Persistent tensor-memory kernel: start the TMA bulk copy of one unit's records (QPW consecutive rows of the batch, fewer at the
-// batch's end) into a landing zone of p.tm_unit_doubles doubles whose last 16 bytes hold the zone's mbarrier.  One lane calls it.
-template <int QPW>
-__device__ __forceinline__ void tm_fetch_records(const KParams& p, double* dst, int unit) {
-  const int first = unit * QPW;
-  const int nq = (p.B - first < QPW) ? p.B - first : QPW;
-  bulk_copy_g2s(smem_u32(dst), p.recs + (size_t)first * p.stride, (uint32_t)((nq - 1) * p.stride * 8 + p.rec_bulk_bytes),
-                smem_u32(dst + p.tm_unit_doubles - 2));
-}
-
 // One unit of work = one QP on WPQ warps, one horizon stage per thread (stage k = tid) — or QPW short-horizon QPs side by side in one warp.
 // NLEV = number of PCR levels = floor(log2(N)) + 1;  LASTFULL = (N + 1 == lanes of the QP): the last thread is an active
 // stage, so the "successor" reads of the last stage wrap onto itself and need a mask.
@@ -71,7 +61,7 @@ template <int NLEV, int WPQ, bool LASTFULL, bool RATE, int QPW, bool TM, bool SB
 __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, double* const smem_all, [[maybe_unused]] const uint32_t tmb,
                                            const int tid, [[maybe_unused]] const uint32_t rec_parity, [[maybe_unused]] const int bar_id = 0) {
   static_assert(QPW == 1 || WPQ == 1, "several QPs per warp only for one-warp horizons");
-  static_assert(!TM || QPW == 1 || (WPQ == 1 && !RATE), "tensor-memory variant with several QPs per warp: base row set only");
+  static_assert(!TM || QPW == 1, "tensor-memory variant: one QP per unit (measured for 2 / 4 QPs per warp, horizons 1..15: 4-9 % slower than their shared-memory kernels)");
   static_assert(!(TM && RATE) || WPQ <= 2, "steering-rate rows in tensor memory: one or two warps per QP");
   static_assert(!SBOX || (WPQ == 1 && QPW == 1 && !RATE && !TM), "state-box rows: one-warp shared-memory kernel, without steering-rate rows");
   constexpr int T = 32 * WPQ;              // threads per unit = columns of the shared-memory and scratch layouts
@@ -111,7 +101,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   Comm<WPQ, QPW == 1 ? 32 : G> cm(smem_all + ((TM && !RATE) ? SCR_ROWS_ALLOC * T : 0) + SM_DOUBLES * T, tid, bar_id);
   // scratch line: global memory (L2), or — tensor-memory variant — the shared memory the multipliers no longer occupy
   double* scr;
-  if constexpr (SCR_SM) scr = smem_all + tid;   // (one column per lane, whichever QP of the warp the lane works for)
+  if constexpr (SCR_SM) scr = smem_all + k;
   else scr = (live ? p.scratch + (size_t)qp * (SCR_ROWS_ALLOC * T) : p.scratch_dummy + (size_t)(tid / G) * (SCR_ROWS_ALLOC * T)) + k;
 
   const int N = p.N;
@@ -125,38 +115,16 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 
   // ---------------- load the parameter record, linearise, stack -----------------------------------------
   const double* rec = p.recs + (size_t)qp * p.stride;
-  // persistent warp (tensor-memory variant, one warp per unit): the index of the warp's NEXT unit is fetched now and used by
-  // post_next() below, by which time the atomic has long returned (a plain atom: the compiler's warp-aggregated atomicAdd would
-  // read the result at once)
-  [[maybe_unused]] int next_unit = 0;
-  if constexpr (TM && WPQ == 1) {
-    // (increment written as 1 - tid, a per-thread operand: with a constant one ptxas rewrites the atomic into its warp-aggregated
-    //  form, whose leader-to-lanes shuffle reads the result at once)
-    int inc = 1 - tid;
-    asm volatile("" : "+r"(inc));
-    if (tid == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(next_unit) : "l"(p.work), "r"(inc) : "memory");
-  }
-  auto post_next = [&]() {
-    if constexpr (TM && WPQ == 1) {
-      if (tid == 0) {
-        double* const rec0 = smem_all + p.rec_smem_offset;
-        if (next_unit < (p.B + QPW - 1) / QPW && p.rec_bulk_bytes)
-          tm_fetch_records<QPW>(p, rec0 + ((rec_parity >> 1) ^ 1u) * p.tm_unit_doubles, next_unit);   // into the landing zone this unit does not use
-        *reinterpret_cast<volatile int*>(rec0 + 2 * p.tm_unit_doubles) = next_unit;
-      }
-    }
-  };
   if (p.rec_bulk_bytes) {
     // one TMA bulk copy of the whole record (host checked 16-byte alignment of base and stride), then every read below
     // is a shared-memory read
     double* rec_sm = smem_all + p.rec_smem_offset;
     if constexpr (TM && WPQ == 1) {
-      // persistent warp: two landing zones, each with its own mbarrier (initialised once by the caller).  The caller issued this
-      // record's copy while the previous QP was being solved; rec_parity = (zone << 1) | phase of the zone's barrier.
-      rec_sm += (rec_parity >> 1) * p.tm_unit_doubles;
-      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.tm_unit_doubles - 2);
-      mbar_wait(smem_u32(bar), rec_parity & 1u);
-      rec = rec_sm + (size_t)(qp - unit * QPW) * p.stride;   // (the unit's records are consecutive rows of the batch)
+      // persistent warp: the mbarrier was initialised once by the caller, its phase alternates from QP to QP
+      uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
+      if (k == 0) bulk_copy_g2s(smem_u32(rec_sm), rec, (uint32_t)p.rec_bulk_bytes, smem_u32(bar));
+      mbar_wait(smem_u32(bar), rec_parity);
+      rec = rec_sm;
     } else if constexpr (QPW == 1) {
       uint64_t* bar = reinterpret_cast<uint64_t*>(rec_sm + p.rec_bulk_bytes / 8);
       if (k == 0) {
@@ -193,7 +161,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       if (p.rho_updates) p.rho_updates[qp] = 0;
       if (p.packed) { double* po = p.packed + 4 * (size_t)qp; po[0] = qn; po[1] = qn; po[2] = (double)ST_UNSOLVED; po[3] = 0.0; }
     }
-    if constexpr (QPW == 1) { post_next(); return; }
+    if constexpr (QPW == 1) return;
     done = true;   // the group idles (on NaN data, inside its own lanes) while its neighbours solve
   }
   Model md;
@@ -271,7 +239,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     // Two passes per trip of the loop: the tail of a pass (the warp-wide sum and max behind the cost scale c) and the head of the next
     // (neighbour exchange, every maximum that does not contain c) are independent, and only inside one basic block can the
     // scheduler interleave them.  c enters each column norm last for the same reason (a maximum does not care about the order).
-#pragma unroll 2
+#pragma unroll(RATE ? 1 : 2)   // (the steering-rate kernels run at the register cap: the longer body costs them 2 %)
     for (int it = 0; it < p.scaling; ++it) {
       double edn[3], dxp[3], dup[2];
       double ern = 0.0;   // scale of the next stage's rate row (RATE)
@@ -422,8 +390,6 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     scr[SCR_NQ * T] = cm.rmax(a);
     scr[SCR_SNQ * T] = c * cm.rmax(b);
   }
-
-  post_next();
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
 #pragma unroll
@@ -775,26 +741,28 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             for (int j = 0; j < 9; ++j) mc[j] = nx[j];
           }
         }
-        {  // top level (single neighbour k ^ h) and the final block inverse, fused:  x~ = B^-1 (r + C nb) = B^-1 r + (B^-1 C) nb.
-           // The factor step stores B^-1 C in the top level's slot, so B^-1 r is formed while the exchange is in flight and only a
-           // three-FMA chain per row follows it.
+        {  // top level: single neighbour k ^ h
           constexpr int h = 1 << (NLEV - 1);
           double nb[3];
           cm.template xr<3>(r, nb, h);
-          double2 c0, c1, c2, c3, c4, q0, q1, q2;
-          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
+          double2 c0, c1, c2, c3, c4;
+          if constexpr (TM) { c0 = mc[0]; c1 = mc[1]; c2 = mc[2]; c3 = mc[3]; c4 = mc[4]; }
           else {
             const double2* cf = TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T;
             c0 = cf[0 * T]; c1 = cf[1 * T]; c2 = cf[2 * T]; c3 = cf[3 * T]; c4 = cf[4 * T];
-            q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T];
           }
+          r[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], r[0])));
+          r[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], r[1])));
+          r[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], r[2])));
+        }
+        {
+          double2 q0, q1, q2;
+          if constexpr (TM) { q0 = mc[5]; q1 = mc[6]; q2 = mc[7]; }
+          else { q0 = sm_pair[(FINAL_PAIR + 0) * T]; q1 = sm_pair[(FINAL_PAIR + 1) * T]; q2 = sm_pair[(FINAL_PAIR + 2) * T]; }
           const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b4 = q1.y, b5 = q2.x, b8 = q2.y;
-          const double t0 = b0 * r[0] + b1 * r[1] + b2 * r[2];
-          const double t1 = b1 * r[0] + b4 * r[1] + b5 * r[2];
-          const double t2f = b2 * r[0] + b5 * r[1] + b8 * r[2];
-          xt[0] = fma(c1.x, nb[2], fma(c0.y, nb[1], fma(c0.x, nb[0], t0)));
-          xt[1] = fma(c2.y, nb[2], fma(c2.x, nb[1], fma(c1.y, nb[0], t1)));
-          xt[2] = fma(c4.x, nb[2], fma(c3.y, nb[1], fma(c3.x, nb[0], t2f)));
+          xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
+          xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
+          xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
         }
         // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
         double axt[3], v[3], xn[3];
@@ -1102,7 +1070,6 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           }
         }
         // parallel cyclic reduction; multipliers alpha, gamma go to tensor memory / shared memory
-        double topc[9];   // the one-sided top level's block
 #pragma unroll 1
         for (int lev = 0; lev < NLEV; ++lev) {
           const int h = 1 << lev;
@@ -1169,24 +1136,21 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             }
           } else {
             // top level: h = 2^(NLEV-1) > N/2, so a stage has its k-h or its k+h neighbour, never both, and that
-            // neighbour is stage k ^ h.  One 3x3 block (the non-zero one), kept until the final inverse is known.
+            // neighbour is stage k ^ h.  One 3x3 block (the non-zero one) + padding: 5 pairs.
+            double one[10];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) topc[e] = alp[e] + gam[e];   // exactly one of them is non-zero
+            for (int e = 0; e < 9; ++e) one[e] = alp[e] + gam[e];   // exactly one of them is non-zero
+            one[9] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              if constexpr (TM) tmem_st_pair(tmb + 4 * (lev * 9 + q), one[2 * q], one[2 * q + 1]);
+              else (TOPG ? gl_pair + GTOP * T : sm_pair + (lev * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
+            }
           }
         }
         {
           double Bi[9];
           inv_spd3(Bm, Bi);
-          {  // the iteration applies the top level and the final inverse in one step: store B^-1 C (5 pairs: 9 values + padding)
-            double one[10];
-            mm3(Bi, topc, one);
-            one[9] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-              if constexpr (TM) tmem_st_pair(tmb + 4 * ((NLEV - 1) * 9 + q), one[2 * q], one[2 * q + 1]);
-              else (TOPG ? gl_pair + GTOP * T : sm_pair + ((NLEV - 1) * 9) * T)[q * T] = make_double2(one[2 * q], one[2 * q + 1]);
-            }
-          }
           if constexpr (TM) {
             tmem_st_pair(tmb + 4 * (FINAL_PAIR + 0), Bi[0], Bi[1]);
             tmem_st_pair(tmb + 4 * (FINAL_PAIR + 1), Bi[2], Bi[4]);
@@ -1546,7 +1510,7 @@ __global__ void __launch_bounds__(32 * WPQ, (WPQ == 1 && !RATE && !SBOX) ? ADMM_
 // in the warp's shared memory where the base variant keeps its scratch line; its scratch line stays in global memory.
 template <int RATE>
 __host__ __device__ constexpr int tm_warp_head() { return RATE ? 26 * 32 : SCR_ROWS_ALLOC * 32; }   // doubles at the head of a warp's shared-memory region
-template <int NLEV, bool LASTFULL, bool RATE = false, int QPW = 1>
+template <int NLEV, bool LASTFULL, bool RATE = false>
 __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
   __shared__ uint32_t tmem_base;
@@ -1556,35 +1520,22 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tmb = tmem_base + ((uint32_t)(32 * w) << 16);
-  const int zone = p.tm_unit_doubles;   // doubles per landing zone: the unit's records + the zone's mbarrier
-  const int nunits = (p.B + QPW - 1) / QPW;
-  double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + 2 * zone + 2);
-  double* const rec0 = smem_w + p.rec_smem_offset;
-  if (p.rec_bulk_bytes && lane == 0) {
-    mbar_init(smem_u32(rec0 + zone - 2), 1);
-    mbar_init(smem_u32(rec0 + 2 * zone - 2), 1);
-  }
+  double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2);
+  if (p.rec_bulk_bytes && lane == 0) mbar_init(smem_u32(smem_w + p.rec_smem_offset + p.rec_bulk_bytes / 8), 1);
   __syncwarp();
-  // The work queue runs one unit ahead of the solve (inside solve_unit): at the start of unit i lane 0 fetches the index of the
-  // warp's next unit from the counter, and once the Ruiz passes are done — the atomic's round trip long over — it starts the TMA
-  // bulk copy of that unit's records into the other landing zone and posts the index in the warp's shared-memory slot.  Neither
-  // the atomic nor the record's HBM latency sits between two solves.  A warp stops at its first index >= the number of units:
-  // exactly one such fetch per warp, which is what the re-arm below counts on.
-  int cur = 0;
-  if (lane == 0) {
-    cur = atomicAdd(p.work, 1);
-    if (cur < nunits && p.rec_bulk_bytes) tm_fetch_records<QPW>(p, rec0, cur);
-  }
-  cur = __shfl_sync(FULL, cur, 0);
-  const volatile int* next_slot = reinterpret_cast<const volatile int*>(rec0 + 2 * zone);
-  uint32_t z = 0, phase = 0;   // bit z of phase = parity of zone z's barrier
-  while (cur < nunits) {
-    solve_unit<NLEV, 1, LASTFULL, RATE, QPW, true>(p, cur, smem_w, tmb, lane, (z << 1) | ((phase >> z) & 1u));
-    phase ^= 1u << z;
-    z ^= 1u;
-    __syncwarp();   // every lane is done with the records and the scratch line before the next unit overwrites them; the slot is posted
-    cur = *next_slot;
-    __syncwarp();
+  // QPs are claimed one at a time, when the warp is free to solve them.  (Claiming the next QP while the current one is being
+  // solved — to have its record in flight early — was measured: the one-QP lookahead costs more in load balance at the batch's
+  // tail than the hidden atomic + record latency gains, 0.230 vs 0.227 ms per 4096 QPs, and far more on batches under two QPs
+  // per warp.)
+  uint32_t parity = 0;
+  for (;;) {
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(p.work, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= p.B) break;
+    solve_unit<NLEV, 1, LASTFULL, RATE, 1, true>(p, unit, smem_w, tmb, lane, parity);
+    if (p.rec_bulk_bytes) parity ^= 1u;
+    __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
   }
   // the last warp to run dry re-arms the counter pair for the next launch that uses it
   if (lane == 0) {
@@ -1680,7 +1631,7 @@ static cudaError_t launch_one(const KParams& pin, cudaStream_t stream) {
 
 // Launch of the tensor-memory variant: at most two CTAs per SM (they own the SM's 512 tensor-memory columns between them),
 // fewer when the batch has fewer than 8 QPs per SM.
-template <int NLEV, bool LASTFULL, bool RATE = false, int QPW = 1>
+template <int NLEV, bool LASTFULL, bool RATE = false>
 static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   KParams p = pin;
   if (!p.work) return cudaErrorInvalidValue;
@@ -1698,23 +1649,17 @@ static cudaError_t launch_tm(const KParams& pin, cudaStream_t stream) {
   const int rec_even = (11 + 3 * p.N + 1) & ~1;
   p.rec_bulk_bytes = 0;
   p.rec_smem_offset = tm_warp_head<RATE>();
-  p.tm_unit_doubles = 2;   // landing zone: the unit's QPW records (when they are staged by TMA) + the zone's mbarrier
-  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) {
-    p.rec_bulk_bytes = rec_even * (int)sizeof(double);
-    p.tm_unit_doubles = (QPW - 1) * p.stride + rec_even + 2;
-  }
-  const size_t smem = 4 * (size_t)(tm_warp_head<RATE>() + 2 * p.tm_unit_doubles + 2) * sizeof(double);   // per warp: head + two landing zones + the next-unit slot
-  static size_t attr_smem[64] = {0};   // (one array per instantiation of this template)
-  if (smem > attr_smem[dev]) {
-    const size_t want = smem > 64 * 1024 ? smem : 64 * 1024;
-    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL, RATE, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+  if (reinterpret_cast<uintptr_t>(p.recs) % 16 == 0 && p.stride % 2 == 0 && p.stride >= rec_even) p.rec_bulk_bytes = rec_even * (int)sizeof(double);
+  const size_t smem = 4 * (size_t)(tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2) * sizeof(double);
+  static bool attr_set[64] = {false};   // (one flag array per instantiation of this template)
+  if (!attr_set[dev]) {
+    e = cudaFuncSetAttribute(admm_kernel_tm<NLEV, LASTFULL, RATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    attr_smem[dev] = want;
+    attr_set[dev] = true;
   }
-  const int nunits = (p.B + QPW - 1) / QPW;
-  int grid = (nunits + 3) / 4;
+  int grid = (p.B + 3) / 4;
   if (grid > 2 * sms_of[dev]) grid = 2 * sms_of[dev];
-  admm_kernel_tm<NLEV, LASTFULL, RATE, QPW><<<grid, 128, smem, stream>>>(p);
+  admm_kernel_tm<NLEV, LASTFULL, RATE><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
