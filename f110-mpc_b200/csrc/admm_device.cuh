@@ -215,15 +215,29 @@ struct Comm {
   static constexpr int KMAX = (WPQ == 4 || ADMM_W2_GLOBAL_LEVELS > 0) ? 5 : 9;   // values per exchange; with four warps the 9-wide ones (factor step only) go in two rounds to save shared memory
   double* xb;   // [2][KMAX][T] exchange buffers
   double* rb;   // [2][WPQ] reduction slots
-  int tid, xph = 0, rph = 0;
+  double* bb;   // [2][2][4] boundary slots (two-warp QPs, partitioned solve)
+  int tid, xph = 0, rph = 0, bph = 0;
   int bar;      // hardware barrier of this QP's T threads: 0 when the QP is the whole CTA, 1 + q when several QPs share a CTA
-  __device__ __forceinline__ Comm(double* smem, int t, int bar_id = 0) : xb(smem), rb(smem + 2 * KMAX * T), tid(t), bar(bar_id) {}
+  __device__ __forceinline__ Comm(double* smem, int t, int bar_id = 0)
+      : xb(smem), rb(smem + 2 * KMAX * T), bb(smem + 2 * KMAX * T + 2 * WPQ), tid(t), bar(bar_id) {}
   __device__ __forceinline__ void barrier() const {   // immediate barrier numbers: a register operand would make ptxas reserve all 16
     if (bar == 0) asm volatile("bar.sync 0, %0;" ::"n"(T) : "memory");
     else if (bar == 1) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
     else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
   }
-  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ; }
+  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ + 16; }
+  // Two-warp QP, partitioned solve: the last stage of warp 0 (thread 31) and the first stage of warp 1 (thread 32) post a 3-vector;
+  // every thread gets its own warp's (`own`) and the other warp's (`other`).  Double-buffered like the exchanges above.
+  __device__ __forceinline__ void boundary(const double* v, double* own, double* other) {
+    static_assert(WPQ == 2, "boundary slots: two warps per QP");
+    double* b = bb + bph * 8;
+    bph ^= 1;
+    const int w = tid >> 5;
+    if (tid == 31 || tid == 32) { b[4 * w] = v[0]; b[4 * w + 1] = v[1]; b[4 * w + 2] = v[2]; }
+    barrier();
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { own[i] = b[4 * w + i]; other[i] = b[4 * (w ^ 1) + i]; }
+  }
   template <int K> __device__ __forceinline__ double* put(const double* v) {
     static_assert(K <= KMAX, "exchange wider than the buffer");
     double* b = xb + xph * KMAX * T;

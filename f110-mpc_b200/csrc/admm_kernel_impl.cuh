@@ -82,8 +82,17 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   constexpr bool TOPG = GL > 0;
   constexpr int GLP = GL == 2 ? 14 : 5;            // pairs per stage in the global line
   constexpr int GTOP = GL == 2 ? 9 : 0;            // where the top level starts in it
-  constexpr int SM_PAIRS = NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
-  constexpr int FINAL_PAIR = SM_PAIRS - 3;
+  // PART: the partitioned solve of a two-warp QP (tensor-memory variant, base row set).  Each warp runs the cyclic reduction on its
+  // own 32 stages with shuffles only (NLEVP = 5 levels, no barrier); the coupling block between stage 31 and stage 32 enters as a
+  // "spike": with V = T_own^-1 [coupling columns] (three PCR applications per factor step), the true solution is
+  //     x_k = y_k + WT_k y_other + WO_k y_own,    y = T_own^-1 r,   y_own / y_other = y at this / the other warp's boundary stage,
+  // where the per-stage 3x3 blocks WT = -V_k S, WO = -WT V_other, S = (I - V_other V_own)^-1 are formed once per factor step.
+  // One exchange of six doubles (one barrier) per iteration replaces the six barrier-separated exchanges of a 64-lane reduction.
+  constexpr bool PART = TM && WPQ == 2 && !RATE;
+  constexpr int NLEVP = PART ? 5 : NLEV;   // levels of the reduction that is actually run
+  constexpr int SM_PAIRS = PART ? NLEVP * 9 - 1 + 9 : NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
+  constexpr int FINAL_PAIR = PART ? NLEVP * 9 - 4 : SM_PAIRS - 3;
+  constexpr int W_PAIR = NLEVP * 9 - 1;   // (PART) the nine pairs of WT, WO
   static_assert(!TM || RATE || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
   // Steering-rate rows + tensor memory: the 16 pairs of each of the first TML two-sided levels live in the strip (4 x 16 pairs = all
   // 256 columns; NLEV = 5 has four such levels, NLEV = 6 five); what is left — a fifth two-sided level, the one-sided top level
@@ -563,6 +572,50 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   // ---------- one ADMM iteration (OSQP update_xz_tilde / update_x / update_z / update_y) ---------------------
   // A solve's FIRST iteration is its own instantiation: it alone sees a z on the dynamics rows that is not their right-hand side
   // (0 on a cold start, the slot's value on a warm start; read from the scratch line).  Every later iteration uses z = b.
+  // ---------- (partitioned solve) y = T_own^-1 r by cyclic reduction inside the warp; mc = level 0's multipliers, load already issued ---
+  [[maybe_unused]] Comm<1, 32> cw(nullptr, tid & 31);
+  [[maybe_unused]] auto pcr_own = [&](double2 (&mc)[9], double (&r)[3], double (&y)[3]) {
+    if constexpr (PART) {
+      tmem_wait_ld();
+      tmem_tie<9>(mc);
+#pragma unroll
+      for (int lev = 0; lev < NLEVP - 1; ++lev) {
+        const int h = 1 << lev;
+        double lo[3], hi[3];
+        double2 nx[9];
+        if (lev + 1 < NLEVP - 1) tmem_ld_pairs<9>(tmb + 36 * (lev + 1), nx);
+        else { tmem_ld_pairs<8>(tmb + 36 * (NLEVP - 1), nx); nx[8] = make_double2(0.0, 0.0); }
+        cw.template both<3>(r, lo, hi, h);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double2 c0 = mc[3 * i], c1 = mc[3 * i + 1], c2 = mc[3 * i + 2];
+          double a = fma(c0.x, lo[0], r[i]);
+          a = fma(c1.y, hi[0], a);
+          a = fma(c0.y, lo[1], a);
+          a = fma(c2.x, hi[1], a);
+          a = fma(c1.x, lo[2], a);
+          r[i] = fma(c2.y, hi[2], a);
+        }
+        tmem_wait_ld();
+        tmem_tie<9>(nx);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) mc[j] = nx[j];
+      }
+      {  // top level: single neighbour lane ^ 16
+        constexpr int h = 1 << (NLEVP - 1);
+        double nb[3];
+        cw.template xr<3>(r, nb, h);
+        r[0] = fma(mc[1].x, nb[2], fma(mc[0].y, nb[1], fma(mc[0].x, nb[0], r[0])));
+        r[1] = fma(mc[2].y, nb[2], fma(mc[2].x, nb[1], fma(mc[1].y, nb[0], r[1])));
+        r[2] = fma(mc[4].x, nb[2], fma(mc[3].y, nb[1], fma(mc[3].x, nb[0], r[2])));
+      }
+      const double b0 = mc[5].x, b1 = mc[5].y, b2 = mc[6].x, b4 = mc[6].y, b5 = mc[7].x, b8 = mc[7].y;
+      y[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
+      y[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
+      y[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+    }
+  };
+
   auto iterate = [&](auto first_c) {
     constexpr bool FIRST = decltype(first_c)::value;
       // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
@@ -709,6 +762,23 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         cm.template up<3>(f, fp, 1);
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = fma(hm, fp[i], gx[i] - t3[i]);   // + fp from the predecessor, if there is one
+        if constexpr (PART) {
+          // own-block solve, then the spike correction from the two boundary values (posted in the QP's exchange slots)
+          double y[3];
+          pcr_own(mc, r, y);
+          double2 wv[9];
+          tmem_ld_pairs<9>(tmb + 4 * W_PAIR, wv);
+          double yo[3], yt[3];
+          cm.boundary(y, yo, yt);
+          tmem_wait_ld();
+          tmem_tie<9>(wv);
+          const double wt[9] = {wv[0].x, wv[0].y, wv[1].x, wv[1].y, wv[2].x, wv[2].y, wv[3].x, wv[3].y, wv[4].x};
+          const double wo[9] = {wv[4].y, wv[5].x, wv[5].y, wv[6].x, wv[6].y, wv[7].x, wv[7].y, wv[8].x, wv[8].y};
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            xt[i] = fma(wo[3 * i + 2], yo[2], fma(wt[3 * i + 2], yt[2], fma(wo[3 * i + 1], yo[1], fma(wt[3 * i + 1], yt[1],
+                    fma(wo[3 * i], yo[0], fma(wt[3 * i], yt[0], y[i]))))));
+        } else {
         // PCR: apply the stored multipliers level by level (fully unrolled, constant offsets)
         if constexpr (TM) { tmem_wait_ld(); tmem_tie<9>(mc); }
 #pragma unroll
@@ -763,6 +833,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           xt[0] = b0 * r[0] + b1 * r[1] + b2 * r[2];
           xt[1] = b1 * r[0] + b4 * r[1] + b5 * r[2];
           xt[2] = b2 * r[0] + b5 * r[1] + b8 * r[2];
+        }
         }
         // recover u~_k = h - W^-1 B' R_{k+1} (A x~_k - x~_{k+1})   (rdn = 0 on the last stage)
         double axt[3], v[3], xn[3];
@@ -1069,12 +1140,28 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             for (int e = 0; e < 9; ++e) { Bm[e] = (e % 4 == 0) ? 1.0 : 0.0; Lm[e] = 0.0; Um[e] = 0.0; }
           }
         }
+        // (partitioned solve) the block that couples the two warps leaves the reduction and becomes the spike's right-hand side:
+        // U_31 on stage 31, L_32 on stage 32
+        [[maybe_unused]] double cpl[9];
+        if constexpr (PART) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) {
+            cpl[e] = (tid == 31) ? Um[e] : ((tid == 32) ? Lm[e] : 0.0);
+            Um[e] = (tid == 31) ? 0.0 : Um[e];
+            Lm[e] = (tid == 32) ? 0.0 : Lm[e];
+          }
+        }
+        const int kq = PART ? (tid & 31) : k;   // stage index inside the system that is reduced
+        auto both9 = [&](const double* v, double* lo, double* hi, int h) {
+          if constexpr (PART) cw.template both<9>(v, lo, hi, h);
+          else cm.template both<9>(v, lo, hi, h);
+        };
         // parallel cyclic reduction; multipliers alpha, gamma go to tensor memory / shared memory
 #pragma unroll 1
-        for (int lev = 0; lev < NLEV; ++lev) {
+        for (int lev = 0; lev < NLEVP; ++lev) {
           const int h = 1 << lev;
-          const bool vlo = act && (k - h >= 0);
-          const bool vhi = act && (k + h <= N);
+          const bool vlo = act && (kq - h >= 0);
+          const bool vhi = act && (k + h <= N) && (!PART || kq + h <= 31);
           // alpha = L_k B_{k-h}^-1, gamma = U_k B_{k+h}^-1; the reduced blocks follow from them and the neighbours' L, U:
           //   B_k -= alpha U_{k-h} + gamma L_{k+h},   L_k <- -alpha L_{k-h},   U_k <- -gamma U_{k+h}      (6 products per level)
           // (ordered so that few temporaries are alive at once: the register peak of this rare step decides what the hot loop spills)
@@ -1082,7 +1169,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           {
             double Bi[9];
             inv_spd3(Bm, Bi);
-            cm.template both<9>(Bi, nlo, nhi, h);
+            both9(Bi, nlo, nhi, h);
           }
           mm3(Lm, nlo, alp);
           mm3(Um, nhi, gam);
@@ -1091,7 +1178,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             alp[e] = vlo ? alp[e] : 0.0;
             gam[e] = vhi ? gam[e] : 0.0;
           }
-          cm.template both<9>(Um, nlo, nhi, h);
+          both9(Um, nlo, nhi, h);
           {
             double t1[9];
             mm3(alp, nlo, t1);
@@ -1100,7 +1187,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           }
           double Un[9];
           mm3(gam, nhi, Un);
-          cm.template both<9>(Lm, nlo, nhi, h);
+          both9(Lm, nlo, nhi, h);
           {
             double t2[9];
             mm3(gam, nhi, t2);
@@ -1118,7 +1205,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             alp[e] = -alp[e];   // stored negated: the solve is r += coef * neighbour
             gam[e] = -gam[e];
           }
-          if (lev < NLEV - 1) {
+          if (lev < NLEVP - 1) {
             // 9 pairs per level, each pair one 16-byte word per stage: (a0,a1) (a2,g0) (g1,g2) per row
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -1160,6 +1247,45 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             sm_pair[(FINAL_PAIR + 1) * T] = make_double2(Bi[2], Bi[4]);
             sm_pair[(FINAL_PAIR + 2) * T] = make_double2(Bi[5], Bi[8]);
           }
+        }
+        if constexpr (PART) {
+          // ---- spikes: V = T_own^-1 [coupling block's columns], one application of the warp's reduction per column; the boundary
+          // stages' V (own: Vo, the other warp's: Vt) reach every lane through the QP's boundary slots
+          tmem_wait_st();
+          double V[9], Vo[9], Vt[9];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            double2 mc[9];
+            tmem_ld_pairs<9>(tmb, mc);
+            double rr[3] = {cpl[c], cpl[3 + c], cpl[6 + c]}, y[3], yo[3], yt[3];
+            pcr_own(mc, rr, y);
+            cm.boundary(y, yo, yt);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { V[3 * i + c] = y[i]; Vo[3 * i + c] = yo[i]; Vt[3 * i + c] = yt[i]; }
+          }
+          // x_other_boundary = S (y_other - Vt y_own),  S = (I - Vt Vo)^-1;   x_k = y_k - V_k x_other_boundary
+          double M[9], S[9];
+          mm3(Vt, Vo, M);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) M[e] = (e % 4 == 0 ? 1.0 : 0.0) - M[e];
+          {
+            const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+            const double idet = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+            S[0] = c00 * idet; S[1] = (M[2] * M[7] - M[1] * M[8]) * idet; S[2] = (M[1] * M[5] - M[2] * M[4]) * idet;
+            S[3] = c01 * idet; S[4] = (M[0] * M[8] - M[2] * M[6]) * idet; S[5] = (M[2] * M[3] - M[0] * M[5]) * idet;
+            S[6] = c02 * idet; S[7] = (M[1] * M[6] - M[0] * M[7]) * idet; S[8] = (M[0] * M[4] - M[1] * M[3]) * idet;
+          }
+          double wt[9], wo[9];
+          mm3(V, S, wt);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) wt[e] = -wt[e];   // WT = -V S      (multiplies y_other)
+          mm3(wt, Vt, wo);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) wo[e] = -wo[e];   // WO = -WT Vt    (multiplies y_own)
+          const double w18[18] = {wt[0], wt[1], wt[2], wt[3], wt[4], wt[5], wt[6], wt[7], wt[8],
+                                  wo[0], wo[1], wo[2], wo[3], wo[4], wo[5], wo[6], wo[7], wo[8]};
+#pragma unroll
+          for (int q = 0; q < 9; ++q) tmem_st_pair(tmb + 4 * (W_PAIR + q), w18[2 * q], w18[2 * q + 1]);
         }
       }
       if constexpr (TM) tmem_wait_st();   // the iteration below reads the strip back

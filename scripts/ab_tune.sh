@@ -4,15 +4,8 @@ cd "$(dirname "$0")/.."
 out=gpurun_out/ab_tune.txt; mkdir -p gpurun_out; : > $out
 run() { echo "## $*" >> $out; env "$@" python scripts/tune.py 2>&1 | tail -1 >> $out; }
 cur=$PWD/f110-mpc_b200/libf110mpc_b200.so
-for lib in f110-mpc_b200/tune_libs/*.so f110-mpc_b200/libf110mpc_b200.so; do
-  run F110_LIB=$PWD/$lib
-  run F110_LIB=$PWD/$lib TUNE_B=1024
-done
 for lib in $PWD/f110-mpc_b200/tune_libs/base.so $cur; do
-  run F110_LIB=$lib TUNE_N=10
-  run F110_LIB=$lib TUNE_N=50
-  run F110_LIB=$lib TUNE_N=100
-  run F110_LIB=$lib TUNE_N=30 TUNE_RATE=0.032
-  run F110_LIB=$lib TUNE_N=50 TUNE_RATE=0.032
+  for n in 32 40 50 63; do run F110_LIB=$lib TUNE_N=$n; done
+  run F110_LIB=$lib
 done
 cat $out
