@@ -345,8 +345,9 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         psum = actu ? pu : (act ? ps : 0.0);
         qn = actu ? dmax(qs, qv) : (act ? qs : 0.0);
       }
-      const double mean = cm.rsum(psum) * inv_nvar;
-      const double qinf = limit_scaling(c * cm.rmax(qn));
+      cm.template reduce<1, 1>(&qn, &psum);
+      const double mean = psum * inv_nvar;
+      const double qinf = limit_scaling(c * qn);
       const double ct = limit_scaling(dmax(mean, qinf));
       c *= rcp_pos(ct);
     }
@@ -396,8 +397,12 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
       for (int j = 0; j < 2; ++j) { a = dmax(a, fabs(qu[j])); b = dmax(b, fabs(du[j] * qu[j])); }
     }
-    scr[SCR_NQ * T] = cm.rmax(a);
-    scr[SCR_SNQ * T] = c * cm.rmax(b);
+    {
+      double ab[2] = {a, b};
+      cm.template reduce<2, 0>(ab, nullptr);
+      scr[SCR_NQ * T] = ab[0];
+      scr[SCR_SNQ * T] = c * ab[1];
+    }
   }
 
   // ---------------- iterates: cold start or the slot's stored (scaled) iterates -----------------------------
@@ -1428,13 +1433,23 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           q_pri = dmax(q_pri, erv * rr); q_z = dmax(q_z, erv * zz); q_Ax = dmax(q_Ax, erv * aa);
         }
       }
-      poisoned = cm.any(poisoned);
-      pri_res = cm.rmax(m_pri); n_z = cm.rmax(m_z); n_Ax = cm.rmax(m_Ax);
-      if (poisoned) pri_res = 2.0 * OSQP_INFTY;
-      dua_res = cm.rmax(m_dua); n_Aty = cm.rmax(m_Aty); n_Px = cm.rmax(m_Px);
-      s_pri = cm.rmax(q_pri); s_z = cm.rmax(q_z); s_Ax = cm.rmax(q_Ax);
-      s_dua = c * cm.rmax(q_dua); s_Aty = c * cm.rmax(q_Aty); s_Px = c * cm.rmax(q_Px);
-      obj = cm.rsum(o);
+      if constexpr (WPQ == 1) {
+        poisoned = cm.any(poisoned);
+        pri_res = cm.rmax(m_pri); n_z = cm.rmax(m_z); n_Ax = cm.rmax(m_Ax);
+        if (poisoned) pri_res = 2.0 * OSQP_INFTY;
+        dua_res = cm.rmax(m_dua); n_Aty = cm.rmax(m_Aty); n_Px = cm.rmax(m_Px);
+        s_pri = cm.rmax(q_pri); s_z = cm.rmax(q_z); s_Ax = cm.rmax(q_Ax);
+        s_dua = c * cm.rmax(q_dua); s_Aty = c * cm.rmax(q_Aty); s_Px = c * cm.rmax(q_Px);
+        obj = cm.rsum(o);
+      } else {   // a QP on several warps: all thirteen maxima (the NaN flag among them) and the sum in one exchange, one barrier
+        double mv[13] = {m_pri, m_z, m_Ax, m_dua, m_Aty, m_Px, q_pri, q_z, q_Ax, q_dua, q_Aty, q_Px, poisoned ? 1.0 : 0.0};
+        cm.template reduce<13, 1>(mv, &o);
+        pri_res = mv[12] != 0.0 ? 2.0 * OSQP_INFTY : mv[0]; n_z = mv[1]; n_Ax = mv[2];
+        dua_res = mv[3]; n_Aty = mv[4]; n_Px = mv[5];
+        s_pri = mv[6]; s_z = mv[7]; s_Ax = mv[8];
+        s_dua = c * mv[9]; s_Aty = c * mv[10]; s_Px = c * mv[11];
+        obj = o;
+      }
     }
 
     // ---------- termination (OSQP check_termination, exact then — on the last iteration — approximate) ---------
@@ -1499,8 +1514,9 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
             mx = dmax(mx, dmax(fabs(dyg[r]), fabs(dyb[r])));
             lhs += s.gl[r] * dmin(dyg[r], 0.0) + p.u_max[r] * dmax(dyb[r], 0.0) + p.u_min[r] * dmin(dyb[r], 0.0);
           }
-          const double ndy = cm.rmax(mx);  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
-          const double lhs_all = cm.rsum(lhs);
+          cm.template reduce<1, 1>(&mx, &lhs);
+          const double ndy = mx;  // unscaled ||dy||; OSQP's scaled-back norm is c * ndy
+          const double lhs_all = lhs;
           if (c * ndy > epi && lhs_all < -epi * ndy) {
             double dn[3], t3[3], t2[2];
             [[maybe_unused]] double dyrn = 0.0;
@@ -1540,8 +1556,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
 #pragma unroll
             for (int j = 0; j < 2; ++j) { mx = dmax(mx, fabs(ddu[j])); qd += qu[j] * ddu[j]; mp = dmax(mp, fabs(p.R[j] * ddu[j])); }
           }
-          const double ndx = cm.rmax(mx);
-          const double qd_all = cm.rsum(qd), mp_all = cm.rmax(mp);
+          double nm[2] = {mx, mp};
+          cm.template reduce<2, 1>(nm, &qd);
+          const double ndx = nm[0];
+          const double qd_all = qd, mp_all = nm[1];
           if (ndx > edi && qd_all < -edi * ndx && mp_all < edi * ndx) {
             double ax[3], pred[3];
             A_mul(md, ddx, ax);
