@@ -1162,7 +1162,7 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           else cm.template both<9>(v, lo, hi, h);
         };
         // parallel cyclic reduction; multipliers alpha, gamma go to tensor memory / shared memory
-#pragma unroll 1
+#pragma unroll 1   // (two levels per trip measured: 0.223 vs 0.221 ms per 4096 N=30 QPs)
         for (int lev = 0; lev < NLEVP; ++lev) {
           const int h = 1 << lev;
           const bool vlo = act && (kq - h >= 0);
