@@ -27,7 +27,7 @@ cudaError_t launch_admm(const KParams& p, cudaStream_t stream, int* launches) {
     return launch_admm_w1s(p, stream, nlev);
   }
   if (p.rate_rows) {
-    // the 4x4 multipliers of a 4-warp QP do not fit in one SM's shared memory: horizons above 63 are refused at create
+    // (horizons above 63 are refused at create: the 4x4 multipliers of a four-warp QP fit neither the strip nor the shared memory)
     if (nlev >= 1 && nlev <= 5) return launch_admm_w1r(p, stream, nlev);
     if (nlev == 6) return launch_admm_w2r(p, stream);
     return cudaErrorInvalidValue;

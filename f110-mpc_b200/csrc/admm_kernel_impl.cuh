@@ -16,11 +16,14 @@
 //    every lane busy at every level.  The PCR multipliers are computed once per rho (factor step) and kept
 //    on chip (negated, in 16-byte pairs); each iteration only applies them to the right-hand side as FMA
 //    chains.  The top level is one-sided (partner = stage k XOR h) and stores a single 3x3 block.
-//  * Where the multipliers live: in TENSOR MEMORY for horizons 16..127 of the base row set and 16..31 with
+//  * Where the multipliers live: in TENSOR MEMORY for horizons 16..127 of the base row set and 16..63 with
 //    steering-rate rows (TM = true: tcgen05.st in the factor step, tcgen05.ld one PCR level ahead of its use in
 //    the iteration; each lane reads back exactly what it wrote, so the warp's 32-row strip is private storage
 //    with its own datapath), in shared memory otherwise.  The round-1 kernel was bound by the shared-memory /
 //    shuffle data pipe; see admm_device.cuh and DESIGN.md section 3.1.
+//  * A QP on two warps (horizons 32..63, base row set) is solved in two partitions: each warp reduces its own
+//    32 stages with shuffles, the block that couples stage 31 to stage 32 enters as a spike correction from
+//    one boundary exchange per iteration (PART below) — one barrier instead of six for the reduction.
 //  * The parameter record is staged into shared memory by one bulk asynchronous copy (TMA, cp.async.bulk +
 //    mbarrier) when it is 16-byte aligned; the Ruiz passes do not wait for anything but that one transfer.
 //  * x/z/y update, projection onto [l,u], residual norms and the termination test are fused in the same
@@ -1691,10 +1694,12 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   if (w == 0) tmem_free(tmem_base, TM_COLS);
 }
 
-// Tensor-memory variant for multi-warp QPs (horizons 32..127, base row set): a CTA of four warps holds 4 / WPQ QPs (two two-warp QPs
-// side by side, or one four-warp QP), allocates 256 tensor-memory columns and keeps every PCR multiplier of its QPs there — the
+// Tensor-memory variant for multi-warp QPs (horizons 32..127 of the base row set, 32..63 with steering-rate rows): a CTA of four
+// warps holds 4 / WPQ QPs (two two-warp QPs side by side, or one four-warp QP), allocates 256 tensor-memory columns and keeps the PCR
+// multipliers of its QPs there (all of them for the base row set, four of five two-sided levels with steering-rate rows) — the
 // shared-memory kernels of these horizons were bound by the multiplier loads (LSU data pipe 73-78 % busy).  Two QPs of one CTA
-// synchronise on their own hardware barriers (bar.sync 1 + q, 64).  The scratch line lives in shared memory.
+// synchronise on their own hardware barriers (bar.sync 1 + q, 64).  The scratch line lives in shared memory (base row set) or in
+// global memory (steering-rate rows).
 template <int NLEV, int WPQ, bool LASTFULL, bool RATE = false>
 __global__ void __launch_bounds__(128, 2) admm_kernel_tmw(const KParams p) {
   extern __shared__ __align__(16) double smem_all[];
