@@ -222,19 +222,19 @@ struct Comm {
   static constexpr int KMAX = (WPQ == 4 || ADMM_W2_GLOBAL_LEVELS > 0) ? 5 : 9;   // values per exchange; with four warps the 9-wide ones (factor step only) go in two rounds to save shared memory
   double* xb;   // [2][KMAX][T] exchange buffers
   double* rb;   // [2][WPQ] reduction slots
-  double* bb;   // [2][2][4] boundary slots (two-warp QPs, partitioned solve)
+  double* bb;   // [2][4][4] boundary slots (partitioned solve)
   double* kb;   // [2][RK][WPQ] slots of the several-values-at-once reduction
   static constexpr int RK = 16;
   int tid, xph = 0, rph = 0, bph = 0, kph = 0;
   int bar;      // hardware barrier of this QP's T threads: 0 when the QP is the whole CTA, 1 + q when several QPs share a CTA
   __device__ __forceinline__ Comm(double* smem, int t, int bar_id = 0)
-      : xb(smem), rb(smem + 2 * KMAX * T), bb(smem + 2 * KMAX * T + 2 * WPQ), kb(smem + 2 * KMAX * T + 2 * WPQ + 16), tid(t), bar(bar_id) {}
+      : xb(smem), rb(smem + 2 * KMAX * T), bb(smem + 2 * KMAX * T + 2 * WPQ), kb(smem + 2 * KMAX * T + 2 * WPQ + 32), tid(t), bar(bar_id) {}
   __device__ __forceinline__ void barrier() const {   // immediate barrier numbers: a register operand would make ptxas reserve all 16
     if (bar == 0) asm volatile("bar.sync 0, %0;" ::"n"(T) : "memory");
     else if (bar == 1) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
     else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
   }
-  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ + 16 + 2 * RK * WPQ; }
+  static constexpr int doubles() { return 2 * KMAX * T + 2 * WPQ + 32 + 2 * RK * WPQ; }
   // (Measured and dropped for two-warp QPs: shifts by one as a warp shuffle + one boundary value through a slot guarded by a one-way
   //  hardware barrier — bar.arrive by the producing warp, bar.sync by the consuming one.  Fewer stalls, but 60 more instructions per
   //  iteration: N=50 0.575 vs 0.521 ms per 4096 QPs.)
@@ -270,17 +270,21 @@ struct Comm {
       sm[j] = m;
     }
   }
-  // Two-warp QP, partitioned solve: the last stage of warp 0 (thread 31) and the first stage of warp 1 (thread 32) post a 3-vector;
-  // every thread gets its own warp's (`own`) and the other warp's (`other`).  Double-buffered like the exchanges above.
-  __device__ __forceinline__ void boundary(const double* v, double* own, double* other) {
-    static_assert(WPQ == 2, "boundary slots: two warps per QP");
-    double* b = bb + bph * 8;
+  // Partitioned solve: the two stages on either side of a partition boundary post a 3-vector; every thread gets the value of its own
+  // side (`own`) and of the other side (`other`).  LEVEL 1: warps (0, 1) — and (2, 3) of a four-warp QP — across stages 31 | 32
+  // (95 | 96); LEVEL 2 (four warps): the two pairs across stages 63 | 64.  Double-buffered like the exchanges above.
+  template <int LEVEL> __device__ __forceinline__ void boundary(const double* v, double* own, double* other) {
+    static_assert((WPQ == 2 && LEVEL == 1) || (WPQ == 4 && (LEVEL == 1 || LEVEL == 2)), "boundary slots: two or four warps per QP");
+    double* b = bb + bph * 16;
     bph ^= 1;
     const int w = tid >> 5;
-    if (tid == 31 || tid == 32) { b[4 * w] = v[0]; b[4 * w + 1] = v[1]; b[4 * w + 2] = v[2]; }
+    // slot of this thread's side: LEVEL 1 -> one per warp; LEVEL 2 -> one per pair of warps
+    const int side = LEVEL == 1 ? w : (w >> 1);
+    const bool posts = LEVEL == 1 ? ((tid & 63) == 31 || (tid & 63) == 32) : (tid == 63 || tid == 64);
+    if (posts) { b[4 * side] = v[0]; b[4 * side + 1] = v[1]; b[4 * side + 2] = v[2]; }
     barrier();
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { own[i] = b[4 * w + i]; other[i] = b[4 * (w ^ 1) + i]; }
+    for (int i = 0; i < 3; ++i) { own[i] = b[4 * side + i]; other[i] = b[4 * (side ^ 1) + i]; }
   }
   template <int K> __device__ __forceinline__ double* put(const double* v) {
     static_assert(K <= KMAX, "exchange wider than the buffer");

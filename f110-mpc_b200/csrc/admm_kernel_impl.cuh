@@ -91,11 +91,14 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
   //     x_k = y_k + WT_k y_other + WO_k y_own,    y = T_own^-1 r,   y_own / y_other = y at this / the other warp's boundary stage,
   // where the per-stage 3x3 blocks WT = -V_k S, WO = -WT V_other, S = (I - V_other V_own)^-1 are formed once per factor step.
   // One exchange of six doubles (one barrier) per iteration replaces the six barrier-separated exchanges of a 64-lane reduction.
-  constexpr bool PART = TM && WPQ == 2 && !RATE;
+  // A four-warp QP nests the construction: level 1 joins warps (0, 1) and (2, 3) across stages 31 | 32 and 95 | 96, level 2 joins
+  // the two pairs across stages 63 | 64, its spikes computed with the level-1 solve — two exchanges per iteration instead of seven.
+  constexpr bool PART = TM && (WPQ == 2 || WPQ == 4) && !RATE;
+  constexpr int PLEV = WPQ == 4 ? 2 : 1;   // levels of the partition
   constexpr int NLEVP = PART ? 5 : NLEV;   // levels of the reduction that is actually run
-  constexpr int SM_PAIRS = PART ? NLEVP * 9 - 1 + 9 : NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
+  constexpr int SM_PAIRS = PART ? NLEVP * 9 - 1 + 9 * PLEV : NLEV * 9 - 1 - (GL >= 1 ? 5 : 0) - (GL == 2 ? 9 : 0);
   constexpr int FINAL_PAIR = PART ? NLEVP * 9 - 4 : SM_PAIRS - 3;
-  constexpr int W_PAIR = NLEVP * 9 - 1;   // (PART) the nine pairs of WT, WO
+  constexpr int W_PAIR = NLEVP * 9 - 1;   // (PART) the nine pairs of WT, WO of level 1; level 2's follow
   static_assert(!TM || RATE || 4 * SM_PAIRS <= TM_COLS, "multipliers exceed the warp's tensor-memory strip");
   // Steering-rate rows + tensor memory: the 16 pairs of each of the first TML two-sided levels live in the strip (4 x 16 pairs = all
   // 256 columns; NLEV = 5 has four such levels, NLEV = 6 five); what is left — a fifth two-sided level, the one-sided top level
@@ -624,6 +627,26 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     }
   };
 
+  // ---------- (partitioned solve) spike correction of one partition level: y += WT y_other + WO y_own, the two boundary values from
+  // one exchange through the QP's boundary slots; WT, WO from the strip ---
+  [[maybe_unused]] auto spike_correct = [&](auto level_c, double (&y)[3]) {
+    if constexpr (PART) {
+      constexpr int LEVEL = decltype(level_c)::value;
+      double2 wv[9];
+      tmem_ld_pairs<9>(tmb + 4 * (W_PAIR + 9 * (LEVEL - 1)), wv);
+      double yo[3], yt[3];
+      cm.template boundary<LEVEL>(y, yo, yt);
+      tmem_wait_ld();
+      tmem_tie<9>(wv);
+      const double wt[9] = {wv[0].x, wv[0].y, wv[1].x, wv[1].y, wv[2].x, wv[2].y, wv[3].x, wv[3].y, wv[4].x};
+      const double wo[9] = {wv[4].y, wv[5].x, wv[5].y, wv[6].x, wv[6].y, wv[7].x, wv[7].y, wv[8].x, wv[8].y};
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        y[i] = fma(wo[3 * i + 2], yo[2], fma(wt[3 * i + 2], yt[2], fma(wo[3 * i + 1], yo[1], fma(wt[3 * i + 1], yt[1],
+               fma(wo[3 * i], yo[0], fma(wt[3 * i], yt[0], y[i]))))));
+    }
+  };
+
   auto iterate = [&](auto first_c) {
     constexpr bool FIRST = decltype(first_c)::value;
       // tensor-memory variant: the multipliers are fetched one PCR level ahead of their use; level 0 flies during the rhs assembly
@@ -774,18 +797,10 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           // own-block solve, then the spike correction from the two boundary values (posted in the QP's exchange slots)
           double y[3];
           pcr_own(mc, r, y);
-          double2 wv[9];
-          tmem_ld_pairs<9>(tmb + 4 * W_PAIR, wv);
-          double yo[3], yt[3];
-          cm.boundary(y, yo, yt);
-          tmem_wait_ld();
-          tmem_tie<9>(wv);
-          const double wt[9] = {wv[0].x, wv[0].y, wv[1].x, wv[1].y, wv[2].x, wv[2].y, wv[3].x, wv[3].y, wv[4].x};
-          const double wo[9] = {wv[4].y, wv[5].x, wv[5].y, wv[6].x, wv[6].y, wv[7].x, wv[7].y, wv[8].x, wv[8].y};
+          spike_correct(std::integral_constant<int, 1>{}, y);
+          if constexpr (PLEV == 2) spike_correct(std::integral_constant<int, 2>{}, y);
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
-            xt[i] = fma(wo[3 * i + 2], yo[2], fma(wt[3 * i + 2], yt[2], fma(wo[3 * i + 1], yo[1], fma(wt[3 * i + 1], yt[1],
-                    fma(wo[3 * i], yo[0], fma(wt[3 * i], yt[0], y[i]))))));
+          for (int i = 0; i < 3; ++i) xt[i] = y[i];
         } else {
         // PCR: apply the stored multipliers level by level (fully unrolled, constant offsets)
         if constexpr (TM) { tmem_wait_ld(); tmem_tie<9>(mc); }
@@ -1150,13 +1165,16 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
         }
         // (partitioned solve) the block that couples the two warps leaves the reduction and becomes the spike's right-hand side:
         // U_31 on stage 31, L_32 on stage 32
-        [[maybe_unused]] double cpl[9];
+        // (four-warp QP: level 1 couples stages 31 | 32 and 95 | 96, level 2 stages 63 | 64)
+        [[maybe_unused]] double cpl[9], cpl2[9];
         if constexpr (PART) {
+          const int t64 = tid & 63;
 #pragma unroll
           for (int e = 0; e < 9; ++e) {
-            cpl[e] = (tid == 31) ? Um[e] : ((tid == 32) ? Lm[e] : 0.0);
-            Um[e] = (tid == 31) ? 0.0 : Um[e];
-            Lm[e] = (tid == 32) ? 0.0 : Lm[e];
+            cpl[e] = (t64 == 31) ? Um[e] : ((t64 == 32) ? Lm[e] : 0.0);
+            cpl2[e] = (PLEV == 2 && tid == 63) ? Um[e] : ((PLEV == 2 && tid == 64) ? Lm[e] : 0.0);
+            Um[e] = ((tid & 31) == 31) ? 0.0 : Um[e];
+            Lm[e] = ((tid & 31) == 0) ? 0.0 : Lm[e];
           }
         }
         const int kq = PART ? (tid & 31) : k;   // stage index inside the system that is reduced
@@ -1257,43 +1275,49 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
           }
         }
         if constexpr (PART) {
-          // ---- spikes: V = T_own^-1 [coupling block's columns], one application of the warp's reduction per column; the boundary
-          // stages' V (own: Vo, the other warp's: Vt) reach every lane through the QP's boundary slots
-          tmem_wait_st();
-          double V[9], Vo[9], Vt[9];
+          // ---- spikes of one level: V = (solve below this level) [coupling block's columns], one application per column; the
+          // boundary stages' V (own: Vo, the other side's: Vt) reach every lane through the QP's boundary slots
+          auto spikes = [&](auto level_c, const double* cp) {
+            constexpr int LEVEL = decltype(level_c)::value;
+            tmem_wait_st();
+            double V[9], Vo[9], Vt[9];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            double2 mc[9];
-            tmem_ld_pairs<9>(tmb, mc);
-            double rr[3] = {cpl[c], cpl[3 + c], cpl[6 + c]}, y[3], yo[3], yt[3];
-            pcr_own(mc, rr, y);
-            cm.boundary(y, yo, yt);
+            for (int c = 0; c < 3; ++c) {
+              double2 mc[9];
+              tmem_ld_pairs<9>(tmb, mc);
+              double rr[3] = {cp[c], cp[3 + c], cp[6 + c]}, y[3], yo[3], yt[3];
+              pcr_own(mc, rr, y);
+              if constexpr (LEVEL == 2) spike_correct(std::integral_constant<int, 1>{}, y);
+              cm.template boundary<LEVEL>(y, yo, yt);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { V[3 * i + c] = y[i]; Vo[3 * i + c] = yo[i]; Vt[3 * i + c] = yt[i]; }
-          }
-          // x_other_boundary = S (y_other - Vt y_own),  S = (I - Vt Vo)^-1;   x_k = y_k - V_k x_other_boundary
-          double M[9], S[9];
-          mm3(Vt, Vo, M);
+              for (int i = 0; i < 3; ++i) { V[3 * i + c] = y[i]; Vo[3 * i + c] = yo[i]; Vt[3 * i + c] = yt[i]; }
+            }
+            // x_other_boundary = S (y_other - Vt y_own),  S = (I - Vt Vo)^-1;   x_k = y_k - V_k x_other_boundary
+            double M[9], S[9];
+            mm3(Vt, Vo, M);
 #pragma unroll
-          for (int e = 0; e < 9; ++e) M[e] = (e % 4 == 0 ? 1.0 : 0.0) - M[e];
-          {
-            const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
-            const double idet = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
-            S[0] = c00 * idet; S[1] = (M[2] * M[7] - M[1] * M[8]) * idet; S[2] = (M[1] * M[5] - M[2] * M[4]) * idet;
-            S[3] = c01 * idet; S[4] = (M[0] * M[8] - M[2] * M[6]) * idet; S[5] = (M[2] * M[3] - M[0] * M[5]) * idet;
-            S[6] = c02 * idet; S[7] = (M[1] * M[6] - M[0] * M[7]) * idet; S[8] = (M[0] * M[4] - M[1] * M[3]) * idet;
-          }
-          double wt[9], wo[9];
-          mm3(V, S, wt);
+            for (int e = 0; e < 9; ++e) M[e] = (e % 4 == 0 ? 1.0 : 0.0) - M[e];
+            {
+              const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+              const double idet = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+              S[0] = c00 * idet; S[1] = (M[2] * M[7] - M[1] * M[8]) * idet; S[2] = (M[1] * M[5] - M[2] * M[4]) * idet;
+              S[3] = c01 * idet; S[4] = (M[0] * M[8] - M[2] * M[6]) * idet; S[5] = (M[2] * M[3] - M[0] * M[5]) * idet;
+              S[6] = c02 * idet; S[7] = (M[1] * M[6] - M[0] * M[7]) * idet; S[8] = (M[0] * M[4] - M[1] * M[3]) * idet;
+            }
+            double wt[9], wo[9];
+            mm3(V, S, wt);
 #pragma unroll
-          for (int e = 0; e < 9; ++e) wt[e] = -wt[e];   // WT = -V S      (multiplies y_other)
-          mm3(wt, Vt, wo);
+            for (int e = 0; e < 9; ++e) wt[e] = -wt[e];   // WT = -V S      (multiplies y_other)
+            mm3(wt, Vt, wo);
 #pragma unroll
-          for (int e = 0; e < 9; ++e) wo[e] = -wo[e];   // WO = -WT Vt    (multiplies y_own)
-          const double w18[18] = {wt[0], wt[1], wt[2], wt[3], wt[4], wt[5], wt[6], wt[7], wt[8],
-                                  wo[0], wo[1], wo[2], wo[3], wo[4], wo[5], wo[6], wo[7], wo[8]};
+            for (int e = 0; e < 9; ++e) wo[e] = -wo[e];   // WO = -WT Vt    (multiplies y_own)
+            const double w18[18] = {wt[0], wt[1], wt[2], wt[3], wt[4], wt[5], wt[6], wt[7], wt[8],
+                                    wo[0], wo[1], wo[2], wo[3], wo[4], wo[5], wo[6], wo[7], wo[8]};
 #pragma unroll
-          for (int q = 0; q < 9; ++q) tmem_st_pair(tmb + 4 * (W_PAIR + q), w18[2 * q], w18[2 * q + 1]);
+            for (int q = 0; q < 9; ++q) tmem_st_pair(tmb + 4 * (W_PAIR + 9 * (LEVEL - 1) + q), w18[2 * q], w18[2 * q + 1]);
+          };
+          spikes(std::integral_constant<int, 1>{}, cpl);
+          if constexpr (PLEV == 2) spikes(std::integral_constant<int, 2>{}, cpl2);   // (its solves use level 1's WT, WO: stored and waited for)
         }
       }
       if constexpr (TM) tmem_wait_st();   // the iteration below reads the strip back
