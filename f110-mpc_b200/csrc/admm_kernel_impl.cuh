@@ -21,9 +21,10 @@
 //    the iteration; each lane reads back exactly what it wrote, so the warp's 32-row strip is private storage
 //    with its own datapath), in shared memory otherwise.  The round-1 kernel was bound by the shared-memory /
 //    shuffle data pipe; see admm_device.cuh and DESIGN.md section 3.1.
-//  * A QP on two warps (horizons 32..63, base row set) is solved in two partitions: each warp reduces its own
-//    32 stages with shuffles, the block that couples stage 31 to stage 32 enters as a spike correction from
-//    one boundary exchange per iteration (PART below) — one barrier instead of six for the reduction.
+//  * A QP on two or four warps (horizons 32..127, base row set) is solved in partitions: each warp reduces its
+//    own 32 stages with shuffles, the blocks that couple neighbouring warps enter as spike corrections from one
+//    boundary exchange per partition level and iteration (PART below) — one or two barriers instead of six or
+//    seven for the reduction.
 //  * The parameter record is staged into shared memory by one bulk asynchronous copy (TMA, cp.async.bulk +
 //    mbarrier) when it is 16-byte aligned; the Ruiz passes do not wait for anything but that one transfer.
 //  * x/z/y update, projection onto [l,u], residual norms and the termination test are fused in the same

@@ -9,6 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${P}_cycle_launches.csv python scripts/cycle_profile.py > $O/${P}_ncu_cycle.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:admm_kernel_tm -s 3 -c 1 -f -o $O/${P}_prof_n30 python scripts/tune.py > $O/${P}_ncu_n30.log 2>&1
 TUNE_N=50 ncu --set full --clock-control none --import-source on -k regex:admm_kernel_tmw -s 3 -c 1 -f -o $O/${P}_prof_n50 python scripts/tune.py > $O/${P}_ncu_n50.log 2>&1
+TUNE_N=100 ncu --set full --clock-control none --import-source on -k regex:admm_kernel_tmw -s 3 -c 1 -f -o $O/${P}_prof_n100 python scripts/tune.py > $O/${P}_ncu_n100.log 2>&1
 TUNE_N=50 TUNE_RATE=0.032 ncu --set full --clock-control none --import-source on -k regex:admm_kernel_tmw -s 3 -c 1 -f -o $O/${P}_prof_rate50 python scripts/tune.py > $O/${P}_ncu_rate50.log 2>&1
 python bench.py --configs --configs-out $O/${P}_configs_report.json > $O/${P}_configs.log 2>&1
 ls -la $O | tail -20
