@@ -54,6 +54,10 @@ struct KParams {
   double* mult_global;  // [B][28 * 128] top-level PCR multipliers of multi-warp QPs (horizon >= 32; used from 64 up), else null
   double* scratch_dummy;  // 4 more lines: lane groups without a QP (several short-horizon QPs per warp, odd batch) scribble here
   int* work;              // tensor-memory variant: {next QP, warps run dry}, both 0 at launch; the kernel re-arms them itself
+  // single-QP latency path (f110_mpc_solve_host, one QP): results go straight to mapped pinned host memory; the last warp of the
+  // persistent kernel then raises this flag (mapped host memory too) to done_seq, after a system-wide fence.  Null otherwise.
+  int32_t* done_flag;
+  int32_t done_seq;
 };
 
 // constraint rows: dynamics 3(N+1) | gap pairs 2(N+1) | input box 2N | steering rate N (optional) | state box 3(N+1) (optional)

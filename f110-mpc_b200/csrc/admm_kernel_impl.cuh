@@ -1709,10 +1709,19 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
     if (p.rec_bulk_bytes) parity ^= 1u;
     __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
   }
-  // the last warp to run dry re-arms the counter pair for the next launch that uses it
+  // the last warp to run dry re-arms the counter pair for the next launch that uses it — and, on the single-QP latency path, tells
+  // the host that the results (written to mapped host memory by whichever warp solved) are complete
+  if (p.done_flag) __threadfence_system();   // (every lane: its own result stores before the warp's count below)
+  __syncwarp();
   if (lane == 0) {
     const int finished = atomicAdd(p.work + 1, 1);
-    if (finished == (int)gridDim.x * 4 - 1) { p.work[0] = 0; p.work[1] = 0; }
+    if (finished == (int)gridDim.x * 4 - 1) {
+      p.work[0] = 0; p.work[1] = 0;
+      if (p.done_flag) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int32_t*>(p.done_flag) = p.done_seq;
+      }
+    }
   }
   tmem_fence_before_sync();
   __syncthreads();

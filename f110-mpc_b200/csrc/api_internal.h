@@ -81,6 +81,8 @@ struct f110_mpc_solver {
   // f110_cycle_host pipelines its scenes in chunks over two streams (copies of chunk c+1 under the kernels of chunk c)
   // single-QP latency path: the copy-in / solve / copy-out triple captured once as a CUDA graph per output shape (u0 only, +x, +x+y)
   cudaGraphExec_t lat_graph[3] = {nullptr, nullptr, nullptr};
+  int32_t* done_flag_next = nullptr;   // single-QP latency path: completion flag (device view of mapped host memory) for the NEXT solve
+  int32_t done_seq = 0;
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_tab = nullptr, ev_join = nullptr;
   // asynchronous cycles: `depth` lanes (2 by default, f110_cycle_set_depth).  Everything before a solve overlaps the previous

@@ -2,6 +2,7 @@
 // CUDA device and fails with F110_ERR_CUDA otherwise.
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <string>
 
@@ -181,6 +182,8 @@ int f110api::solve_device_range(f110_mpc_solver* s, int slot0, int count, const 
   p.recs = d_recs; p.x_out = d_x; p.y_out = d_y; p.u0_out = d_u0; p.status = d_status; p.iters = d_iters;
   p.rho_updates = d_rho_updates; p.info = d_info; p.packed = s->d_packed_next;
   s->d_packed_next = nullptr;
+  p.done_flag = s->done_flag_next; p.done_seq = s->done_seq;
+  s->done_flag_next = nullptr;
   const int T = s->cfg.horizon < 32 ? 32 : (s->cfg.horizon < 64 ? 64 : 128);   // threads (stage slots) per QP
   p.state = s->st.warm_start ? s->d_state + (size_t)slot0 * f110::state_doubles(s->cfg.horizon, s->cfg.rate_rows, s->cfg.state_rows) : nullptr;
   p.scratch = s->d_scratch + (size_t)slot0 * f110::SCR_ROWS_ALLOC * T;
@@ -224,7 +227,8 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
     s->out_bytes = B * (2 * sizeof(double) + 2 * sizeof(int32_t)) + 16 + B * (size_t)(n + m) * sizeof(double);
     CUDA_TRY(cudaMalloc(&s->d_recs, B * rdp * sizeof(double)));
     CUDA_TRY(cudaMalloc(&s->d_out, s->out_bytes));
-    CUDA_TRY(cudaHostAlloc(&s->h_pin, kSmallBatch * (size_t)(rdp + 2 + 1 + n + m) * sizeof(double) + 64, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_pin, kSmallBatch * (size_t)(rdp + 2 + 1 + n + m) * sizeof(double) + 64, cudaHostAllocMapped));   // (+64: completion flag of the single-QP path)
+    std::memset(s->h_pin + kSmallBatch * (size_t)(rdp + 2 + 1 + n + m) * sizeof(double), 0, 64);
   }
   const bool small = count <= kSmallBatch;
   // small batches use a compact layout sized for kSmallBatch so the whole result is ONE device-to-host copy
@@ -240,6 +244,42 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
     // latency path: records staged through pinned memory (true async DMA)
     double* hp = reinterpret_cast<double*>(s->h_pin);
     for (int b = 0; b < count; ++b) std::memcpy(hp + (size_t)b * rdp, recs + (size_t)b * rec_stride, rd * sizeof(double));
+    // One QP at horizons 16..31 (the reference's own call pattern and horizon, mpc.cpp:69-143): no copy at all.  The kernel stages
+    // the record from the pinned buffer itself (its TMA bulk copy reads mapped host memory), writes the results into the pinned
+    // buffer and raises a flag there; the host polls the flag instead of waiting on the stream.  One kernel launch is the whole
+    // call.  F110_LATENCY_PATH=graph selects the captured copy-in / solve / copy-out graph below instead (A/B measurements).
+    static const bool direct_ok = [] { const char* e = std::getenv("F110_LATENCY_PATH"); return !(e && e[0] == 'g'); }();
+    if (direct_ok && count == 1 && !s->cfg.rate_rows && !s->cfg.state_rows && N >= 16 && N <= 31 && !s->d_packed_next) {
+      unsigned char* ho = s->h_pin + (size_t)kSmallBatch * rdp * sizeof(double);
+      volatile int32_t* flag = reinterpret_cast<volatile int32_t*>(s->h_pin + kSmallBatch * (size_t)(rdp + 2 + 1 + n + m) * sizeof(double));
+      unsigned char* pin_d = nullptr;   // device view of the pinned block
+      CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pin_d), s->h_pin, 0));
+      unsigned char* ho_d = pin_d + (ho - s->h_pin);
+      const int32_t seq = ++s->done_seq;
+      s->done_flag_next = reinterpret_cast<int32_t*>(pin_d + (reinterpret_cast<volatile unsigned char*>(flag) - s->h_pin));
+      s->last_launches = 0;
+      const int rc1 = f110api::solve_device_range(s, 0, 1, reinterpret_cast<const double*>(pin_d), rdp, x ? reinterpret_cast<double*>(ho_d + o_x) : nullptr,
+                                                  y ? reinterpret_cast<double*>(ho_d + o_y) : nullptr, reinterpret_cast<double*>(ho_d),
+                                                  reinterpret_cast<int32_t*>(ho_d + o_status), reinterpret_cast<int32_t*>(ho_d + o_iters), nullptr,
+                                                  nullptr, s->stream);
+      if (rc1) return rc1;
+      // poll the flag; every so often ask the stream as well, so that a failed launch or a kernel without the flag (F110_NO_TMEM)
+      // still ends the wait
+      for (unsigned spins = 0; *flag != seq; ++spins) {
+        if ((spins & 1023u) == 1023u) {
+          const cudaError_t q = cudaStreamQuery(s->stream);
+          if (q == cudaSuccess) break;
+          if (q != cudaErrorNotReady) return cuda_fail(q, "f110_mpc_solve_host: single-QP solve");
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      if (u0) std::memcpy(u0, ho, 2 * sizeof(double));
+      if (status) std::memcpy(status, ho + o_status, sizeof(int32_t));
+      if (iters) std::memcpy(iters, ho + o_iters, sizeof(int32_t));
+      if (x) std::memcpy(x, ho + o_x, (size_t)n * sizeof(double));
+      if (y) std::memcpy(y, ho + o_y, (size_t)m * sizeof(double));
+      return F110_OK;
+    }
     if (count == 1 && !s->cfg.rate_rows && !s->cfg.state_rows && N <= 31 && !s->d_packed_next) {   // (longer horizons set a function attribute at launch: not captured;
                                                                           //  a packed-output request is per call and must not be frozen into the graph)
       // one QP (the reference's own call pattern, mpc.cpp:69-143): copy-in, solve and copy-out are replayed as one captured graph,
