@@ -1695,33 +1695,36 @@ __global__ void __launch_bounds__(128, 2) admm_kernel_tm(const KParams p) {
   double* const smem_w = smem_all + (size_t)w * (tm_warp_head<RATE>() + p.rec_bulk_bytes / 8 + 2);
   if (p.rec_bulk_bytes && lane == 0) mbar_init(smem_u32(smem_w + p.rec_smem_offset + p.rec_bulk_bytes / 8), 1);
   __syncwarp();
-  // QPs are claimed one at a time, when the warp is free to solve them.  (Claiming the next QP while the current one is being
-  // solved — to have its record in flight early — was measured: the one-QP lookahead costs more in load balance at the batch's
-  // tail than the hidden atomic + record latency gains, 0.230 vs 0.227 ms per 4096 QPs, and far more on batches under two QPs
-  // per warp.)
+  // A batch that fits the resident warps needs no work queue: warp i of the grid solves QP i, without the atomic round trip in front
+  // of the solve (about 2 us of a lone QP's 50), and the counter pair stays zero.  Larger batches: QPs are claimed one at a time,
+  // when the warp is free to solve them.  (Claiming the next QP while the current one is being solved — to have its record in flight
+  // early — was measured: the one-QP lookahead costs more in load balance at the batch's tail than the hidden atomic + record
+  // latency gains, 0.230 vs 0.227 ms per 4096 QPs, and far more on batches under two QPs per warp.)
+  const bool queue = p.B > (int)gridDim.x * 4;
+  int unit = (int)blockIdx.x * 4 + w;
   uint32_t parity = 0;
   for (;;) {
-    int unit = 0;
-    if (lane == 0) unit = atomicAdd(p.work, 1);
-    unit = __shfl_sync(FULL, unit, 0);
+    if (queue) {
+      if (lane == 0) unit = atomicAdd(p.work, 1);
+      unit = __shfl_sync(FULL, unit, 0);
+    }
     if (unit >= p.B) break;
     solve_unit<NLEV, 1, LASTFULL, RATE, 1, true>(p, unit, smem_w, tmb, lane, parity);
+    if (!queue) {
+      if (p.done_flag) {   // (single-QP latency path, B = 1: this warp's results are the call's results)
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int32_t*>(p.done_flag) = p.done_seq;
+      }
+      break;
+    }
     if (p.rec_bulk_bytes) parity ^= 1u;
     __syncwarp();   // every lane is done with the record and the scratch line before the next QP overwrites them
   }
-  // the last warp to run dry re-arms the counter pair for the next launch that uses it — and, on the single-QP latency path, tells
-  // the host that the results (written to mapped host memory by whichever warp solved) are complete
-  if (p.done_flag) __threadfence_system();   // (every lane: its own result stores before the warp's count below)
-  __syncwarp();
-  if (lane == 0) {
+  // the last warp to run dry re-arms the counter pair for the next launch that uses it
+  if (queue && lane == 0) {
     const int finished = atomicAdd(p.work + 1, 1);
-    if (finished == (int)gridDim.x * 4 - 1) {
-      p.work[0] = 0; p.work[1] = 0;
-      if (p.done_flag) {
-        __threadfence_system();
-        *reinterpret_cast<volatile int32_t*>(p.done_flag) = p.done_seq;
-      }
-    }
+    if (finished == (int)gridDim.x * 4 - 1) { p.work[0] = 0; p.work[1] = 0; }
   }
   tmem_fence_before_sync();
   __syncthreads();

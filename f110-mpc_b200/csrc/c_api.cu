@@ -262,7 +262,7 @@ int f110_mpc_solve_host(f110_mpc_solver* s, int count, const double* recs, int r
                                                   y ? reinterpret_cast<double*>(ho_d + o_y) : nullptr, reinterpret_cast<double*>(ho_d),
                                                   reinterpret_cast<int32_t*>(ho_d + o_status), reinterpret_cast<int32_t*>(ho_d + o_iters), nullptr,
                                                   nullptr, s->stream);
-      if (rc1) return rc1;
+      if (rc1) { s->done_flag_next = nullptr; return rc1; }
       // poll the flag; every so often ask the stream as well, so that a failed launch or a kernel without the flag (F110_NO_TMEM)
       // still ends the wait
       for (unsigned spins = 0; *flag != seq; ++spins) {
