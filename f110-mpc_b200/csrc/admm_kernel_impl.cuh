@@ -1336,22 +1336,28 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
     const bool last = (iter == p.max_iter), chk = (ct_left == 0), adp = (ar_left == 0);
     if (chk) ct_left = p.check_termination;
     if (adp) ar_left = ari;
-    for (;;) {
-      --togo;
-      if (togo == 0) {  // the infeasibility tests need delta x, delta y of this iteration
+    auto keep_previous = [&]() {   // the infeasibility tests need delta x, delta y of the trip's last iteration
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
+      for (int j = 0; j < 3; ++j) { scr[(SCR_PX + j) * T] = s.x[j]; scr[(SCR_PYD + j) * T] = s.yd[j]; }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
-        if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
-        if constexpr (SBOX) {
+      for (int j = 0; j < 2; ++j) { scr[(SCR_PU + j) * T] = s.u[j]; scr[(SCR_PYG + j) * T] = s.yg[j]; scr[(SCR_PYB + j) * T] = s.yb[j]; }
+      if constexpr (RATE) scr[SCR_PYR * T] = s.yr;
+      if constexpr (SBOX) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) scr[(SCR_PYS + j) * T] = s.ys[j];
-        }
+        for (int j = 0; j < 3; ++j) scr[(SCR_PYS + j) * T] = s.ys[j];
       }
-      if (first_iter) { iterate(std::true_type{}); first_iter = false; }
-      else iterate(std::false_type{});
-      if (togo == 0) break;
+    };
+    // (the solve's first iteration is peeled off: the loop below holds one instantiation of the iteration and nothing else)
+    if (first_iter) {
+      first_iter = false;
+      --togo;
+      if (togo == 0) keep_previous();
+      iterate(std::true_type{});
+    }
+    while (togo != 0) {
+      --togo;
+      if (togo == 0) keep_previous();
+      iterate(std::false_type{});
     }
 
     // ---------- residuals & norms (OSQP update_info + the norms of compute_rho_estimate) -----------------------
