@@ -1354,9 +1354,9 @@ __device__ __forceinline__ void solve_unit(const KParams& p, const int unit, dou
       if (togo == 0) keep_previous();
       iterate(std::true_type{});
     }
-    while (togo != 0) {
-      --togo;
-      if (togo == 0) keep_previous();
+    if (togo != 0) {   // (the trip's last iteration stands after the loop: nothing but the iteration inside it)
+      while (--togo != 0) iterate(std::false_type{});
+      keep_previous();
       iterate(std::false_type{});
     }
 
